@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py — MLUPS of the colour-gradient two-phase LBM time step on B200 (contract: see the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--prec f64|f32] [--size S] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): synthetic SxSxS random sphere pack (S=256, porosity ~0.4, radius 12), drainage,
+velocity inlet + convective outlet, contact angle 45 deg, FP64.  For N > 1 the lattice is (S*N) x S x S cut into N
+x-slabs (weak scaling), PDF/phi halos exchanged with NCCL send/recv between neighbours.
+
+One JSON line on stdout (rank 0).  `value` = MLUPS with the reference's definition nx*ny*nz*steps/1e6/s
+(/root/reference/src/main.cpp:270), state resident in HBM; `e2e` = the same through the C ABI starting from pinned
+host arrays (H2D of the full state, K steps, monitor + D2H of the full state - the post-condition the reference's
+main_iteration_kernel_GPU gives its host on timer steps, src/main_iteration_GPU.cu:2059-2076).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent
+for p in (REPO / "mf-lbm-cuda_b200", REPO / "tests"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+
+FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+# ----------------------------------------------------------------------------------------------------------
+# workload
+# ----------------------------------------------------------------------------------------------------------
+def workload_control(nx: int, ny: int, nz: int) -> dict:
+    import refcase as rc
+    ctl = dict(rc.DEFAULT_CONTROL)
+    ctl.update(nxGlobal=nx, nyGlobal=ny, nzGlobal=nz, initial_fluid_distribution_option=1, saturation_injection=1.0, theta=45,
+               initial_interface_position=8.0, inlet_BC=1, outlet_BC=1, capillary_number=1e-4, n_exclude_inlet=10, n_exclude_outlet=10,
+               fluid1_viscosity=0.04, fluid2_viscosity=0.4, surface_tension=0.03, RK_beta=0.95, body_force_0=0.0)
+    return ctl
+
+
+def workload_geometry(nx: int, ny: int, nz: int, seed: int = 20240229) -> np.ndarray:
+    """interior walls after set_walls (src/Misc.cpp:59-87): sphere pack + solid x/y faces, int8 [nz, ny, nx]"""
+    import refcase as rc
+    radius = 12.0 * min(nx, ny, nz) / 256.0 if min(nx, ny, nz) < 256 else 12.0
+    solid = rc.sphere_pack(nx, ny, nz, radius=max(radius, 3.0), porosity=0.4, buffer=max(2, round(10 * nz / 256)), seed=seed)
+    solid[:, :, 0] = 1; solid[:, :, -1] = 1; solid[:, 0, :] = 1; solid[:, -1, :] = 1
+    return solid
+
+
+def inlet_profile(ctl: dict, prec: str) -> np.ndarray:
+    """W_in of the velocity inlet (src/Init_multiphase.cpp:258-284, src/Misc.cpp:387-419), evaluated in numpy."""
+    R = np.float32 if prec == "f32" else np.float64
+    nx, ny = ctl["nxGlobal"], ctl["nyGlobal"]
+    la_x, la_y = R(nx - 2), R(ny - 2)
+    uin = R(R(ctl["capillary_number"]) * R(ctl["surface_tension"]) / R(ctl["fluid1_viscosity"]))
+    a, b = R(0.5) * la_x, R(0.5) * la_y
+    n = np.arange(1, 1000, 2).astype(R)
+    pi = R(np.pi)
+    t1 = np.sum(np.tanh(R(0.5) * n * pi * b / a) / n ** 5, dtype=R)
+    t2 = R(1.) - R(192.) / pi ** 5 * (a / b) * t1
+    t2 = R(-3.) * uin / (t2 * a ** 2)
+    W = np.zeros((ny + 2, nx + 2), dtype=R)
+    xx = (np.arange(2, nx).astype(R) - R(1.5) - a)[None, :, None]
+    yy = (np.arange(2, ny).astype(R) - R(1.5) - b)[:, None, None]
+    nn = n[None, None, :]
+    sign = np.where(((n - 1) / 2) % 2 == 0, R(1.), R(-1.))[None, None, :]
+    with np.errstate(over="ignore", under="ignore"):
+        term = sign * np.cos(R(0.5) * nn * pi * xx / a) / nn ** 3 * (
+            R(1.) - (np.exp(R(0.5) * nn * pi * (yy - b) / a) + np.exp(R(0.5) * nn * pi * (-yy - b) / a)) / (R(1.) + np.exp(R(0.5) * nn * pi * (-b - b) / a)))
+    W[2:ny, 2:nx] = term.sum(axis=2, dtype=R) * (R(-16.) * t2 * a ** 2 * pi ** -3)
+    return W
+
+
+# ----------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self) -> dict:
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------
+def hbm_peak():
+    f = REPO / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(prec: str) -> dict:
+    """the C oracle (a port: the reference has no CPU solver) on a bounded sample of the same workload"""
+    sys.path.insert(0, str(REPO / "oracle"))
+    from oracle import Oracle
+    n = 64
+    ctl = workload_control(n, n, n)
+    solid = workload_geometry(n, n, n)
+    o = Oracle(ctl, prec)
+    o.set_walls(solid)
+    o.geometry_preprocess(); o.init_new(); o.color_gradient()
+    o.run(1, 2)
+    steps, dt, nt = 0, 0.0, 3
+    while dt < 12.0:   # bounded sample: ~12 s of CPU work
+        t = time.perf_counter(); o.run(nt, 10); dt += time.perf_counter() - t
+        steps += 10; nt += 10
+    return {"value": n ** 3 * steps / 1e6 / dt, "unit": "MLUPS", "cores": int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1)),
+            "kind": "port", "sample": f"{n}^3 sphere pack, {steps} steps, C oracle with OpenMP (the reference has no CPU solver path)"}
+
+
+def run_ours(args) -> dict:
+    import torch
+    import mflbm
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from mflbm import slab as slabmod
+        return slabmod.bench_slabs(args, rank, world, local)
+    S = args.size
+    prec = args.prec
+    rt = np.float64 if prec == "f64" else np.float32
+    ctl = workload_control(S, S, S)
+    solid = workload_geometry(S, S, S)
+    stream = torch.cuda.Stream()
+    solver = mflbm.Solver(mflbm.derive_params(ctl, prec), prec, device=local, stream=stream.cuda_stream)
+    t0 = time.perf_counter()
+    solver.preprocess_geometry(solid)
+    t_geo = time.perf_counter() - t0
+    W = inlet_profile(ctl, prec)
+    solver.init_state(1, ctl["initial_interface_position"], W_in=W)
+    n_fluid, n_site = solver.num_fluid_nodes, S ** 3
+    # ---- device-resident timing -------------------------------------------------------------------
+    solver.run(1, args.warmup)
+    solver.sync()
+    l0 = solver.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nt = 1 + args.warmup
+    with ClockSampler(local) as clk:
+        torch.cuda.synchronize()
+        e0.record(stream)
+        solver.run(nt, args.steps)
+        e1.record(stream)
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = solver.kernel_launches - l0
+    nt += args.steps
+    mon = solver.monitor()
+    assert mon["nan_detected"] == 0, "simulation produced non-finite values"
+    ms_step = ms / args.steps
+    mlups = n_site * args.steps / 1e6 / (ms * 1e-3)
+    s_bytes = 8 if prec == "f64" else 4
+    bytes_step = 78 * s_bytes * n_fluid + n_site
+    peak, peak_src = hbm_peak()
+    achieved = bytes_step / (ms_step * 1e-3) / 1e9
+    traffic = None
+    tf = REPO / "profiles" / "traffic.json"
+    if tf.exists():
+        try:
+            traffic = json.loads(tf.read_text()).get(f"{prec}_{S}", None)
+        except Exception:
+            traffic = None
+    # ---- end to end through the C ABI with host buffers ---------------------------------------------
+    st = solver.download_state()
+    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in st.items()}
+    host = {k: v.numpy() for k, v in pinned.items()}
+    h2d = sum(v.nbytes for v in host.values())
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    solver.upload_state(pdf=host["pdf"], phi=host["phi"], cn_x=host["cn_x"], cn_y=host["cn_y"], cn_z=host["cn_z"], c_norm=host["c_norm"],
+                        curv=host["curv"], f_convec=host.get("f_convec"), g_convec=host.get("g_convec"), phi_convec=host.get("phi_convec"))
+    solver.run(nt, args.steps)
+    mon2 = solver.monitor()
+    lib = solver.lib
+    fn = getattr(lib, f"mflbm_{prec}_download_state")
+    ptr = lambda k: host[k].ctypes.data if k in host else None
+    rc_ = fn(solver.h, ptr("pdf"), ptr("phi"), ptr("cn_x"), ptr("cn_y"), ptr("cn_z"), ptr("c_norm"), ptr("curv"), ptr("f_convec"), ptr("g_convec"), ptr("phi_convec"))
+    assert rc_ == 0
+    t_e2e = time.perf_counter() - t0
+    e2e_mlups = n_site * args.steps / 1e6 / t_e2e
+    d2h = h2d + 11 * 8 * S
+    out = {
+        "metric": "multiphase MLUPS (all lattice sites, reference definition src/main.cpp:270)", "value": mlups, "unit": "MLUPS",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": prec, "data": "synthetic",
+        "config": {"workload": f"{S}^3 random sphere pack (radius 12, porosity ~0.4), drainage, velocity inlet + convective outlet, theta 45, {prec}",
+                   "lattice": [S, S, S], "fluid_nodes": n_fluid, "porosity": n_fluid / n_site, "parallelism": "1 GPU",
+                   "l2": f"state {h2d / 1e9:.2f} GB >> 126 MB L2 (inputs larger than L2, no flush needed)",
+                   "fluid_mlups": n_fluid * args.steps / 1e6 / (ms * 1e-3), "geometry_preprocess_s": t_geo,
+                   "saturation_full_domain": mon2["saturation_full_domain"]},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": peak_src, "bytes_model": "78*sizeof(real)*N_fluid + N_site per step (whole step, all kernels)",
+                     "bytes_per_step": bytes_step},
+        "e2e": {"value": e2e_mlups, "unit": "MLUPS", "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
+                "what": "upload_state from pinned host + K steps + monitor + download_state, through the C ABI"},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+    }
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(prec)
+    solver.close()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CUDA build (it has no CPU solver), unmodified sources, oracle/_ref/
+# ----------------------------------------------------------------------------------------------------------
+def run_reference(args) -> dict:
+    import refcase as rc
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        sys.exit(0)
+    S, prec = args.size, args.prec
+    exe = rc.ref_binary("gpu", prec)
+    base = {"impl": "reference", "metric": "multiphase MLUPS (all lattice sites, reference definition src/main.cpp:270)", "unit": "MLUPS",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": prec, "data": "synthetic"}
+    if not exe.exists():
+        base["unavailable"] = f"{exe} missing (oracle/build_ref.sh needs /root/reference)"
+        return base
+    ctl = workload_control(S, S, S)
+    solid = workload_geometry(S, S, S)
+    solid_file = solid.copy()   # the reference applies the x/y walls itself (src/Misc.cpp:67-78); harmless to pre-apply
+    with tempfile.TemporaryDirectory() as td:
+        td = Path(td)
+        rc.write_case(td, ctl, solid_file)
+        t0 = time.perf_counter()
+        out = rc.run_ref("gpu", prec, td, td / "out", time=(args.warmup, args.steps), timeout=3000)
+        wall = time.perf_counter() - t0
+        tim = dict(l.split() for l in (out / "timing.txt").read_text().splitlines())
+        host = dict(l.split() for l in (out / "host_timing.txt").read_text().splitlines())
+    mlups = float(tim["mlups"])
+    base.update({"value": mlups, "ms_per_step": float(tim["ms_per_step"]),
+                 "config": {"workload": f"{S}^3 random sphere pack (radius 12, porosity ~0.4), drainage, velocity inlet + convective outlet, theta 45, {prec}",
+                            "what": "reference CUDA kernels (unmodified sources, nvcc sm_100 -O3, block 128x1x1) via main_iteration_kernel_GPU()",
+                            "host_setup_s": float(host["initialization_basic_multi_s"]), "wall_s": wall},
+                 "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": 1, "kind": "reference",
+                                  "sample": "the reference has no CPU solver: this is its own CUDA build on 1 B200; 1 host core drives it"},
+                 "e2e": {"value": mlups, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    return base
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--prec", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        out = run_reference(args)
+    else:
+        out = run_ours(args)
+    if out is not None and int(os.environ.get("RANK", 0)) == 0:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,305 @@
+// kernels_aux.cuh — set-up and diagnostics kernels: bit-exact geometry preprocessing, initial state, monitor
+// reductions, x-slab halo pack/unpack.  Reference citations relative to /root/reference.
+#pragma once
+#include "core.cuh"
+
+namespace mflbm {
+
+// IEEE operations that the compiler must not contract into FMAs: the host reference (g++ -O3, x86-64 baseline,
+// Makefile:47-49) evaluates these stages with separately rounded multiplies and adds, and the results are
+// specified to be bit-exact.
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float sqrt_rn(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ double sqrt_rn(double a) { return __dsqrt_rn(a); }
+
+// =====================================================================================================
+// geometry preprocessing: src/Geometry_preprocessing.cpp:29-403 on the device
+// Work arrays carry G = 10 ghost layers like the reference's temporaries (:38-47).
+// =====================================================================================================
+struct GeoDims {
+    int nx, ny, nz;            // local real extents
+    int TX, TY, TZ;            // nx + 20, ...
+    int x0, nxg, nyg, nzg;     // global offset of local column 1 and global extents
+    int iper, jper, kper;
+    __device__ __forceinline__ long long t10(int x, int y, int z) const { return (x + 9) + (long long)TX * ((y + 9) + (long long)TY * (z + 9)); }
+};
+
+__device__ __forceinline__ int wrap_or_clamp(int c, int n, int per) {
+    if (per) { while (c < 1) c += n; while (c > n) c -= n; return c; }
+    return c < 1 ? 1 : (c > n ? n : c);
+}
+
+// ghost fill (:59-132): the sequential z, y, x fills of the reference compose to a per-axis clamp (non-periodic)
+// or wrap (periodic) of the source coordinate.  Writes the int flags and both float copies (:144-151).
+template <typename T>
+__global__ void k_geo_fill(GeoDims D, const int8_t* __restrict__ interior_global, int8_t* __restrict__ wt, T* __restrict__ ws1, T* __restrict__ ws2) {
+    const int x = -9 + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int y = -9 + (int)blockIdx.y, z = -9 + (int)blockIdx.z;
+    if (x > D.nx + 10) return;
+    const int gx = wrap_or_clamp(x + D.x0 - 1, D.nxg, D.iper);
+    const int gy = wrap_or_clamp(y, D.nyg, D.jper), gz = wrap_or_clamp(z, D.nzg, D.kper);
+    const int8_t v = interior_global[(gx - 1) + (long long)D.nxg * ((gy - 1) + (long long)D.nyg * (gz - 1))];
+    const long long n = D.t10(x, y, z);
+    wt[n] = v; ws1[n] = (T)v; ws2[n] = (T)v;
+}
+
+// node classification (:154-175): solid with a fluid D3Q18 neighbour -> 2, fluid with a solid neighbour -> -1.
+// The reference updates in place; the tests it applies (<= 0, >= 1) do not distinguish updated from original
+// values, so an out-of-place pass is identical.
+__global__ void k_geo_classify(GeoDims D, const int8_t* __restrict__ wt, int8_t* __restrict__ type) {
+    const int x = -8 + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int y = -8 + (int)blockIdx.y, z = -8 + (int)blockIdx.z;
+    if (x > D.nx + 9) return;
+    const long long n = D.t10(x, y, z);
+    const int8_t me = wt[n];
+    int8_t out = me;
+    bool hit = false;
+#pragma unroll
+    for (int q = 1; q < 19; q++) {
+        const int8_t nb = wt[D.t10(x + ex(q), y + ey(q), z + ez(q))];
+        hit = hit || (me == 1 ? nb <= 0 : nb >= 1);
+    }
+    if (hit) out = me == 1 ? 2 : -1;
+    type[n] = out;
+}
+
+// one 27-point smoothing pass (:187-198), summation order and weights of the reference, no FMA contraction
+template <typename T>
+__global__ void k_geo_smooth(GeoDims D, const T* __restrict__ src, T* __restrict__ dst) {
+    const int x = -8 + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int y = -8 + (int)blockIdx.y, z = -8 + (int)blockIdx.z;
+    if (x > D.nx + 9) return;
+    constexpr int iex[27] = {0, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1};
+    constexpr int iey[27] = {0, 0, 0, 1, -1, 0, 0, 1, 1, -1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1, -1, 1, -1, 1};
+    constexpr int iez[27] = {0, 0, 0, 0, 0, 1, -1, 0, 0, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1, -1, 1, 1, -1, -1, 1, 1, -1};
+    constexpr T we[4] = {T(8) / T(27), T(2) / T(27), T(1) / T(54), T(1) / T(216)};
+    T acc = T(0);
+#pragma unroll
+    for (int n = 0; n < 27; n++) {
+        const int m = iex[n] * iex[n] + iey[n] * iey[n] + iez[n] * iez[n];
+        acc = add_rn(acc, mul_rn(src[D.t10(x + iex[n], y + iey[n], z + iez[n])], we[m]));
+    }
+    dst[D.t10(x, y, z)] = acc;
+}
+// copy-back of the interior region (:199-205): the outermost layer keeps the raw flags
+template <typename T>
+__global__ void k_geo_copy_inner(GeoDims D, const T* __restrict__ src, T* __restrict__ dst) {
+    const int x = -8 + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int y = -8 + (int)blockIdx.y, z = -8 + (int)blockIdx.z;
+    if (x > D.nx + 9) return;
+    const long long n = D.t10(x, y, z);
+    dst[n] = src[n];
+}
+
+// ISO8 two-ring gradient tables (src/Geometry_preprocessing.cpp:233-375): every term is w(x+o) - w(x-o); the
+// "+o" offsets are listed in source order, seven groups per axis with sizes ISO8_N.
+struct Iso8Tables { signed char o[3][34][3]; };
+
+// solid-surface normals at fluid-boundary nodes + export of walls / walls_type (:135-141, :178-184, :229-386)
+template <typename T>
+__global__ void k_geo_export(GeoDims D, Iso8Tables tab, const int8_t* __restrict__ wt, const int8_t* __restrict__ type,
+                             const T* __restrict__ ws2, int* __restrict__ walls, int* __restrict__ walls_type,
+                             T* __restrict__ s_nx, T* __restrict__ s_ny, T* __restrict__ s_nz, T eps) {
+    const int x = -3 + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int y = -3 + (int)blockIdx.y, z = -3 + (int)blockIdx.z;
+    if (x > D.nx + 4) return;
+    const long long n = D.t10(x, y, z);
+    const int NX4 = D.nx + 8, NY4 = D.ny + 8, NX2 = D.nx + 4, NY2 = D.ny + 4;
+    const long long c4 = (x + 3) + (long long)NX4 * ((y + 3) + (long long)NY4 * (z + 3));
+    const int ty = type[n];
+    walls_type[c4] = ty;
+    if (x >= -1 && x <= D.nx + 2 && y >= -1 && y <= D.ny + 2 && z >= -1 && z <= D.nz + 2)
+        walls[(x + 1) + (long long)NX2 * ((y + 1) + (long long)NY2 * (z + 1))] = wt[n];
+    if (ty != -1) return;
+    constexpr int ISO8_N[7] = {1, 4, 4, 1, 8, 12, 4};
+    constexpr T ISO8[7] = {T(4) / T(45), T(1) / T(21), T(2) / T(105), T(5) / T(504), T(1) / T(315), T(1) / T(630), T(1) / T(5040)};
+    T nw[3];
+#pragma unroll 1
+    for (int a = 0; a < 3; a++) {
+        T total = T(0);
+        int pos = 0;
+#pragma unroll
+        for (int g = 0; g < 7; g++) {
+            T s = T(0);
+            for (int m = 0; m < ISO8_N[g]; m++, pos++) {
+                const int dx = tab.o[a][pos][0], dy = tab.o[a][pos][1], dz = tab.o[a][pos][2];
+                const T plus = ws2[D.t10(x + dx, y + dy, z + dz)], minus = ws2[D.t10(x - dx, y - dy, z - dz)];
+                s = (m == 0) ? sub_rn(plus, minus) : sub_rn(add_rn(s, plus), minus);
+            }
+            total = (g == 0) ? mul_rn(ISO8[g], s) : add_rn(total, mul_rn(ISO8[g], s));
+        }
+        nw[a] = total;
+    }
+    const T n2 = add_rn(add_rn(mul_rn(nw[0], nw[0]), mul_rn(nw[1], nw[1])), mul_rn(nw[2], nw[2]));
+    const T tmp = div_rn(T(1), add_rn(sqrt_rn(n2), eps));   // :377
+    s_nx[c4] = mul_rn(nw[0], tmp); s_ny[c4] = mul_rn(nw[1], tmp); s_nz[c4] = mul_rn(nw[2], tmp);
+}
+
+// =====================================================================================================
+// initial state: src/Init_multiphase.cpp:299-496 (options 1-5), u = v = w = 0, rho = 1
+// =====================================================================================================
+template <typename T>
+__global__ void k_init_phi(const Lattice<T> L, int option, T interface_z0, int nyg, int nzg, int open_z) {
+    // phi: [-3..n+4]^3 threads; pattern written on [0..n+1]^3 (:308-356), then phi_inlet for z <= 0 (:358-372)
+    const int i = -3 + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int j = -3 + (int)blockIdx.y, k = -3 + (int)blockIdx.z;
+    if (i > L.nx + 4) return;
+    const int gi = i + L.x0 - 1;   // global x
+    T ph = T(0);
+    bool set = false;
+    // slab note: columns 0 and nx+1 of an interior slab are real columns of the neighbour, the pattern formula is
+    // the same there; beyond the global range [0..nxg+1] the reference array keeps its calloc'ed 0
+    if (gi >= 0 && gi <= L.nx_global + 1 && j >= 0 && j <= nyg + 1 && k >= 0 && k <= nzg + 1) {
+        const T x = (T)gi, y = (T)j, z = (T)k;
+        set = true;
+        if (option == 1) { ph = T(-1); if (z <= interface_z0) ph = T(1); }
+        else if (option == 2) { ph = T(1); if (z <= interface_z0) ph = T(-1); }
+        else {
+            const T cx = option == 5 ? lit<T>(0.5) : lit<T>(0.);
+            const T dx = x - (L.nx_global + 1) * cx, dz = z - (nzg + 1) * lit<T>(0.5), dy = y - (nyg + 1) * lit<T>(0.5);
+            // pow(a,2) on the host == a*a correctly rounded; sums left to right as :328
+            const T d = add_rn(add_rn(mul_rn(dx, dx), mul_rn(dz, dz)), mul_rn(dy, dy));
+            const bool inside = d <= mul_rn(interface_z0, interface_z0);
+            ph = option == 4 ? (inside ? T(-1) : T(1)) : (inside ? T(1) : T(-1));
+        }
+    }
+    if (open_z && k <= 0) { ph = L.phi_inlet; set = true; }
+    if (set) L.phi[L.i4(i, j, k)] = ph;
+}
+
+template <typename T>
+__global__ void k_init_pdf(const Lattice<T> L, int outlet_convective) {
+    // equilibrium at rest on [0..n+1]^3 (:393-442): pdf_q = rho_g * w_q  (+ rho_g*w_q*(-1.5*0) == same value)
+    const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int j = (int)blockIdx.y, k = (int)blockIdx.z;
+    if (i > L.nx + 1) return;
+    const T ph = L.phi[L.i4(i, j, k)];
+    const T rho1 = mul_rn(mul_rn(T(1), add_rn(T(1), ph)), lit<T>(0.5));
+    const T rho2 = mul_rn(mul_rn(T(1), sub_rn(T(1), ph)), lit<T>(0.5));
+    const int c1 = L.i1(i, j, k);
+#pragma unroll
+    for (int q = 0; q < 19; q++) {
+        L.slot(q, 0)[c1] = mul_rn(rho1, w_equ<T>(q));
+        L.slot(q, 1)[c1] = mul_rn(rho2, w_equ<T>(q));
+    }
+    if (outlet_convective && k == L.nz) {   // :445-494
+        const int cb = L.i1(i, j, 0), plane = L.NX1 * L.NY1;
+#pragma unroll
+        for (int q = 0; q < 19; q++) {
+            L.f_convec[cb + plane * q] = mul_rn(rho1, w_equ<T>(q));
+            L.g_convec[cb + plane * q] = mul_rn(rho2, w_equ<T>(q));
+        }
+        L.phi_convec[cb] = ph;
+    }
+}
+
+// =====================================================================================================
+// monitor: compute_macro_vars (src/Misc.cpp:222-274) + per-slice sums (src/Monitor.cpp:34-80) in one pass.
+// One block per z slice; sums in double (the reference sums sequentially in T).
+// out layout per slice k-1: [0..6] fl1, fl2, pre, mass1, mass2, vol1, vol2, [7] max |u|^2, [8] usq1, [9] usq2, [10] nan flag
+// =====================================================================================================
+#define MFLBM_MON_N 11
+template <typename T>
+__global__ void __launch_bounds__(256) k_monitor(const Lattice<T> L, double* __restrict__ out) {
+    const int k = 1 + blockIdx.x;
+    double acc[MFLBM_MON_N];
+#pragma unroll
+    for (int n = 0; n < MFLBM_MON_N; n++) acc[n] = 0.0;
+    const int plane = L.nx * L.ny;
+    for (int t = threadIdx.x; t < plane; t += blockDim.x) {
+        const int i = 1 + t % L.nx, j = 1 + t / L.nx;
+        const int c1 = L.i1(i, j, k);
+        if (L.solid1[c1]) continue;
+        T ft[19];
+#pragma unroll
+        for (int q = 0; q < 19; q++) ft[q] = L.slot(q, 0)[c1] + L.slot(q, 1)[c1];
+        T rho = ft[0];
+#pragma unroll
+        for (int q = 1; q < 19; q++) rho = rho + ft[q];
+        const int c2 = L.i2(i, j, k);
+        const T tmp = lit<T>(0.5) * L.lbm_gamma * L.curv[c1] * L.c_norm[c2];
+        const T fx = tmp * L.cn_x[c2], fy = tmp * L.cn_y[c2], fz = tmp * L.cn_z[c2] + L.force_z;
+        const T u = ft[1] - ft[2] + ft[7] - ft[8] + ft[9] - ft[10] + ft[11] - ft[12] + ft[13] - ft[14] - lit<T>(0.5) * fx;
+        const T v = ft[3] - ft[4] + ft[7] + ft[8] - ft[9] - ft[10] + ft[15] - ft[16] + ft[17] - ft[18] - lit<T>(0.5) * fy;
+        const T w = ft[5] - ft[6] + ft[11] + ft[12] - ft[13] - ft[14] + ft[15] + ft[16] - ft[17] - ft[18] - lit<T>(0.5) * fz;
+        const T ph = L.phi[L.i4(i, j, k)];
+        const T usq = u * u + v * v + w * w;
+        const double hp = (double)(lit<T>(0.5) * (lit<T>(1.) + ph)), hm = (double)(lit<T>(0.5) * (lit<T>(1.) - ph));
+        acc[0] += (double)w * hp; acc[1] += (double)w * hm; acc[2] += (double)rho;
+        acc[3] += (double)rho * hp; acc[4] += (double)rho * hm; acc[5] += hp; acc[6] += hm;
+        acc[7] = fmax(acc[7], (double)usq);
+        if (ph > lit<T>(0.999)) acc[8] += (double)usq; else if (ph < lit<T>(-0.999)) acc[9] += (double)usq;
+        if (!(isfinite((double)usq) && isfinite((double)rho) && isfinite((double)ph))) acc[10] = 1.0;
+    }
+    __shared__ double sm[MFLBM_MON_N][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int n = 0; n < MFLBM_MON_N; n++) {
+        double v = acc[n];
+        const bool is_max = (n == 7 || n == 10);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double other = __shfl_xor_sync(0xffffffffu, v, o);
+            v = is_max ? fmax(v, other) : v + other;
+        }
+        if (lane == 0) sm[n][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < MFLBM_MON_N) {
+        const int n = threadIdx.x;
+        const bool is_max = (n == 7 || n == 10);
+        double v = sm[n][0];
+        for (int wv = 1; wv < (int)(blockDim.x >> 5); wv++) v = is_max ? fmax(v, sm[n][wv]) : v + sm[n][wv];
+        out[(long long)(k - 1) * MFLBM_MON_N + n] = v;
+    }
+}
+
+// =====================================================================================================
+// x-slab halo exchange (new).  Buffers are dense [item][z][y] planes.
+// PDF halos carry the ten populations with ex = +1 (slots 1,7,9,11,13) or ex = -1 (2,8,10,12,14) of both
+// components over the full (ny+2)(nz+2) plane; the phi halo carries 4 columns over (ny+8)(nz+8).
+// =====================================================================================================
+__host__ __device__ constexpr int slot_exp(int n) { constexpr int t[5] = {1, 7, 9, 11, 13}; return t[n]; }   // ex = +1
+__host__ __device__ constexpr int slot_exm(int n) { constexpr int t[5] = {2, 8, 10, 12, 14}; return t[n]; }  // ex = -1
+
+// copy column `col` of the ten slots (PLUS ? ex=+1 : ex=-1) between the lattice and a buffer
+template <typename T, bool PLUS, bool PACK>
+__global__ void k_halo_pdf(const Lattice<T> L, T* __restrict__ buf, const int col) {
+    const int y = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
+    if (y >= L.NY1) return;
+    const int plane = L.NY1 * L.NZ1;
+    const int c1 = L.i1(col, y, z);
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
+#pragma unroll
+        for (int n = 0; n < 5; n++) {
+            const int q = PLUS ? slot_exp(n) : slot_exm(n);
+            T* cell = L.slot(q, g) + c1;
+            T* b = buf + (long long)(g * 5 + n) * plane + (y + L.NY1 * z);
+            if (PACK) *b = *cell; else *cell = *b;
+        }
+    }
+}
+
+// copy 4 phi columns starting at local column `col0` between the lattice and a buffer
+template <typename T, bool PACK>
+__global__ void k_halo_phi(const Lattice<T> L, T* __restrict__ buf, const int col0) {
+    const int y = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;   // 0-based over the 4-ghost extents
+    if (y >= L.NY4) return;
+    const int plane = L.NY4 * L.NZ4;
+#pragma unroll
+    for (int n = 0; n < 4; n++) {
+        T* cell = L.phi + ((col0 + n + 3) + L.NX4 * (y + L.NY4 * z));
+        T* b = buf + (long long)n * plane + (y + L.NY4 * z);
+        if (PACK) *b = *cell; else *cell = *b;
+    }
+}
+
+}  // namespace mflbm

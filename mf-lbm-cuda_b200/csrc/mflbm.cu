@@ -1,0 +1,595 @@
+// mflbm.cu — Solver<T> (device state, per-step sequencing, CUDA-graph replay) and the C ABI of include/mflbm.h.
+// One translation unit, both precisions.  Build: see mf-lbm-cuda_b200/csrc/Makefile (sm_100a, -lineinfo).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mflbm.h"
+#include "core.cuh"
+#include "kernels_aux.cuh"
+#include "kernels_step.cuh"
+
+namespace mflbm {
+
+static thread_local std::string g_last_error;
+
+struct Error {
+    std::string msg;
+};
+#define MF_FAIL(...)                                        \
+    do {                                                    \
+        char buf_[512];                                     \
+        snprintf(buf_, sizeof buf_, __VA_ARGS__);           \
+        throw Error{std::string(buf_)};                     \
+    } while (0)
+#define MF_CUDA(x)                                                                                   \
+    do {                                                                                             \
+        cudaError_t e_ = (x);                                                                        \
+        if (e_ != cudaSuccess) MF_FAIL("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #x); \
+    } while (0)
+
+template <typename T> struct ParamsOf;
+template <> struct ParamsOf<float> { using type = mflbm_f32_params; };
+template <> struct ParamsOf<double> { using type = mflbm_f64_params; };
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+template <typename T>
+struct Solver {
+    using Params = typename ParamsOf<T>::type;
+    Params P{};
+    mflbm_slab slab{};
+    bool is_slab = false;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    Lattice<T> L{};
+    long long N1 = 0, N2 = 0, N4 = 0, NP = 0;   // cells of 1/2/4-ghost arrays, cells of an (NX1*NY1) plane
+    // device memory
+    T *d_pdf = nullptr, *d_phi = nullptr, *d_cnx = nullptr, *d_cny = nullptr, *d_cnz = nullptr, *d_cnorm = nullptr, *d_curv = nullptr;
+    T *d_Win = nullptr, *d_fconv = nullptr, *d_gconv = nullptr, *d_phiconv = nullptr;
+    int *d_walls = nullptr, *d_wtype = nullptr;
+    uint8_t* d_solid1 = nullptr;
+    T *d_snx = nullptr, *d_sny = nullptr, *d_snz = nullptr;
+    int *d_list_phi = nullptr, *d_list_alter = nullptr, *d_list_cn = nullptr;
+    int n_list_phi = 0, n_list_alter = 0, n_list_cn = 0;
+    long long counts[4] = {0, 0, 0, 0};
+    long long n_fluid = 0;
+    long long launches = 0;
+    bool have_geometry = false;
+    bool solids_zeroed = false;   // cn_*/c_norm hold 0 at every solid node (allows k_normals<SKIP_SOLID>)
+    // monitor
+    double* d_mon = nullptr;
+    double* h_mon = nullptr;
+    // halo buffers: [kind 0..2][side 0..1]
+    T* d_send[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    T* d_recv[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    // CUDA graph of one (odd, even) or (even, odd) step pair
+    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+
+    int nx() const { return L.nx; }
+
+    // ------------------------------------------------------------------------------------------------
+    void create(const Params* p, const mflbm_slab* sl, int dev, void* strm) {
+        device = dev;
+        MF_CUDA(cudaSetDevice(device));
+        if (strm) { stream = (cudaStream_t)strm; own_stream = false; }
+        else { MF_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true; }
+        if (p->nx < 3 || p->ny < 3 || p->nz < 3) MF_FAIL("lattice too small");
+        if (p->iper != 0) MF_FAIL("x-periodic boundaries are not supported (reference: src/IO_multiphase.cpp:210)");
+        if (p->mrt < 1 || p->mrt > 4) MF_FAIL("mrt must be 1..4");
+        is_slab = sl != nullptr;
+        if (is_slab) slab = *sl;
+        else { slab.x0 = 1; slab.nx_local = p->nx; slab.has_left = 0; slab.has_right = 0; }
+        if (slab.nx_local < 4 && is_slab) MF_FAIL("slab narrower than the 4-column phi halo");
+        L.nx = (int)slab.nx_local; L.ny = (int)p->ny; L.nz = (int)p->nz;
+        L.x0 = (int)slab.x0; L.nx_global = (int)p->nx;
+        L.NX1 = L.nx + 2; L.NY1 = L.ny + 2; L.NZ1 = L.nz + 2;
+        L.NX2 = L.nx + 4; L.NY2 = L.ny + 4; L.NZ2 = L.nz + 4;
+        L.NX4 = L.nx + 8; L.NY4 = L.ny + 8; L.NZ4 = L.nz + 8;
+        N1 = (long long)L.NX1 * L.NY1 * L.NZ1; N2 = (long long)L.NX2 * L.NY2 * L.NZ2; N4 = (long long)L.NX4 * L.NY4 * L.NZ4;
+        NP = (long long)L.NX1 * L.NY1;
+        if (N4 >= (1LL << 31)) MF_FAIL("lattice (or slab) exceeds 2^31 cells per field; decompose into more slabs");
+        L.N1 = N1;
+        auto zalloc = [&](void** ptr, size_t bytes) { MF_CUDA(cudaMalloc(ptr, bytes)); MF_CUDA(cudaMemsetAsync(*ptr, 0, bytes, stream)); };
+        zalloc((void**)&d_pdf, sizeof(T) * N1 * 38);
+        zalloc((void**)&d_phi, sizeof(T) * N4);
+        zalloc((void**)&d_cnx, sizeof(T) * N2); zalloc((void**)&d_cny, sizeof(T) * N2); zalloc((void**)&d_cnz, sizeof(T) * N2);
+        zalloc((void**)&d_cnorm, sizeof(T) * N2);
+        zalloc((void**)&d_curv, sizeof(T) * N1);
+        zalloc((void**)&d_Win, sizeof(T) * NP);
+        zalloc((void**)&d_fconv, sizeof(T) * NP * 19); zalloc((void**)&d_gconv, sizeof(T) * NP * 19); zalloc((void**)&d_phiconv, sizeof(T) * NP);
+        zalloc((void**)&d_walls, sizeof(int) * N2); zalloc((void**)&d_wtype, sizeof(int) * N4);
+        zalloc((void**)&d_solid1, N1);
+        zalloc((void**)&d_snx, sizeof(T) * N4); zalloc((void**)&d_sny, sizeof(T) * N4); zalloc((void**)&d_snz, sizeof(T) * N4);
+        zalloc((void**)&d_mon, sizeof(double) * MFLBM_MON_N * L.nz);
+        MF_CUDA(cudaMallocHost((void**)&h_mon, sizeof(double) * MFLBM_MON_N * L.nz));
+        if (is_slab) {
+            const long long npdf = 10LL * L.NY1 * L.NZ1, nphi = 4LL * L.NY4 * L.NZ4;
+            for (int kind = 0; kind < 3; kind++)
+                for (int side = 0; side < 2; side++) {
+                    const long long n = kind == 2 ? nphi : npdf;
+                    zalloc((void**)&d_send[kind][side], sizeof(T) * n);
+                    zalloc((void**)&d_recv[kind][side], sizeof(T) * n);
+                }
+        }
+        L.pdf = d_pdf; L.phi = d_phi; L.cn_x = d_cnx; L.cn_y = d_cny; L.cn_z = d_cnz; L.c_norm = d_cnorm; L.curv = d_curv;
+        L.W_in = d_Win; L.f_convec = d_fconv; L.g_convec = d_gconv; L.phi_convec = d_phiconv;
+        L.walls = d_walls; L.walls_type = d_wtype; L.solid1 = d_solid1; L.s_nx = d_snx; L.s_ny = d_sny; L.s_nz = d_snz;
+        set_params(p);
+        MF_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    void destroy() {
+        cudaSetDevice(device);
+        drop_graphs();
+        void* ptrs[] = {d_pdf, d_phi, d_cnx, d_cny, d_cnz, d_cnorm, d_curv, d_Win, d_fconv, d_gconv, d_phiconv, d_walls, d_wtype,
+                        d_solid1, d_snx, d_sny, d_snz, d_list_phi, d_list_alter, d_list_cn, d_mon};
+        for (void* q : ptrs) if (q) cudaFree(q);
+        for (int kind = 0; kind < 3; kind++) for (int side = 0; side < 2; side++) { if (d_send[kind][side]) cudaFree(d_send[kind][side]); if (d_recv[kind][side]) cudaFree(d_recv[kind][side]); }
+        if (h_mon) cudaFreeHost(h_mon);
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+
+    void drop_graphs() {
+        for (auto& g : graph_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    }
+
+    // copyConstantData, src/main_iteration_GPU.cu:14-47
+    void set_params(const Params* p) {
+        if (have_geometry && (p->nx != P.nx || p->ny != P.ny || p->nz != P.nz)) MF_FAIL("lattice dimensions cannot change after create");
+        P = *p;
+        L.lbm_gamma = p->lbm_gamma; L.force_z = p->force_z; L.la_nui1 = p->la_nui1; L.la_nui2 = p->la_nui2; L.lbm_beta = p->lbm_beta;
+        L.RK_weight2 = T(1) / std::sqrt(T(2)) / T(36);   // includes/Fluid_multiphase.h:32, evaluated on the host in T
+        L.phi_inlet = p->phi_inlet; L.relaxation = p->relaxation; L.sa_inject = p->sa_inject; L.uin_avg = p->uin_avg;
+        L.cos_theta = p->cos_theta; L.rho_in = p->rho_in; L.rho_out = p->rho_out;
+        L.Z_porous_plate = p->Z_porous_plate; L.porous_plate_cmd = p->porous_plate_cmd;
+        drop_graphs();   // kernel arguments are baked into captured graphs
+    }
+
+    // ------------------------------------------------------------------------------------------------
+    // launch helpers
+    dim3 block2() const { const int bx = std::min(128, 32 * ceil_div(L.nx + 2, 32)); return dim3(bx, std::max(1, 128 / bx), 1); }
+    void count(int n = 1) { launches += n; }
+    void check_launch() { MF_CUDA(cudaGetLastError()); }
+
+    // ------------------------------------------------------------------------------------------------
+    // geometry
+    void finish_geometry(const std::vector<int>& walls, const std::vector<int>& wtype) {
+        // byte copy of walls on the 1-ghost extents + fluid count
+        std::vector<uint8_t> s1((size_t)N1);
+        n_fluid = 0;
+        for (int k = 0; k <= L.nz + 1; k++) for (int j = 0; j <= L.ny + 1; j++) for (int i = 0; i <= L.nx + 1; i++) {
+            const int w = walls[(size_t)(i + 1) + (size_t)L.NX2 * ((j + 1) + (size_t)L.NY2 * (k + 1))];
+            s1[(size_t)i + (size_t)L.NX1 * (j + (size_t)L.NY1 * k)] = (uint8_t)(w != 0);
+            if (w == 0 && i >= 1 && i <= L.nx && j >= 1 && j <= L.ny && k >= 1 && k <= L.nz) n_fluid++;
+        }
+        MF_CUDA(cudaMemcpyAsync(d_solid1, s1.data(), (size_t)N1, cudaMemcpyHostToDevice, stream));
+        // compact boundary-node lists over the ranges the reference kernels scan
+        // (:737 [-2..n+3] type 2; :814 [-1..n+2] type -1; :885 [0..n+1] type 2) and the reference's counters
+        std::vector<int> lphi, lalt, lcn;
+        counts[0] = counts[1] = counts[2] = counts[3] = 0;
+        for (int k = -3; k <= L.nz + 4; k++) for (int j = -3; j <= L.ny + 4; j++) for (int i = -3; i <= L.nx + 4; i++) {
+            const int n = (i + 3) + L.NX4 * ((j + 3) + L.NY4 * (k + 3));
+            const int t = wtype[(size_t)n];
+            if (t != 2 && t != -1) continue;
+            const bool in3 = i >= -2 && i <= L.nx + 3 && j >= -2 && j <= L.ny + 3 && k >= -2 && k <= L.nz + 3;
+            const bool in2 = i >= -1 && i <= L.nx + 2 && j >= -1 && j <= L.ny + 2 && k >= -1 && k <= L.nz + 2;
+            const bool in1 = i >= 0 && i <= L.nx + 1 && j >= 0 && j <= L.ny + 1 && k >= 0 && k <= L.nz + 1;
+            if (t == 2) { counts[0]++; if (in3) { counts[2]++; lphi.push_back(n); } if (in1) lcn.push_back(n); }
+            else { counts[1]++; if (in3) counts[3]++; if (in2) lalt.push_back(n); }
+        }
+        auto up = [&](int*& d, int& cnt, const std::vector<int>& v) {
+            if (d) { MF_CUDA(cudaFree(d)); d = nullptr; }
+            cnt = (int)v.size();
+            if (cnt) { MF_CUDA(cudaMalloc((void**)&d, sizeof(int) * v.size())); MF_CUDA(cudaMemcpyAsync(d, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice, stream)); }
+        };
+        up(d_list_phi, n_list_phi, lphi); up(d_list_alter, n_list_alter, lalt); up(d_list_cn, n_list_cn, lcn);
+        MF_CUDA(cudaStreamSynchronize(stream));
+        have_geometry = true;
+        solids_zeroed = false;
+        drop_graphs();
+    }
+
+    void upload_geometry(const int32_t* walls, const int32_t* wtype, const T* snx, const T* sny, const T* snz) {
+        if (!walls || !wtype || !snx || !sny || !snz) MF_FAIL("upload_geometry: null array");
+        MF_CUDA(cudaMemcpyAsync(d_walls, walls, sizeof(int) * N2, cudaMemcpyHostToDevice, stream));
+        MF_CUDA(cudaMemcpyAsync(d_wtype, wtype, sizeof(int) * N4, cudaMemcpyHostToDevice, stream));
+        MF_CUDA(cudaMemcpyAsync(d_snx, snx, sizeof(T) * N4, cudaMemcpyHostToDevice, stream));
+        MF_CUDA(cudaMemcpyAsync(d_sny, sny, sizeof(T) * N4, cudaMemcpyHostToDevice, stream));
+        MF_CUDA(cudaMemcpyAsync(d_snz, snz, sizeof(T) * N4, cudaMemcpyHostToDevice, stream));
+        std::vector<int> w(walls, walls + N2), t(wtype, wtype + N4);
+        finish_geometry(w, t);
+    }
+
+    void preprocess_geometry(const int8_t* interior_global) {
+        if (!interior_global) MF_FAIL("preprocess_geometry: null array");
+        GeoDims D{};
+        D.nx = L.nx; D.ny = L.ny; D.nz = L.nz; D.TX = L.nx + 20; D.TY = L.ny + 20; D.TZ = L.nz + 20;
+        D.x0 = L.x0; D.nxg = (int)P.nx; D.nyg = (int)P.ny; D.nzg = (int)P.nz; D.iper = P.iper; D.jper = P.jper; D.kper = P.kper;
+        const size_t TN = (size_t)D.TX * D.TY * D.TZ, NG = (size_t)P.nx * P.ny * P.nz;
+        int8_t *d_in = nullptr, *d_wt = nullptr, *d_ty = nullptr;
+        T *d_ws1 = nullptr, *d_ws2 = nullptr;
+        MF_CUDA(cudaMalloc((void**)&d_in, NG)); MF_CUDA(cudaMalloc((void**)&d_wt, TN)); MF_CUDA(cudaMalloc((void**)&d_ty, TN));
+        MF_CUDA(cudaMalloc((void**)&d_ws1, TN * sizeof(T))); MF_CUDA(cudaMalloc((void**)&d_ws2, TN * sizeof(T)));
+        MF_CUDA(cudaMemcpyAsync(d_in, interior_global, NG, cudaMemcpyHostToDevice, stream));
+        MF_CUDA(cudaMemsetAsync(d_ty, 0, TN, stream));
+        const int bx = 128;
+        k_geo_fill<T><<<dim3(ceil_div(D.TX, bx), D.TY, D.TZ), bx, 0, stream>>>(D, d_in, d_wt, d_ws1, d_ws2); check_launch(); count();
+        const dim3 ginner(ceil_div(D.TX - 2, bx), D.TY - 2, D.TZ - 2);
+        k_geo_classify<<<ginner, bx, 0, stream>>>(D, d_wt, d_ty); check_launch(); count();
+        for (int it = 0; it < 4; it++) {   // :187-206
+            k_geo_smooth<T><<<ginner, bx, 0, stream>>>(D, d_ws1, d_ws2); check_launch();
+            k_geo_copy_inner<T><<<ginner, bx, 0, stream>>>(D, d_ws2, d_ws1); check_launch();
+            count(2);
+        }
+        Iso8Tables tab;
+        static const signed char TX_[34][3] = {{1,0,0},{1,1,0},{1,-1,0},{1,0,1},{1,0,-1},{1,1,1},{1,1,-1},{1,-1,1},{1,-1,-1},{2,0,0},
+            {2,1,0},{2,-1,0},{2,0,1},{2,0,-1},{1,2,0},{1,-2,0},{1,0,2},{1,0,-2},
+            {2,1,1},{2,1,-1},{2,-1,1},{2,-1,-1},{1,2,1},{1,2,-1},{1,-2,1},{1,-2,-1},{1,1,2},{1,1,-2},{1,-1,2},{1,-1,-2},
+            {2,2,0},{2,-2,0},{2,0,2},{2,0,-2}};
+        static const signed char TY_[34][3] = {{0,1,0},{1,1,0},{-1,1,0},{0,1,1},{0,1,-1},{1,1,1},{1,1,-1},{-1,1,-1},{-1,1,1},{0,2,0},
+            {2,1,0},{-2,1,0},{0,2,1},{0,2,-1},{1,2,0},{-1,2,0},{0,1,2},{0,1,-2},
+            {2,1,1},{2,1,-1},{-2,1,1},{-2,1,-1},{1,2,1},{1,2,-1},{-1,2,1},{-1,2,-1},{1,1,2},{1,1,-2},{-1,1,2},{-1,1,-2},
+            {2,2,0},{-2,2,0},{0,2,2},{0,2,-2}};
+        static const signed char TZ_[34][3] = {{0,0,1},{0,1,1},{0,-1,1},{1,0,1},{-1,0,1},{1,1,1},{1,-1,1},{-1,1,1},{-1,-1,1},{0,0,2},
+            {0,1,2},{0,-1,2},{2,0,1},{-2,0,1},{0,2,1},{0,-2,1},{1,0,2},{-1,0,2},
+            {2,1,1},{2,-1,1},{-2,1,1},{-2,-1,1},{1,2,1},{1,-2,1},{-1,2,1},{-1,-2,1},{1,1,2},{1,-1,2},{-1,1,2},{-1,-1,2},
+            {0,2,2},{0,-2,2},{2,0,2},{-2,0,2}};
+        memcpy(tab.o[0], TX_, sizeof TX_); memcpy(tab.o[1], TY_, sizeof TY_); memcpy(tab.o[2], TZ_, sizeof TZ_);
+        MF_CUDA(cudaMemsetAsync(d_snx, 0, sizeof(T) * N4, stream)); MF_CUDA(cudaMemsetAsync(d_sny, 0, sizeof(T) * N4, stream));
+        MF_CUDA(cudaMemsetAsync(d_snz, 0, sizeof(T) * N4, stream));
+        const T eps = (T)1.1920928955078125e-07f;   // includes/Module.h:10-16: float epsilon in both precisions
+        k_geo_export<T><<<dim3(ceil_div(L.NX4, bx), L.NY4, L.NZ4), bx, 0, stream>>>(D, tab, d_wt, d_ty, d_ws2, d_walls, d_wtype, d_snx, d_sny, d_snz, eps);
+        check_launch(); count();
+        std::vector<int> w((size_t)N2), t((size_t)N4);
+        MF_CUDA(cudaMemcpyAsync(w.data(), d_walls, sizeof(int) * N2, cudaMemcpyDeviceToHost, stream));
+        MF_CUDA(cudaMemcpyAsync(t.data(), d_wtype, sizeof(int) * N4, cudaMemcpyDeviceToHost, stream));
+        MF_CUDA(cudaStreamSynchronize(stream));
+        cudaFree(d_in); cudaFree(d_wt); cudaFree(d_ty); cudaFree(d_ws1); cudaFree(d_ws2);
+        finish_geometry(w, t);
+    }
+
+    void download_geometry(int32_t* walls, int32_t* wtype, T* snx, T* sny, T* snz, int64_t* cnt) {
+        if (walls) MF_CUDA(cudaMemcpyAsync(walls, d_walls, sizeof(int) * N2, cudaMemcpyDeviceToHost, stream));
+        if (wtype) MF_CUDA(cudaMemcpyAsync(wtype, d_wtype, sizeof(int) * N4, cudaMemcpyDeviceToHost, stream));
+        if (snx) MF_CUDA(cudaMemcpyAsync(snx, d_snx, sizeof(T) * N4, cudaMemcpyDeviceToHost, stream));
+        if (sny) MF_CUDA(cudaMemcpyAsync(sny, d_sny, sizeof(T) * N4, cudaMemcpyDeviceToHost, stream));
+        if (snz) MF_CUDA(cudaMemcpyAsync(snz, d_snz, sizeof(T) * N4, cudaMemcpyDeviceToHost, stream));
+        MF_CUDA(cudaStreamSynchronize(stream));
+        if (cnt) for (int n = 0; n < 4; n++) cnt[n] = counts[n];
+    }
+
+    // ------------------------------------------------------------------------------------------------
+    // state
+    void upload_state(const T* pdf, const T* phi, const T* cnx, const T* cny, const T* cnz, const T* cnorm, const T* curv,
+                      const T* Win, const T* fconv, const T* gconv, const T* phiconv) {
+        auto up = [&](T* d, const T* h, long long n) { if (h) MF_CUDA(cudaMemcpyAsync(d, h, sizeof(T) * n, cudaMemcpyHostToDevice, stream)); };
+        up(d_pdf, pdf, N1 * 38); up(d_phi, phi, N4); up(d_cnx, cnx, N2); up(d_cny, cny, N2); up(d_cnz, cnz, N2); up(d_cnorm, cnorm, N2);
+        up(d_curv, curv, N1); up(d_Win, Win, NP); up(d_fconv, fconv, NP * 19); up(d_gconv, gconv, NP * 19); up(d_phiconv, phiconv, NP);
+        MF_CUDA(cudaStreamSynchronize(stream));
+        solids_zeroed = false;   // the caller's cn arrays are not trusted to hold zeros in solids
+    }
+
+    void download_state(T* pdf, T* phi, T* cnx, T* cny, T* cnz, T* cnorm, T* curv, T* fconv, T* gconv, T* phiconv) {
+        if (curv && have_geometry) {   // the stepping path keeps curv at fluid nodes only; give the caller the reference's dense array
+            const dim3 b = block2();
+            k_curvature<T, false><<<dim3(ceil_div(L.nx, b.x), ceil_div(L.ny, b.y), L.nz), b, 0, stream>>>(L, 1, L.nx); check_launch(); count();
+        }
+        auto dn = [&](T* h, const T* d, long long n) { if (h) MF_CUDA(cudaMemcpyAsync(h, d, sizeof(T) * n, cudaMemcpyDeviceToHost, stream)); };
+        dn(pdf, d_pdf, N1 * 38); dn(phi, d_phi, N4); dn(cnx, d_cnx, N2); dn(cny, d_cny, N2); dn(cnz, d_cnz, N2); dn(cnorm, d_cnorm, N2);
+        dn(curv, d_curv, N1); dn(fconv, d_fconv, NP * 19); dn(gconv, d_gconv, NP * 19); dn(phiconv, d_phiconv, NP);
+        MF_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    bool open_z() const { return P.kper == 0 && P.wall_z_min == 0 && P.wall_z_max == 0; }
+
+    void init_state(int option, T interface_z0, const T* Win) {
+        if (!have_geometry) MF_FAIL("init_state before geometry");
+        if (option < 1 || option > 5) MF_FAIL("initial_fluid_distribution_option %d not supported on the device (1..5)", option);
+        const int bx = 128;
+        MF_CUDA(cudaMemsetAsync(d_phi, 0, sizeof(T) * N4, stream));
+        k_init_phi<T><<<dim3(ceil_div(L.NX4, bx), L.NY4, L.NZ4), bx, 0, stream>>>(L, option, interface_z0, (int)P.ny, (int)P.nz, open_z() ? 1 : 0);
+        check_launch();
+        k_init_pdf<T><<<dim3(ceil_div(L.NX1, bx), L.NY1, L.NZ1), bx, 0, stream>>>(L, P.outlet_BC == 1 ? 1 : 0); check_launch();
+        count(2);
+        if (Win) MF_CUDA(cudaMemcpyAsync(d_Win, Win, sizeof(T) * NP, cudaMemcpyHostToDevice, stream));
+        MF_CUDA(cudaMemsetAsync(d_cnx, 0, sizeof(T) * N2, stream)); MF_CUDA(cudaMemsetAsync(d_cny, 0, sizeof(T) * N2, stream));
+        MF_CUDA(cudaMemsetAsync(d_cnz, 0, sizeof(T) * N2, stream)); MF_CUDA(cudaMemsetAsync(d_cnorm, 0, sizeof(T) * N2, stream));
+        MF_CUDA(cudaMemsetAsync(d_curv, 0, sizeof(T) * N1, stream));
+        solids_zeroed = false;
+        gradient_chain(true);
+        MF_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    // ------------------------------------------------------------------------------------------------
+    // x ranges of plane kernels: extended over the ghost column on sides that face a neighbour slab
+    int plo() const { return slab.has_left ? 0 : 1; }
+    int phi_() const { return slab.has_right ? L.nx + 1 : L.nx; }
+
+    // the five colour-gradient kernels, call order of src/main_iteration_GPU.cu:2027-2055
+    void gradient_chain(bool dense) {
+        if (!have_geometry) MF_FAIL("gradient chain before geometry");
+        const dim3 b = block2();
+        const int bl = 128;
+        if (n_list_phi) { k_extrap_phi<T><<<ceil_div(n_list_phi, bl), bl, 0, stream>>>(L, d_list_phi, n_list_phi); check_launch(); count(); }
+        const dim3 gn(ceil_div(L.nx + 4, b.x), ceil_div(L.ny + 4, b.y), L.nz + 4);
+        if (dense || !solids_zeroed) { k_normals<T, false><<<gn, b, 0, stream>>>(L, -1, L.nx + 2); solids_zeroed = true; }
+        else k_normals<T, true><<<gn, b, 0, stream>>>(L, -1, L.nx + 2);
+        check_launch(); count();
+        if (n_list_alter) { k_alter<T><<<ceil_div(n_list_alter, bl), bl, 0, stream>>>(L, d_list_alter, n_list_alter); check_launch(); count(); }
+        if (n_list_cn) { k_extrap_cn<T><<<ceil_div(n_list_cn, bl), bl, 0, stream>>>(L, d_list_cn, n_list_cn); check_launch(); count(); }
+        const dim3 gc(ceil_div(L.nx, b.x), ceil_div(L.ny, b.y), L.nz);
+        if (dense) k_curvature<T, false><<<gc, b, 0, stream>>>(L, 1, L.nx);
+        else k_curvature<T, true><<<gc, b, 0, stream>>>(L, 1, L.nx);
+        check_launch(); count();
+    }
+
+    template <int MRT>
+    void launch_collide(bool odd) {
+        const dim3 b = block2();
+        const dim3 g(ceil_div(L.nx, b.x), ceil_div(L.ny, b.y), L.nz);
+        if (odd) k_collide<T, MRT, true><<<g, b, 0, stream>>>(L, 1, L.nx);
+        else k_collide<T, MRT, false><<<g, b, 0, stream>>>(L, 1, L.nx);
+        check_launch(); count();
+    }
+
+    void phase_collide(int ntime) {
+        const bool odd = (ntime % 2) != 0;
+        switch (P.mrt) {
+            case 1: launch_collide<1>(odd); break;
+            case 3: launch_collide<3>(odd); break;
+            case 4: launch_collide<4>(odd); break;
+            default: launch_collide<2>(odd); break;
+        }
+    }
+
+    // boundary kernels in the reference's order (:1903-1958 even, :1969-2023 odd)
+    void phase_boundaries(int ntime) {
+        const bool odd = (ntime % 2) != 0;
+        const dim3 b = block2();
+        const int lo = plo(), hi = phi_();
+        const int ni = hi - lo + 1;
+        const dim3 gz(ceil_div(ni, b.x), ceil_div(L.ny, b.y), 1), gy(ceil_div(ni, b.x), ceil_div(L.nz, b.y), 1), ge(ceil_div(ni, b.x), 1, 1);
+        if (P.kper) {
+            if (odd) k_periodic_pdf<T, 2, true><<<gz, b, 0, stream>>>(L, lo, hi); else k_periodic_pdf<T, 2, false><<<gz, b, 0, stream>>>(L, lo, hi);
+            k_periodic_phi<T, 2><<<gz, b, 0, stream>>>(L, lo, hi);
+            check_launch(); count(2);
+        }
+        if (P.jper) {
+            if (odd) k_periodic_pdf<T, 1, true><<<gy, b, 0, stream>>>(L, lo, hi); else k_periodic_pdf<T, 1, false><<<gy, b, 0, stream>>>(L, lo, hi);
+            k_periodic_phi<T, 1><<<gy, b, 0, stream>>>(L, lo, hi);
+            check_launch(); count(2);
+        }
+        if (P.jper && P.kper) {
+            const dim3 be(b.x, 1, 1);
+            if (odd) k_periodic_pdf_edges<T, true><<<ge, be, 0, stream>>>(L, lo, hi); else k_periodic_pdf_edges<T, false><<<ge, be, 0, stream>>>(L, lo, hi);
+            k_periodic_phi<T, 3><<<ge, be, 0, stream>>>(L, lo, hi);
+            check_launch(); count(2);
+        }
+        const dim3 gp(ceil_div(L.nx, b.x), ceil_div(L.ny, b.y), 1);
+        if (open_z()) {
+            if (P.inlet_BC == 1) { if (odd) k_inlet_velocity<T, true><<<gp, b, 0, stream>>>(L, 1, L.nx); else k_inlet_velocity<T, false><<<gp, b, 0, stream>>>(L, 1, L.nx); count(); }
+            else if (P.inlet_BC == 2) { if (odd) k_inlet_pressure<T, true><<<gp, b, 0, stream>>>(L, 1, L.nx); else k_inlet_pressure<T, false><<<gp, b, 0, stream>>>(L, 1, L.nx); count(); }
+            if (P.outlet_BC == 1) { if (odd) k_outlet_convective<T, true><<<gp, b, 0, stream>>>(L, 1, L.nx); else k_outlet_convective<T, false><<<gp, b, 0, stream>>>(L, 1, L.nx); count(); }
+            else if (P.outlet_BC == 2) { if (odd) k_outlet_pressure<T, true><<<gp, b, 0, stream>>>(L, 1, L.nx); else k_outlet_pressure<T, false><<<gp, b, 0, stream>>>(L, 1, L.nx); count(); }
+            check_launch();
+        }
+        if (P.porous_plate_cmd != 0) {
+            if (odd) k_porous_plate<T, true><<<gp, b, 0, stream>>>(L, 1, L.nx); else k_porous_plate<T, false><<<gp, b, 0, stream>>>(L, 1, L.nx);
+            check_launch(); count();
+        }
+    }
+
+    void step_phase(int ntime, int phase) {
+        if (!have_geometry) MF_FAIL("step before geometry");
+        if (phase == 0) phase_collide(ntime);
+        else if (phase == 1) phase_boundaries(ntime);
+        else if (phase == 2) gradient_chain(false);
+        else MF_FAIL("bad phase");
+    }
+
+    void step(int ntime) { step_phase(ntime, 0); step_phase(ntime, 1); step_phase(ntime, 2); }
+
+    // nsteps consecutive steps; pairs of steps are replayed from a captured CUDA graph (launch-bound small lattices)
+    void run(int ntime_first, int nsteps) {
+        if (nsteps <= 0) return;
+        int nt = ntime_first, left = nsteps;
+        if (left >= 4 && !is_slab) {
+            if (!solids_zeroed) { step(nt); nt++; left--; }   // first chain pass is the dense variant; keep it out of the graph
+            const int par = nt & 1;
+            if (!graph_exec[par]) {
+                const long long l0 = launches;
+                cudaGraph_t g = nullptr;
+                MF_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+                try { step(nt); step(nt + 1); }
+                catch (...) { cudaStreamEndCapture(stream, &g); if (g) cudaGraphDestroy(g); throw; }
+                MF_CUDA(cudaStreamEndCapture(stream, &g));
+                MF_CUDA(cudaGraphInstantiate(&graph_exec[par], g, 0));
+                MF_CUDA(cudaGraphDestroy(g));
+                pair_launches = launches - l0;
+                launches = l0;   // capture does not execute
+            }
+            while (left >= 2) { MF_CUDA(cudaGraphLaunch(graph_exec[par], stream)); launches += pair_launches; nt += 2; left -= 2; }
+        }
+        for (; left > 0; left--, nt++) step(nt);
+    }
+    long long pair_launches = 0;
+
+    // ------------------------------------------------------------------------------------------------
+    void monitor(mflbm_monitor_out* out) {
+        if (!have_geometry) MF_FAIL("monitor before geometry");
+        if (!out) MF_FAIL("monitor: null output");
+        k_monitor<T><<<L.nz, 256, 0, stream>>>(L, d_mon); check_launch(); count();
+        MF_CUDA(cudaMemcpyAsync(h_mon, d_mon, sizeof(double) * MFLBM_MON_N * L.nz, cudaMemcpyDeviceToHost, stream));
+        MF_CUDA(cudaStreamSynchronize(stream));
+        const int nz = L.nz;
+        auto at = [&](int k, int n) { return h_mon[(size_t)(k - 1) * MFLBM_MON_N + n]; };
+        double v1 = 0, v2 = 0, m1 = 0, m2 = 0, v1f = 0, v2f = 0, m1f = 0, m2f = 0, f1 = 0, f2 = 0, f1w = 0, f2w = 0, umax = 0, k1 = 0, k2 = 0, nanf = 0;
+        for (int k = 1; k <= nz; k++) {
+            const bool in = k >= P.n_exclude_inlet + 1 && k <= nz - P.n_exclude_outlet;
+            if (in) { m1 += at(k, 3); m2 += at(k, 4); v1 += at(k, 5); v2 += at(k, 6); f1 += at(k, 0); f2 += at(k, 1); }
+            m1f += at(k, 3); m2f += at(k, 4); v1f += at(k, 5); v2f += at(k, 6); f1w += at(k, 0); f2w += at(k, 1);
+            umax = std::max(umax, at(k, 7)); k1 += at(k, 8); k2 += at(k, 9); nanf = std::max(nanf, at(k, 10));
+            if (out->fl1) out->fl1[k - 1] = at(k, 0);
+            if (out->fl2) out->fl2[k - 1] = at(k, 1);
+            if (out->pre) out->pre[k - 1] = at(k, 2);
+            if (out->mass1) out->mass1[k - 1] = at(k, 3);
+            if (out->mass2) out->mass2[k - 1] = at(k, 4);
+            if (out->vol1) out->vol1[k - 1] = at(k, 5);
+            if (out->vol2) out->vol2[k - 1] = at(k, 6);
+        }
+        out->vol1_sum = v1; out->vol2_sum = v2; out->mass1_sum = m1; out->mass2_sum = m2;
+        out->vol1_full = v1f; out->vol2_full = v2f; out->mass1_full = m1f; out->mass2_full = m2f;
+        out->saturation = v1 / (v1 + v2);
+        out->saturation_full_domain = v1f / (v1f + v2f);
+        const double nin = (double)(nz - P.n_exclude_outlet - P.n_exclude_inlet);
+        out->fl1_avg = f1 / nin; out->fl2_avg = f2 / nin; out->fl1_avg_whole = f1w / nz; out->fl2_avg_whole = f2w / nz;
+        out->ca = ((out->fl1_avg + out->fl2_avg) / (double)P.A_xy) * (double)P.la_nu1 / (double)P.lbm_gamma;   // Monitor.cpp:170-171
+        out->umax = std::sqrt(umax);
+        out->kinetic_energy[0] = 0.5 * k1; out->kinetic_energy[1] = 0.5 * k2;
+        out->nan_detected = (nanf != 0.0) || std::isnan(out->saturation_full_domain) || std::isnan(out->ca);
+    }
+
+    // ------------------------------------------------------------------------------------------------
+    // halo exchange (x slabs)
+    long long halo_count(int kind) const { return kind == 2 ? 4LL * L.NY4 * L.NZ4 : 10LL * L.NY1 * L.NZ1; }
+
+    void halo_pack(int kind) {
+        if (!is_slab) MF_FAIL("halo_pack on a non-slab solver");
+        const int bt = 128;
+        const dim3 g1(ceil_div(L.NY1, bt), L.NZ1), g4(ceil_div(L.NY4, bt), L.NZ4);
+        if (kind == 0) {   // after an even step: real boundary columns -> neighbour ghost columns
+            if (slab.has_left) { k_halo_pdf<T, false, true><<<g1, bt, 0, stream>>>(L, d_send[0][0], 1); count(); }          // ex=-1 slots of column 1
+            if (slab.has_right) { k_halo_pdf<T, true, true><<<g1, bt, 0, stream>>>(L, d_send[0][1], L.nx); count(); }       // ex=+1 slots of column nx
+        } else if (kind == 1) {   // after an odd step: what was pushed into my ghost columns -> neighbour real columns
+            if (slab.has_left) { k_halo_pdf<T, true, true><<<g1, bt, 0, stream>>>(L, d_send[1][0], 0); count(); }           // ex=+1 slots of ghost column 0
+            if (slab.has_right) { k_halo_pdf<T, false, true><<<g1, bt, 0, stream>>>(L, d_send[1][1], L.nx + 1); count(); }  // ex=-1 slots of ghost column nx+1
+        } else if (kind == 2) {
+            if (slab.has_left) { k_halo_phi<T, true><<<g4, bt, 0, stream>>>(L, d_send[2][0], 1); count(); }
+            if (slab.has_right) { k_halo_phi<T, true><<<g4, bt, 0, stream>>>(L, d_send[2][1], L.nx - 3); count(); }
+        } else MF_FAIL("bad halo kind");
+        check_launch();
+    }
+
+    void halo_unpack(int kind) {
+        if (!is_slab) MF_FAIL("halo_unpack on a non-slab solver");
+        const int bt = 128;
+        const dim3 g1(ceil_div(L.NY1, bt), L.NZ1), g4(ceil_div(L.NY4, bt), L.NZ4);
+        if (kind == 0) {   // neighbour's real boundary column -> my ghost column
+            if (slab.has_left) { k_halo_pdf<T, true, false><<<g1, bt, 0, stream>>>(L, d_recv[0][0], 0); count(); }          // left's column nx (ex=+1) -> ghost 0
+            if (slab.has_right) { k_halo_pdf<T, false, false><<<g1, bt, 0, stream>>>(L, d_recv[0][1], L.nx + 1); count(); } // right's column 1 (ex=-1) -> ghost nx+1
+        } else if (kind == 1) {   // neighbour's ghost column -> my real boundary column
+            if (slab.has_left) { k_halo_pdf<T, false, false><<<g1, bt, 0, stream>>>(L, d_recv[1][0], 1); count(); }         // left's ghost nx+1 (ex=-1) -> column 1
+            if (slab.has_right) { k_halo_pdf<T, true, false><<<g1, bt, 0, stream>>>(L, d_recv[1][1], L.nx); count(); }      // right's ghost 0 (ex=+1) -> column nx
+        } else if (kind == 2) {
+            if (slab.has_left) { k_halo_phi<T, false><<<g4, bt, 0, stream>>>(L, d_recv[2][0], -3); count(); }
+            if (slab.has_right) { k_halo_phi<T, false><<<g4, bt, 0, stream>>>(L, d_recv[2][1], L.nx + 1); count(); }
+        } else MF_FAIL("bad halo kind");
+        check_launch();
+    }
+
+    void* device_ptr(const char* name) {
+#define MF_PTR(n, p) if (!strcmp(name, n)) return (void*)(p)
+        MF_PTR("pdf", d_pdf); MF_PTR("phi", d_phi); MF_PTR("cn_x", d_cnx); MF_PTR("cn_y", d_cny); MF_PTR("cn_z", d_cnz); MF_PTR("c_norm", d_cnorm);
+        MF_PTR("curv", d_curv); MF_PTR("W_in", d_Win); MF_PTR("f_convec", d_fconv); MF_PTR("g_convec", d_gconv); MF_PTR("phi_convec", d_phiconv);
+        MF_PTR("walls", d_walls); MF_PTR("walls_type", d_wtype); MF_PTR("s_nx", d_snx); MF_PTR("s_ny", d_sny); MF_PTR("s_nz", d_snz);
+#undef MF_PTR
+        return nullptr;
+    }
+};
+
+}  // namespace mflbm
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+using namespace mflbm;
+
+#define MF_GUARD(body)                                                    \
+    try { body; return 0; }                                               \
+    catch (const Error& e) { g_last_error = e.msg; return 1; }            \
+    catch (const std::exception& e) { g_last_error = e.what(); return 2; } \
+    catch (...) { g_last_error = "unknown error"; return 3; }
+
+#define MF_SOLVER(P, REAL) reinterpret_cast<Solver<REAL>*>(s)
+#define MF_NEED(s) if (!(s)) throw Error{"null solver handle"}
+
+#define MFLBM_DEFINE_API(P, REAL)                                                                                                     \
+    extern "C" int mflbm_##P##_create(const mflbm_##P##_params* params, const mflbm_slab* slab, int device, void* stream,                 \
+                                      mflbm_##P##_solver** out) {                                                                         \
+        MF_GUARD({                                                                                                                        \
+            if (!params || !out) throw Error{"create: null argument"};                                                                    \
+            auto* sv = new Solver<REAL>();                                                                                                \
+            try { sv->create(params, slab, device, stream); } catch (...) { sv->destroy(); delete sv; throw; }                            \
+            *out = reinterpret_cast<mflbm_##P##_solver*>(sv);                                                                             \
+        })                                                                                                                                \
+    }                                                                                                                                     \
+    extern "C" int mflbm_##P##_destroy(mflbm_##P##_solver* s) { MF_GUARD({ if (s) { MF_SOLVER(P, REAL)->destroy(); delete MF_SOLVER(P, REAL); } }) } \
+    extern "C" int mflbm_##P##_set_params(mflbm_##P##_solver* s, const mflbm_##P##_params* params) {                                      \
+        MF_GUARD({ MF_NEED(s); if (!params) throw Error{"null params"}; MF_SOLVER(P, REAL)->set_params(params); })                        \
+    }                                                                                                                                     \
+    extern "C" int mflbm_##P##_upload_geometry(mflbm_##P##_solver* s, const int32_t* walls, const int32_t* walls_type, const REAL* s_nx,   \
+                                               const REAL* s_ny, const REAL* s_nz) {                                                      \
+        MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->upload_geometry(walls, walls_type, s_nx, s_ny, s_nz); })                               \
+    }                                                                                                                                     \
+    extern "C" int mflbm_##P##_preprocess_geometry(mflbm_##P##_solver* s, const int8_t* w) {                                              \
+        MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->preprocess_geometry(w); })                                                             \
+    }                                                                                                                                     \
+    extern "C" int mflbm_##P##_download_geometry(mflbm_##P##_solver* s, int32_t* walls, int32_t* walls_type, REAL* s_nx, REAL* s_ny,       \
+                                                 REAL* s_nz, int64_t* counts) {                                                           \
+        MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->download_geometry(walls, walls_type, s_nx, s_ny, s_nz, counts); })                     \
+    }                                                                                                                                     \
+    extern "C" int mflbm_##P##_upload_state(mflbm_##P##_solver* s, const REAL* pdf, const REAL* phi, const REAL* cn_x, const REAL* cn_y,   \
+                                            const REAL* cn_z, const REAL* c_norm, const REAL* curv, const REAL* W_in, const REAL* f_convec, \
+                                            const REAL* g_convec, const REAL* phi_convec) {                                               \
+        MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->upload_state(pdf, phi, cn_x, cn_y, cn_z, c_norm, curv, W_in, f_convec, g_convec, phi_convec); }) \
+    }                                                                                                                                     \
+    extern "C" int mflbm_##P##_init_state(mflbm_##P##_solver* s, int option, REAL interface_z0, const REAL* W_in) {                       \
+        MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->init_state(option, interface_z0, W_in); })                                             \
+    }                                                                                                                                     \
+    extern "C" int mflbm_##P##_download_state(mflbm_##P##_solver* s, REAL* pdf, REAL* phi, REAL* cn_x, REAL* cn_y, REAL* cn_z,             \
+                                              REAL* c_norm, REAL* curv, REAL* f_convec, REAL* g_convec, REAL* phi_convec) {               \
+        MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->download_state(pdf, phi, cn_x, cn_y, cn_z, c_norm, curv, f_convec, g_convec, phi_convec); }) \
+    }                                                                                                                                     \
+    extern "C" int mflbm_##P##_step(mflbm_##P##_solver* s, int ntime) { MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->step(ntime); }) }       \
+    extern "C" int mflbm_##P##_run(mflbm_##P##_solver* s, int ntime_first, int nsteps) {                                                  \
+        MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->run(ntime_first, nsteps); })                                                           \
+    }                                                                                                                                     \
+    extern "C" int mflbm_##P##_color_gradient(mflbm_##P##_solver* s) { MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->gradient_chain(true); }) } \
+    extern "C" int mflbm_##P##_monitor(mflbm_##P##_solver* s, mflbm_monitor_out* out) { MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->monitor(out); }) } \
+    extern "C" int mflbm_##P##_sync(mflbm_##P##_solver* s) {                                                                              \
+        MF_GUARD({ MF_NEED(s); MF_CUDA(cudaStreamSynchronize(MF_SOLVER(P, REAL)->stream)); })                                             \
+    }                                                                                                                                     \
+    extern "C" int mflbm_##P##_halo_buffers(mflbm_##P##_solver* s, int kind, int side, REAL** send, REAL** recv, int64_t* count) {        \
+        MF_GUARD({                                                                                                                        \
+            MF_NEED(s);                                                                                                                   \
+            if (kind < 0 || kind > 2 || side < 0 || side > 1) throw Error{"halo_buffers: bad kind/side"};                                 \
+            if (!MF_SOLVER(P, REAL)->is_slab) throw Error{"halo_buffers on a non-slab solver"};                                           \
+            if (send) *send = MF_SOLVER(P, REAL)->d_send[kind][side];                                                                     \
+            if (recv) *recv = MF_SOLVER(P, REAL)->d_recv[kind][side];                                                                     \
+            if (count) *count = MF_SOLVER(P, REAL)->halo_count(kind);                                                                     \
+        })                                                                                                                                \
+    }                                                                                                                                     \
+    extern "C" int mflbm_##P##_halo_pack(mflbm_##P##_solver* s, int kind) { MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->halo_pack(kind); }) } \
+    extern "C" int mflbm_##P##_halo_unpack(mflbm_##P##_solver* s, int kind) { MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->halo_unpack(kind); }) } \
+    extern "C" int mflbm_##P##_step_phase(mflbm_##P##_solver* s, int ntime, int phase) {                                                  \
+        MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->step_phase(ntime, phase); })                                                           \
+    }                                                                                                                                     \
+    extern "C" int64_t mflbm_##P##_num_fluid_nodes(mflbm_##P##_solver* s) { return s ? MF_SOLVER(P, REAL)->n_fluid : -1; }                \
+    extern "C" int64_t mflbm_##P##_kernel_launches(mflbm_##P##_solver* s) { return s ? MF_SOLVER(P, REAL)->launches : -1; }               \
+    extern "C" void* mflbm_##P##_stream(mflbm_##P##_solver* s) { return s ? (void*)MF_SOLVER(P, REAL)->stream : nullptr; }                \
+    extern "C" void* mflbm_##P##_device_ptr(mflbm_##P##_solver* s, const char* name) {                                                    \
+        return (s && name) ? MF_SOLVER(P, REAL)->device_ptr(name) : nullptr;                                                              \
+    }
+
+MFLBM_DEFINE_API(f32, float)
+MFLBM_DEFINE_API(f64, double)
+
+extern "C" const char* mflbm_last_error(void) { return g_last_error.c_str(); }
+extern "C" int mflbm_version(void) { return MFLBM_VERSION; }

@@ -1,0 +1,120 @@
+"""Shared test cases and helpers (test infrastructure)."""
+from __future__ import annotations
+
+import numpy as np
+
+import refcase as rc
+
+TOL = {"f64": 1e-12, "f32": 1e-5}   # north_star: field-normalised relative tolerance on pdf / phi
+
+
+def relerr(a: np.ndarray, b: np.ndarray) -> float:
+    """field-normalised relative error max|a-b| / max|b| (hard part ii)"""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    scale = float(np.max(np.abs(b)))
+    d = float(np.max(np.abs(a - b)))
+    return d / scale if scale > 0 else d
+
+
+def case_tube_pressure():
+    """tube + sphere, drainage, Zou-He pressure inlet/outlet, porous plate blocking fluid 1 near the outlet"""
+    solid = rc.tube_sphere(20, 20, 28, buffer=4)
+    ctl = dict(initial_fluid_distribution_option=1, saturation_injection=1.0, inlet_BC=2, outlet_BC=2, theta=65,
+               initial_interface_position=6.0, porous_plate_cmd=1, Z_porous_plate=25, n_exclude_inlet=3, n_exclude_outlet=3,
+               body_force_0=1e-4)
+    return ctl, solid
+
+
+def case_pack_velocity():
+    """sphere pack, drainage, velocity inlet + convective outlet, contact angle 45"""
+    solid = rc.sphere_pack(24, 24, 32, radius=4.0, porosity=0.55, buffer=5, seed=7)
+    ctl = dict(initial_fluid_distribution_option=1, saturation_injection=1.0, inlet_BC=1, outlet_BC=1, theta=45,
+               initial_interface_position=4.0, capillary_number=1e-3, n_exclude_inlet=5, n_exclude_outlet=5, body_force_0=0.0)
+    return ctl, solid
+
+
+def case_imbibition_plate2():
+    """shipped-control flavour: imbibition, pressure/pressure, porous plate blocking fluid 2 near the outlet"""
+    solid = rc.sphere_pack(20, 20, 30, radius=3.5, porosity=0.6, buffer=5, seed=11)
+    ctl = dict(initial_fluid_distribution_option=2, saturation_injection=0.0, inlet_BC=2, outlet_BC=2, theta=65,
+               initial_interface_position=4.0, porous_plate_cmd=2, Z_porous_plate=26, n_exclude_inlet=5, n_exclude_outlet=5)
+    return ctl, solid
+
+
+def case_periodic_drop():
+    """y/z periodic, body force, a drop of fluid 1 around an obstacle: exercises the 9 periodic kernels"""
+    nx, ny, nz = 18, 16, 20
+    solid = np.zeros((nz, ny, nx), dtype=np.int8)
+    k, j, i = np.meshgrid(np.arange(1, nz + 1), np.arange(1, ny + 1), np.arange(1, nx + 1), indexing="ij")
+    solid[(i - 9.5) ** 2 + (j - 3.0) ** 2 + (k - 4.0) ** 2 < 9.0] = 1     # obstacle cut by the periodic faces
+    ctl = dict(initial_fluid_distribution_option=5, saturation_injection=1.0, inlet_BC=2, outlet_BC=2, theta=30,
+               initial_interface_position=5.0, jper=1, kper=1, domain_wall_status_y_min=0, domain_wall_status_y_max=0,
+               body_force_0=2e-5, n_exclude_inlet=0, n_exclude_outlet=0)
+    return ctl, solid
+
+
+def case_duct_no_geometry():
+    """no external geometry: open duct with the hard-coded modify_geometry obstacle (src/Misc.cpp:105)"""
+    ctl = dict(nxGlobal=16, nyGlobal=16, nzGlobal=36, modify_geometry_cmd=1, initial_fluid_distribution_option=1,
+               saturation_injection=1.0, inlet_BC=1, outlet_BC=2, theta=60, initial_interface_position=5.0, capillary_number=5e-4)
+    return ctl, None
+
+
+def case_rect_quirk():
+    """nx != ny: the reference reads the geometry with swapped strides (src/Misc.cpp:171)"""
+    solid = rc.sphere_pack(22, 18, 24, radius=3.5, porosity=0.6, buffer=4, seed=3)
+    ctl = dict(initial_fluid_distribution_option=1, saturation_injection=1.0, inlet_BC=2, outlet_BC=2, theta=50,
+               initial_interface_position=4.0)
+    return ctl, solid
+
+
+CASES = {
+    "tube_pressure": case_tube_pressure,
+    "pack_velocity": case_pack_velocity,
+    "imbibition_plate2": case_imbibition_plate2,
+    "periodic_drop": case_periodic_drop,
+    "duct_no_geometry": case_duct_no_geometry,
+    "rect_quirk": case_rect_quirk,
+}
+
+
+def full_control(name: str) -> tuple[dict, np.ndarray | None]:
+    ctl, solid = CASES[name]()
+    full = dict(rc.DEFAULT_CONTROL)
+    full.update(ctl)
+    if solid is not None:
+        nz, ny, nx = solid.shape
+        full.update(nxGlobal=nx, nyGlobal=ny, nzGlobal=nz, external_geometry_read_cmd=1)
+    else:
+        full["external_geometry_read_cmd"] = 0
+    return full, solid
+
+
+def make_oracle(name: str, prec: str):
+    from oracle import Oracle
+    ctl, solid = full_control(name)
+    o = Oracle(ctl, prec)
+    o.setup(solid)
+    return o, ctl, solid
+
+
+def solver_from_oracle(o, ctl, prec: str, **kw):
+    """A CUDA solver whose geometry and state are uploaded from an oracle context (both in reference layouts)."""
+    import mflbm
+    P = mflbm.derive_params(ctl, prec)
+    s = mflbm.Solver(P, prec, **kw)
+    s.upload_geometry(o.arr("walls"), o.arr("walls_type"), o.arr("s_nx"), o.arr("s_ny"), o.arr("s_nz"))
+    s.upload_state(pdf=o.arr("pdf"), phi=o.arr("phi"), cn_x=o.arr("cn_x"), cn_y=o.arr("cn_y"), cn_z=o.arr("cn_z"),
+                   c_norm=o.arr("c_norm"), curv=o.arr("curv"), W_in=o.arr("W_in"), f_convec=o.arr("f_convec"),
+                   g_convec=o.arr("g_convec"), phi_convec=o.arr("phi_convec"))
+    return s
+
+
+def fluid_mask(o, g: int) -> np.ndarray:
+    """boolean [nz+2g, ny+2g, nx+2g] mask of real fluid nodes"""
+    w = o.arr("walls")   # 2 ghosts
+    nz, ny, nx = o.nz, o.ny, o.nx
+    m = np.zeros((nz + 2 * g, ny + 2 * g, nx + 2 * g), dtype=bool)
+    m[g:g + nz, g:g + ny, g:g + nx] = w[2:2 + nz, 2:2 + ny, 2:2 + nx] == 0
+    return m

@@ -1,0 +1,69 @@
+"""Test infrastructure: run the reference's own GPU kernels (oracle/_ref/ref_gpu_*) on a case and fingerprint
+its state dumps.  A fingerprint = a seeded random sample of individual values plus per-slot z-slice sums: small
+enough to commit under tests/golden/, sharp enough that any real discrepancy shows."""
+from __future__ import annotations
+
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+import common
+import refcase as rc
+
+STEPS = (1, 2, 100)
+N_PDF, N_PHI = 6000, 2000
+
+
+def sample_indices(name: str, shape_pdf, shape_phi):
+    rng = np.random.Generator(np.random.PCG64(sum(map(ord, name))))
+    ip = rng.integers(0, int(np.prod(shape_pdf)), N_PDF)
+    ih = rng.integers(0, int(np.prod(shape_phi)), N_PHI)
+    return ip, ih
+
+
+def fingerprint(name: str, st: dict) -> dict:
+    pdf, phi = st["pdf"], st["phi"]
+    ip, ih = sample_indices(name, pdf.shape, phi.shape)
+    fp = dict(pdf_sample=pdf.reshape(-1)[ip].copy(), phi_sample=phi.reshape(-1)[ih].copy(),
+              pdf_slice=pdf.astype(np.float64).sum(axis=(3, 4)).reshape(38, -1), phi_slice=phi.astype(np.float64).sum(axis=(1, 2)),
+              pdf_absmax=np.float64(np.abs(pdf).max()), phi_absmax=np.float64(np.abs(phi).max()))
+    for k in ("cn_x", "c_norm", "curv"):
+        fp[k + "_slice"] = st[k].astype(np.float64).sum(axis=(1, 2))
+    return fp
+
+
+def run_reference_gpu(name: str, prec: str, steps=STEPS, monitor=()):
+    """-> (meta, geometry, {step: state}) from the reference GPU build, run live (needs a GPU)."""
+    ctl, solid = common.CASES[name]()
+    with tempfile.TemporaryDirectory() as td:
+        td = Path(td)
+        rc.write_case(td, ctl, solid)
+        out = rc.run_ref("gpu", prec, td, td / "out", dump=steps, monitor=monitor)
+        meta = rc.read_meta(out)
+        geom = rc.load_geometry(out, meta)
+        states = {0: rc.load_state(out, 0, meta)}
+        for s in steps:
+            states[s] = rc.load_state(out, s, meta)
+        mon = (out / "monitor.txt").read_text() if monitor else ""
+    return meta, geom, states, mon
+
+
+def compare_fingerprint(name: str, st: dict, gold: dict, tol: float, loose: float) -> list[str]:
+    """-> list of failures; st = full state arrays of the implementation under test, gold = reference fingerprint"""
+    fp = fingerprint(name, st)
+    bad = []
+
+    def chk(key, scale, t):
+        err = float(np.max(np.abs(np.asarray(fp[key], np.float64) - np.asarray(gold[key], np.float64)))) / scale
+        if not err <= t:
+            bad.append(f"{key}: {err:.3e} > {t:.1e}")
+    ps, hs = float(gold["pdf_absmax"]), float(gold["phi_absmax"])
+    chk("pdf_sample", ps, tol)
+    chk("phi_sample", hs, tol)
+    # slice sums add up ~nx*ny values: scale by the largest slice magnitude
+    chk("pdf_slice", max(float(np.abs(gold["pdf_slice"]).max()), 1e-300), tol)
+    chk("phi_slice", max(float(np.abs(gold["phi_slice"]).max()), 1e-300), tol)
+    for k in ("cn_x_slice", "c_norm_slice", "curv_slice"):
+        chk(k, max(float(np.abs(gold[k]).max()), 1e-300), loose)
+    return bad

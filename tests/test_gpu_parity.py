@@ -1,0 +1,173 @@
+"""CUDA path (through the C ABI) against the C oracle on the same seeded inputs.  All tests need a GPU."""
+import numpy as np
+import pytest
+
+import common
+from common import TOL, relerr
+
+pytestmark = pytest.mark.gpu
+
+ALL = sorted(common.CASES)
+DYN = ["tube_pressure", "pack_velocity", "imbibition_plate2", "periodic_drop", "duct_no_geometry", "rect_quirk"]
+
+
+def interior_walls(o):
+    return (o.arr("walls_global") != 0).astype(np.int8)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("name", ALL)
+def test_geometry_preprocessing_bit_exact(gpu_lib, name, prec):
+    import mflbm
+    o, ctl, solid = common.make_oracle(name, prec)
+    s = mflbm.Solver(mflbm.derive_params(ctl, prec), prec)
+    s.preprocess_geometry(interior_walls(o))
+    g = s.download_geometry()
+    for k in ("walls", "walls_type"):
+        assert np.array_equal(g[k], o.arr(k)), k
+    for k in ("s_nx", "s_ny", "s_nz"):
+        assert np.array_equal(g[k].view(np.uint8), o.arr(k).view(np.uint8)), f"{k} not bit-exact"
+    want = [int(o.scalar(k)) for k in ("num_solid_boundary_global", "num_fluid_boundary_global", "num_solid_boundary", "num_fluid_boundary")]
+    assert g["counts"].tolist() == want
+    assert s.num_fluid_nodes == int(o.scalar("pore_sum"))
+    s.close()
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("name", ALL)
+def test_init_state(gpu_lib, name, prec):
+    import mflbm
+    o, ctl, solid = common.make_oracle(name, prec)
+    s = mflbm.Solver(mflbm.derive_params(ctl, prec), prec)
+    s.preprocess_geometry(interior_walls(o))
+    s.init_state(ctl["initial_fluid_distribution_option"], ctl["initial_interface_position"], W_in=o.arr("W_in"))
+    st = s.download_state()
+    assert np.array_equal(st["pdf"], o.arr("pdf")), "initial pdf must be bit-exact"
+    if ctl["outlet_BC"] == 1:
+        for k in ("f_convec", "g_convec", "phi_convec"):
+            assert np.array_equal(st[k], o.arr(k)), k
+    # phi / cn / curv went through the gradient chain on the GPU (FMA contraction) -> tolerance
+    for k in ("phi", "cn_x", "cn_y", "cn_z", "c_norm", "curv"):
+        assert relerr(st[k], o.arr(k)) <= TOL[prec], (k, relerr(st[k], o.arr(k)))
+    s.close()
+
+
+@pytest.mark.parametrize("nsteps", [1, 2, 100])
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("name", DYN)
+def test_steps_match_oracle(gpu_lib, name, prec, nsteps):
+    o, ctl, solid = common.make_oracle(name, prec)
+    s = common.solver_from_oracle(o, ctl, prec)
+    for n in range(nsteps):
+        s.step(1 + n)
+    o.run(1, nsteps)
+    st = s.download_state()
+    tol = TOL[prec]
+    assert np.isfinite(st["pdf"]).all()
+    assert relerr(st["pdf"], o.arr("pdf")) <= tol, ("pdf", relerr(st["pdf"], o.arr("pdf")))
+    assert relerr(st["phi"], o.arr("phi")) <= tol, ("phi", relerr(st["phi"], o.arr("phi")))
+    # derived fields: threshold branches (c_norm < 1e-6, secant solver) may amplify rounding locally -> looser
+    for k in ("cn_x", "cn_y", "cn_z", "c_norm", "curv"):
+        assert relerr(st[k], o.arr(k)) <= 1e3 * tol, (k, relerr(st[k], o.arr(k)))
+    if ctl["outlet_BC"] == 1:
+        for k in ("f_convec", "g_convec", "phi_convec"):
+            assert relerr(st[k], o.arr(k)) <= tol, k
+    s.close()
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_run_with_graph_equals_step_loop(gpu_lib, prec):
+    o, ctl, solid = common.make_oracle("tube_pressure", prec)
+    a = common.solver_from_oracle(o, ctl, prec)
+    b = common.solver_from_oracle(o, ctl, prec)
+    for n in range(21):
+        a.step(1 + n)
+    b.run(1, 21)
+    sa, sb = a.download_state(), b.download_state()
+    for k in ("pdf", "phi", "cn_x", "c_norm", "curv"):
+        assert np.array_equal(sa[k], sb[k]), k
+    assert b.kernel_launches == a.kernel_launches
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("mrt", [1, 2, 3, 4])
+def test_mrt_variants(gpu_lib, mrt):
+    import mflbm
+    from oracle import Oracle
+    ctl, solid = common.full_control("tube_pressure")
+    o = Oracle(ctl, "f64", mrt=mrt).setup(solid)
+    P = mflbm.derive_params(ctl, "f64", mrt=mrt)
+    s = mflbm.Solver(P, "f64")
+    s.upload_geometry(o.arr("walls"), o.arr("walls_type"), o.arr("s_nx"), o.arr("s_ny"), o.arr("s_nz"))
+    s.upload_state(pdf=o.arr("pdf"), phi=o.arr("phi"), cn_x=o.arr("cn_x"), cn_y=o.arr("cn_y"), cn_z=o.arr("cn_z"), c_norm=o.arr("c_norm"),
+                   curv=o.arr("curv"))
+    s.run(1, 10)
+    o.run(1, 10)
+    st = s.download_state()
+    assert relerr(st["pdf"], o.arr("pdf")) <= TOL["f64"]
+    s.close()
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("name", ["tube_pressure", "pack_velocity"])
+def test_monitor_matches_oracle(gpu_lib, name, prec):
+    o, ctl, solid = common.make_oracle(name, prec)
+    s = common.solver_from_oracle(o, ctl, prec)
+    s.run(1, 50)
+    o.run(1, 50)
+    m = s.monitor(profiles=True)
+    mo, prof = o.monitor()
+    # the oracle sums sequentially in T like the reference; the device sums in double -> 1e-6 (north_star) in f64
+    tol = 1e-9 if prec == "f64" else 2e-4
+    assert abs(m["saturation"] - mo["saturation"]) <= tol
+    assert abs(m["saturation_full_domain"] - mo["saturation_full_domain"]) <= tol
+    assert abs(m["umax"] - mo["umax_global"]) <= tol * max(1.0, mo["umax_global"])
+    assert abs(m["ca"] - mo["ca"]) <= (1e-9 if prec == "f64" else 1e-4) * max(abs(mo["ca"]), 1e-6) + 1e-12
+    names = ["fl1", "fl2", "pre", "mass1", "mass2", "vol1", "vol2"]
+    for n, k in enumerate(names):
+        scale = np.abs(prof[n]).max() + 1e-30
+        assert np.abs(m["profiles"][k] - prof[n]).max() / scale <= (1e-9 if prec == "f64" else 1e-3), k
+    assert m["nan_detected"] == 0
+    s.close()
+
+
+def test_errors_are_reported_not_fatal(gpu_lib):
+    import ctypes as C
+    import mflbm
+    ctl, solid = common.full_control("tube_pressure")
+    P = mflbm.derive_params(ctl, "f64")
+    P.iper = 1
+    with pytest.raises(mflbm.MflbmError, match="x-periodic"):
+        mflbm.Solver(P, "f64")
+    P.iper = 0
+    s = mflbm.Solver(P, "f64")
+    with pytest.raises(mflbm.MflbmError, match="before geometry"):
+        s.step(1)
+    assert gpu_lib.mflbm_f64_step(None, 1) != 0
+    assert b"null solver" in gpu_lib.mflbm_last_error()
+    s.close()
+
+
+def test_full_size_properties_256(gpu_lib):
+    """BASELINE config 2 size (256^3 sphere pack, FP64): size-independent properties instead of an oracle run.
+    y/z-periodic + body force so that the two component masses are conserved exactly by collide/stream/bounce-back."""
+    import mflbm
+    import refcase as rc
+    n = 256
+    solid = rc.sphere_pack(n, n, n, radius=12.0, porosity=0.4, buffer=0, seed=20240229)
+    solid[:, :, 0] = 1; solid[:, :, -1] = 1   # x walls
+    ctl = dict(rc.DEFAULT_CONTROL)
+    ctl.update(nxGlobal=n, nyGlobal=n, nzGlobal=n, jper=1, kper=1, domain_wall_status_y_min=0, domain_wall_status_y_max=0,
+               initial_fluid_distribution_option=1, initial_interface_position=128.0, theta=45, body_force_0=1e-5,
+               saturation_injection=1.0, n_exclude_inlet=0, n_exclude_outlet=0)
+    s = mflbm.Solver(mflbm.derive_params(ctl, "f64"), "f64")
+    s.preprocess_geometry(solid)
+    s.init_state(1, 128.0)
+    m0 = s.monitor()
+    s.run(1, 40)
+    m1 = s.monitor()
+    assert m1["nan_detected"] == 0
+    for k in ("mass1_full", "mass2_full"):
+        assert abs(m1[k] - m0[k]) <= 1e-9 * abs(m0[k]), (k, m0[k], m1[k])
+    assert 0.0 < m1["saturation_full_domain"] < 1.0
+    s.close()

@@ -1,0 +1,101 @@
+"""Our CUDA path and the C oracle against the reference's OWN GPU kernels.
+
+  * golden (always): fingerprints of the reference GPU build's state after 1, 2 and 100 steps, committed under
+    tests/golden/ref_gpu_*.npz by tests/golden/make_golden_gpu.py (run on a B200).  The oracle is checked against
+    them on the CPU (this is what pins the oracle's time stepping); the CUDA path is checked under -m gpu.
+  * live (-m gpu, when oracle/_ref/ref_gpu_* travelled to the box): the reference binary is run on the spot and
+    compared array by array, including the monitored saturation.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import common
+import refcase as rc
+import refgpu
+from common import TOL, relerr
+
+GOLD = Path(__file__).parent / "golden"
+CASES = sorted(common.CASES)
+
+
+def load_gold(name, prec):
+    f = GOLD / f"ref_gpu_{name}_{prec}.npz"
+    if not f.exists():
+        pytest.skip(f"{f.name} not generated yet (tests/golden/make_golden_gpu.py on a GPU box)")
+    z = np.load(f)
+    return {step: {k[len(f"s{step}_"):]: z[k] for k in z.files if k.startswith(f"s{step}_")} for step in refgpu.STEPS}
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_steps_match_reference_gpu_golden(name, prec):
+    gold = load_gold(name, prec)
+    o, ctl, solid = common.make_oracle(name, prec)
+    done = 0
+    for step in refgpu.STEPS:
+        o.run(1 + done, step - done)
+        done = step
+        bad = refgpu.compare_fingerprint(name, o.state(), gold[step], TOL[prec], 1e3 * TOL[prec])
+        assert not bad, (step, bad)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("name", CASES)
+def test_cuda_steps_match_reference_gpu_golden(gpu_lib, name, prec):
+    gold = load_gold(name, prec)
+    o, ctl, solid = common.make_oracle(name, prec)
+    s = common.solver_from_oracle(o, ctl, prec)
+    done = 0
+    for step in refgpu.STEPS:
+        s.run(1 + done, step - done)
+        done = step
+        bad = refgpu.compare_fingerprint(name, s.download_state(), gold[step], TOL[prec], 1e3 * TOL[prec])
+        assert not bad, (step, bad)
+    s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("name", ["tube_pressure", "pack_velocity", "periodic_drop"])
+def test_cuda_matches_live_reference_gpu(gpu_lib, name, prec):
+    if not rc.ref_binary("gpu", prec).exists():
+        pytest.skip("oracle/_ref/ref_gpu_* not present")
+    import mflbm
+    meta, geom, states, mon = refgpu.run_reference_gpu(name, prec, steps=(1, 2, 100), monitor=(100,))
+    ctl, solid = common.full_control(name)
+    s = mflbm.Solver(mflbm.derive_params(ctl, prec), prec)
+    s.upload_geometry(geom["walls"], geom["walls_type"], geom["s_nx"], geom["s_ny"], geom["s_nz"])
+    st0 = states[0]
+    s.upload_state(pdf=st0["pdf"], phi=st0["phi"], cn_x=st0["cn_x"], cn_y=st0["cn_y"], cn_z=st0["cn_z"], c_norm=st0["c_norm"],
+                   curv=st0["curv"], W_in=geom["W_in"], f_convec=st0.get("f_convec_bc"), g_convec=st0.get("g_convec_bc"),
+                   phi_convec=st0.get("phi_convec_bc"))
+    done = 0
+    for step in (1, 2, 100):
+        s.run(1 + done, step - done)
+        done = step
+        mine = s.download_state()
+        ref = states[step]
+        for k in ("pdf", "phi"):
+            assert relerr(mine[k], ref[k]) <= TOL[prec], (step, k, relerr(mine[k], ref[k]))
+        for k in ("cn_x", "cn_y", "cn_z", "c_norm"):
+            assert relerr(mine[k], ref[k]) <= 1e3 * TOL[prec], (step, k, relerr(mine[k], ref[k]))
+        fm = common_fluid_mask(geom, 1)
+        assert relerr(np.where(fm, mine["curv"], 0), np.where(fm, ref["curv"], 0)) <= 1e3 * TOL[prec], (step, "curv")
+    # monitored saturation after 100 steps (reference: src/Monitor.cpp:118), north_star tolerance 1e-6
+    vals = mon.split()
+    sat_ref, sat_full_ref = float(vals[2]), float(vals[3])
+    m = s.monitor()
+    tol = 1e-9 if prec == "f64" else 1e-4
+    assert abs(m["saturation"] - sat_ref) <= tol and abs(m["saturation_full_domain"] - sat_full_ref) <= tol
+    s.close()
+
+
+def common_fluid_mask(geom, g):
+    w = geom["walls"]
+    nz, ny, nx = (d - 4 for d in w.shape)
+    m = np.zeros((nz + 2 * g, ny + 2 * g, nx + 2 * g), dtype=bool)
+    m[g:g + nz, g:g + ny, g:g + nx] = w[2:2 + nz, 2:2 + ny, 2:2 + nx] == 0
+    return m
