@@ -68,7 +68,8 @@ def test_steps_match_oracle(gpu_lib, name, prec, nsteps):
     assert relerr(st["phi"], o.arr("phi")) <= tol, ("phi", relerr(st["phi"], o.arr("phi")))
     # derived fields: threshold branches (c_norm < 1e-6, secant solver) may amplify rounding locally -> looser
     for k in ("cn_x", "cn_y", "cn_z", "c_norm", "curv"):
-        assert relerr(st[k], o.arr(k)) <= 1e3 * tol, (k, relerr(st[k], o.arr(k)))
+        ok, msg = common.derived_close(st[k], o.arr(k), tol)
+        assert ok, (k, msg)
     if ctl["outlet_BC"] == 1:
         for k in ("f_convec", "g_convec", "phi_convec"):
             assert relerr(st[k], o.arr(k)) <= tol, k
