@@ -84,10 +84,11 @@ def test_cuda_matches_live_reference_gpu(gpu_lib, name, prec):
         for k in ("pdf", "phi"):
             assert relerr(mine[k], ref[k]) <= TOL[prec], (step, k, relerr(mine[k], ref[k]))
         for k in ("cn_x", "cn_y", "cn_z", "c_norm"):
-            ok, msg = common.derived_close(mine[k], ref[k], TOL[prec])
+            ok, msg = common.derived_close(mine[k], ref[k], TOL[prec], common.derived_weight(ref["c_norm"], k))
             assert ok, (step, k, msg)
         fm = common_fluid_mask(geom, 1)
-        ok, msg = common.derived_close(np.where(fm, mine["curv"], 0), np.where(fm, ref["curv"], 0), TOL[prec])
+        ok, msg = common.derived_close(np.where(fm, mine["curv"], 0), np.where(fm, ref["curv"], 0), TOL[prec],
+                                       common.derived_weight(ref["c_norm"], "curv"))
         assert ok, (step, "curv", msg)
     # monitored saturation after 100 steps (reference: src/Monitor.cpp:118), north_star tolerance 1e-6
     vals = mon.split()
