@@ -46,12 +46,51 @@ def workload_control(nx: int, ny: int, nz: int) -> dict:
     return ctl
 
 
-def workload_geometry(nx: int, ny: int, nz: int, seed: int = 20240229) -> np.ndarray:
+def workload_geometry(nx: int, ny: int, nz: int, seed: int = 20240229, kind: str = "pack") -> np.ndarray:
     """interior walls after set_walls (src/Misc.cpp:59-87): sphere pack + solid x/y faces, int8 [nz, ny, nx]"""
     import refcase as rc
+    if kind == "open":   # diagnostic only: an empty duct (porosity ~1), upper bound for the kernels' bandwidth efficiency
+        solid = np.zeros((nz, ny, nx), dtype=np.int8)
+        solid[:, :, 0] = 1; solid[:, :, -1] = 1; solid[:, 0, :] = 1; solid[:, -1, :] = 1
+        return solid
     radius = 12.0 * min(nx, ny, nz) / 256.0 if min(nx, ny, nz) < 256 else 12.0
     solid = rc.sphere_pack(nx, ny, nz, radius=max(radius, 3.0), porosity=0.4, buffer=max(2, round(10 * nz / 256)), seed=seed)
     solid[:, :, 0] = 1; solid[:, :, -1] = 1; solid[:, 0, :] = 1; solid[:, -1, :] = 1
+    return solid
+
+
+def workload_geometry_window(nx: int, ny: int, nz: int, xlo: int, xhi: int, seed: int = 20240229, kind: str = "pack") -> np.ndarray:
+    """the same geometry as workload_geometry(nx, ny, nz), rasterised only for global columns xlo..xhi (1-based, clipped):
+    what one x-slab's preprocessing reads.  The array has the global shape (untouched pages are never committed)."""
+    import refcase as rc
+    xlo, xhi = max(1, xlo), min(nx, xhi)
+    solid = np.zeros((nz, ny, nx), dtype=np.int8)
+    if kind == "pack":
+        radius = 12.0 * min(nx, ny, nz) / 256.0 if min(nx, ny, nz) < 256 else 12.0
+        radius = max(radius, 3.0)
+        buffer = max(2, round(10 * nz / 256))
+        rng = np.random.Generator(np.random.MT19937(seed))
+        n = int(round(-np.log(0.4) * float(nx) * ny * nz / (4.0 / 3.0 * np.pi * radius ** 3)))
+        cx, cy, cz = rng.uniform(0.5, nx + 0.5, n), rng.uniform(0.5, ny + 0.5, n), rng.uniform(0.5, nz + 0.5, n)   # same draws as rc.sphere_pack
+        r = int(np.ceil(radius))
+        sel = (cx + r + 1 >= xlo) & (cx - r - 1 <= xhi)
+        for x0, y0, z0 in zip(cx[sel], cy[sel], cz[sel]):
+            i0, i1 = max(xlo, int(np.floor(x0)) - r), min(xhi, int(np.ceil(x0)) + r)
+            j0, j1 = max(1, int(np.floor(y0)) - r), min(ny, int(np.ceil(y0)) + r)
+            k0, k1 = max(1, int(np.floor(z0)) - r), min(nz, int(np.ceil(z0)) + r)
+            if i0 > i1 or j0 > j1 or k0 > k1:
+                continue
+            kk, jj, ii = np.meshgrid(np.arange(k0, k1 + 1), np.arange(j0, j1 + 1), np.arange(i0, i1 + 1), indexing="ij")
+            sub = solid[k0 - 1:k1, j0 - 1:j1, i0 - 1:i1]
+            sub[(ii - x0) ** 2 + (jj - y0) ** 2 + (kk - z0) ** 2 <= radius ** 2] = 1
+        solid[:buffer, :, xlo - 1:xhi] = 0
+        solid[nz - buffer:, :, xlo - 1:xhi] = 0
+    if xlo == 1:
+        solid[:, :, 0] = 1
+    if xhi == nx:
+        solid[:, :, -1] = 1
+    solid[:, 0, xlo - 1:xhi] = 1
+    solid[:, -1, xlo - 1:xhi] = 1
     return solid
 
 
@@ -167,7 +206,7 @@ def run_ours(args) -> dict:
     prec = args.prec
     rt = np.float64 if prec == "f64" else np.float32
     ctl = workload_control(S, S, S)
-    solid = workload_geometry(S, S, S)
+    solid = workload_geometry(S, S, S, kind=args.geometry)
     stream = torch.cuda.Stream()
     solver = mflbm.Solver(mflbm.derive_params(ctl, prec), prec, device=local, stream=stream.cuda_stream)
     t0 = time.perf_counter()
@@ -217,11 +256,7 @@ def run_ours(args) -> dict:
                         curv=host["curv"], f_convec=host.get("f_convec"), g_convec=host.get("g_convec"), phi_convec=host.get("phi_convec"))
     solver.run(nt, args.steps)
     mon2 = solver.monitor()
-    lib = solver.lib
-    fn = getattr(lib, f"mflbm_{prec}_download_state")
-    ptr = lambda k: host[k].ctypes.data if k in host else None
-    rc_ = fn(solver.h, ptr("pdf"), ptr("phi"), ptr("cn_x"), ptr("cn_y"), ptr("cn_z"), ptr("c_norm"), ptr("curv"), ptr("f_convec"), ptr("g_convec"), ptr("phi_convec"))
-    assert rc_ == 0
+    solver.download_state_into(host)
     t_e2e = time.perf_counter() - t0
     e2e_mlups = n_site * args.steps / 1e6 / t_e2e
     d2h = h2d + 11 * 8 * S
@@ -229,7 +264,8 @@ def run_ours(args) -> dict:
         "metric": "multiphase MLUPS (all lattice sites, reference definition src/main.cpp:270)", "value": mlups, "unit": "MLUPS",
         "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": prec, "data": "synthetic",
-        "config": {"workload": f"{S}^3 random sphere pack (radius 12, porosity ~0.4), drainage, velocity inlet + convective outlet, theta 45, {prec}",
+        "config": {"workload": (f"{S}^3 random sphere pack (radius 12, porosity ~0.4)" if args.geometry == "pack" else f"DIAGNOSTIC {S}^3 empty duct") +
+                               f", drainage, velocity inlet + convective outlet, theta 45, {prec}",
                    "lattice": [S, S, S], "fluid_nodes": n_fluid, "porosity": n_fluid / n_site, "parallelism": "1 GPU",
                    "l2": f"state {h2d / 1e9:.2f} GB >> 126 MB L2 (inputs larger than L2, no flush needed)",
                    "fluid_mlups": n_fluid * args.steps / 1e6 / (ms * 1e-3), "geometry_preprocess_s": t_geo,
@@ -295,6 +331,7 @@ def main():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--geometry", default="pack", choices=["pack", "open"], help="open = empty duct, diagnostic only (not the benchmark workload)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

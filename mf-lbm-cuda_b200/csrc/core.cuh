@@ -26,32 +26,51 @@ static_assert((float)5.5 == 5.5f && (float)1e-6 == 1e-6f && (float)1e-30 == 1e-3
 // weights, includes/Module.h:114-122 (computed in T, like the reference's static initialisers)
 template <typename T> __host__ __device__ constexpr T w_equ(int q) { return q == 0 ? T(1) / T(3) : (q < 7 ? T(1) / T(18) : T(1) / T(36)); }
 
-// Device-side view of one lattice (or x-slab).  Array layouts are the reference's (includes/Idx_gpu.cuh:52-70):
-// 1-based coordinates, x fastest, ghost widths: pdf/curv 1, cn_*/c_norm/walls 2, phi/walls_type/s_n* 4.
+// Device-side view of one lattice (or x-slab).
+//
+// Memory layout in HBM (internal; the C ABI converts from/to the reference's layouts, includes/Idx_gpu.cuh:52-70):
+//
+//  * "U" grid: ONE dense index space for every per-site scalar (phi, cn_x/y/z, c_norm, node types, the site->PDF
+//    map): 1-based coordinates with 4 ghost layers, x fastest, row pitch PX padded to a multiple of 16 elements:
+//        u(x,y,z) = (x+3) + PX*((y+3) + PY*(z+3)),   neighbour in direction q = u + ex + PX*(ey + PY*ez).
+//    The reference keeps four different ghost widths (0/1/2/4) and hence four index spaces; one space means a kernel
+//    decodes a site once and every stencil offset is the same constant for every field.
+//  * PDFs: struct-of-arrays over the 38 slots like the reference (slot = e + 19*g), but the SITE order inside a slot
+//    is permuted: the n_fluid real fluid nodes first (in z,y,x order), then every other site of the 1-ghost box.
+//        pdf[(q + 19*g)*NC + cmap[u]]
+//    The collide kernels run one thread per entry of the fluid range: warps are full, the even (local) step reads and
+//    writes perfectly contiguous, aligned rows, and no DRAM sector is shared between fluid and solid sites.  Solid
+//    and ghost sites keep their storage (the reference realises bounce-back through it).
+//  * curv is only ever consumed at fluid nodes: stored in the same compact order (curv_c[t]).
 template <typename T>
 struct Lattice {
     int nx, ny, nz;          // real nodes of this lattice (slab-local nx)
-    int NX1, NY1, NZ1, NX2, NY2, NZ2, NX4, NY4, NZ4;
-    long long N1;            // cells of a 1-ghost array = stride between PDF slots
+    int NX1, NY1, NZ1;       // 1-ghost extents (reference layout of W_in / convective buffers / the boundary arrays)
+    int PX, PY, PZ;          // U grid extents (PX padded)
+    int sy, sz;              // U strides: PX, PX*PY
     int x0;                  // global x of local column 1 (1 for a full lattice)
     int nx_global;
+    int n_fluid;             // real fluid nodes = threads of the collide kernels
+    long long NC;            // entries per PDF slot (>= (nx+2)(ny+2)(nz+2), multiple of 32)
     // state
-    T* pdf; T* phi; T* cn_x; T* cn_y; T* cn_z; T* c_norm; T* curv;
+    T* pdf; T* phi; T* cn_x; T* cn_y; T* cn_z; T* c_norm; T* curv_c;
     T* W_in; T* f_convec; T* g_convec; T* phi_convec;
     // geometry
-    const int* walls;        // s2, 0 fluid / 1 solid
-    const int* walls_type;   // s4, 0 fluid, -1 fluid boundary, 1 solid, 2 solid boundary
-    const uint8_t* solid1;   // s1 copy of walls as bytes (the collide kernels read 1 B per site)
-    const T* s_nx; const T* s_ny; const T* s_nz;
+    const signed char* types;   // U: 0 fluid, -1 fluid boundary, 1 solid, 2 solid boundary (walls_type, Geometry_preprocessing.cpp:154-175)
+    const int* cmap;            // U: index of the site inside a PDF slot, -1 outside the 1-ghost box
+    const int* fl_u;            // [n_fluid] U index of the t-th fluid node
     // constants uploaded by copyConstantData in the reference (src/main_iteration_GPU.cu:14-47)
     T lbm_gamma, force_z, la_nui1, la_nui2, lbm_beta, RK_weight2, phi_inlet, relaxation, sa_inject, uin_avg, cos_theta;
     T rho_in, rho_out;
     int Z_porous_plate, porous_plate_cmd;
 
-    __device__ __forceinline__ int i1(int x, int y, int z) const { return x + NX1 * (y + NY1 * z); }
-    __device__ __forceinline__ int i2(int x, int y, int z) const { return (x + 1) + NX2 * ((y + 1) + NY2 * (z + 1)); }
-    __device__ __forceinline__ int i4(int x, int y, int z) const { return (x + 3) + NX4 * ((y + 3) + NY4 * (z + 3)); }
-    __device__ __forceinline__ T* slot(int q, int g) const { return pdf + (long long)(q + 19 * g) * N1; }
+    __device__ __forceinline__ int u(int x, int y, int z) const { return (x + 3) + PX * ((y + 3) + PY * (z + 3)); }
+    __device__ __forceinline__ int off(int q) const { return ex(q) + sy * ey(q) + sz * ez(q); }
+    __device__ __forceinline__ int iplane(int x, int y) const { return x + NX1 * y; }          // W_in, *_convec
+    __device__ __forceinline__ bool solid(int uu) const { return types[uu] > 0; }
+    __device__ __forceinline__ T* slot(int q, int g) const { return pdf + (long long)(q + 19 * g) * NC; }
+    // PDF of slot (q,g) at the site with U index uu (must lie in the 1-ghost box)
+    __device__ __forceinline__ T& f(int q, int g, int uu) const { return pdf[(long long)(q + 19 * g) * NC + cmap[uu]]; }
 };
 
 // MRT relaxation rates, src/main_iteration_GPU.cu:157-186.  MRT is a template parameter so that the compiler folds

@@ -143,6 +143,75 @@ __global__ void k_geo_export(GeoDims D, Iso8Tables tab, const int8_t* __restrict
 }
 
 // =====================================================================================================
+// layout conversion between the reference's boundary layouts (includes/Idx_gpu.cuh:52-70, ghost width G, x fastest,
+// dense) and the internal U grid / permuted PDF slots (core.cuh).  Threads run over the G-ghost box.
+// =====================================================================================================
+template <typename T, typename S, bool TO_U>
+__global__ void k_repitch(const Lattice<T> L, const int G, S* __restrict__ ref, S* __restrict__ ugrid) {
+    const int x = 1 - G + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int y = 1 - G + (int)blockIdx.y, z = 1 - G + (int)blockIdx.z;
+    if (x > L.nx + G) return;
+    const long long r = (x + G - 1) + (long long)(L.nx + 2 * G) * ((y + G - 1) + (long long)(L.ny + 2 * G) * (z + G - 1));
+    if (TO_U) ugrid[L.u(x, y, z)] = ref[r]; else ref[r] = ugrid[L.u(x, y, z)];
+}
+
+// walls_type (s4, int32) -> node types (U, int8); padding cells of the U rows are marked solid
+template <typename T>
+__global__ void k_types_to_u(const Lattice<T> L, const int* __restrict__ wtype_s4, signed char* __restrict__ types) {
+    const int px = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int py = (int)blockIdx.y, pz = (int)blockIdx.z;
+    if (px >= L.PX) return;
+    const int NX4 = L.nx + 8, NY4 = L.ny + 8;
+    signed char t = 1;
+    if (px < NX4) t = (signed char)wtype_s4[px + (long long)NX4 * (py + (long long)NY4 * pz)];
+    types[px + L.PX * (py + L.PY * pz)] = t;
+}
+
+// node types (U) -> the reference's walls (s2) and walls_type (s4) arrays (download_geometry)
+template <typename T>
+__global__ void k_types_from_u(const Lattice<T> L, int* __restrict__ walls_s2, int* __restrict__ wtype_s4) {
+    const int x = -3 + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int y = -3 + (int)blockIdx.y, z = -3 + (int)blockIdx.z;
+    if (x > L.nx + 4) return;
+    const int t = L.types[L.u(x, y, z)];
+    wtype_s4[(x + 3) + (long long)(L.nx + 8) * ((y + 3) + (long long)(L.ny + 8) * (z + 3))] = t;
+    if (x >= -1 && x <= L.nx + 2 && y >= -1 && y <= L.ny + 2 && z >= -1 && z <= L.nz + 2)
+        walls_s2[(x + 1) + (long long)(L.nx + 4) * ((y + 1) + (long long)(L.ny + 4) * (z + 1))] = t > 0 ? 1 : 0;
+}
+
+// s4 array <-> values in list order (solid-surface normals live only on the fluid-boundary list)
+template <typename T, bool GATHER>
+__global__ void k_list_s4(const Lattice<T> L, const int* __restrict__ list, const int count, T* __restrict__ s4, T* __restrict__ compact) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const int u = list[t];
+    const int px = u % L.PX, r = u / L.PX, py = r % L.PY, pz = r / L.PY;
+    const long long c4 = px + (long long)(L.nx + 8) * (py + (long long)(L.ny + 8) * pz);
+    if (GATHER) compact[t] = s4[c4]; else s4[c4] = compact[t];
+}
+
+// one PDF slot: dense 1-ghost array (reference order) <-> permuted slot
+template <typename T, bool TO_SLOT>
+__global__ void k_pdf_slot(const Lattice<T> L, T* __restrict__ dense_s1, T* __restrict__ slot) {
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int y = (int)blockIdx.y, z = (int)blockIdx.z;
+    if (x > L.nx + 1) return;
+    const long long c1 = x + (long long)L.NX1 * (y + (long long)L.NY1 * z);
+    const int e = L.cmap[L.u(x, y, z)];
+    if (TO_SLOT) slot[e] = dense_s1[c1]; else dense_s1[c1] = slot[e];
+}
+
+// curv: reference 1-ghost array -> fluid-node order (upload_state)
+template <typename T>
+__global__ void k_curv_gather(const Lattice<T> L, const T* __restrict__ curv_s1) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= L.n_fluid) return;
+    const int u = L.fl_u[t];
+    const int px = u % L.PX, r = u / L.PX, py = r % L.PY, pz = r / L.PY;   // = x+3, y+3, z+3
+    L.curv_c[t] = curv_s1[(px - 3) + (long long)L.NX1 * ((py - 3) + (long long)L.NY1 * (pz - 3))];
+}
+
+// =====================================================================================================
 // initial state: src/Init_multiphase.cpp:299-496 (options 1-5), u = v = w = 0, rho = 1
 // =====================================================================================================
 template <typename T>
@@ -171,7 +240,7 @@ __global__ void k_init_phi(const Lattice<T> L, int option, T interface_z0, int n
         }
     }
     if (open_z && k <= 0) { ph = L.phi_inlet; set = true; }
-    if (set) L.phi[L.i4(i, j, k)] = ph;
+    if (set) L.phi[L.u(i, j, k)] = ph;
 }
 
 template <typename T>
@@ -180,17 +249,18 @@ __global__ void k_init_pdf(const Lattice<T> L, int outlet_convective) {
     const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     const int j = (int)blockIdx.y, k = (int)blockIdx.z;
     if (i > L.nx + 1) return;
-    const T ph = L.phi[L.i4(i, j, k)];
+    const int u = L.u(i, j, k);
+    const T ph = L.phi[u];
     const T rho1 = mul_rn(mul_rn(T(1), add_rn(T(1), ph)), lit<T>(0.5));
     const T rho2 = mul_rn(mul_rn(T(1), sub_rn(T(1), ph)), lit<T>(0.5));
-    const int c1 = L.i1(i, j, k);
+    const int e = L.cmap[u];
 #pragma unroll
     for (int q = 0; q < 19; q++) {
-        L.slot(q, 0)[c1] = mul_rn(rho1, w_equ<T>(q));
-        L.slot(q, 1)[c1] = mul_rn(rho2, w_equ<T>(q));
+        L.slot(q, 0)[e] = mul_rn(rho1, w_equ<T>(q));
+        L.slot(q, 1)[e] = mul_rn(rho2, w_equ<T>(q));
     }
     if (outlet_convective && k == L.nz) {   // :445-494
-        const int cb = L.i1(i, j, 0), plane = L.NX1 * L.NY1;
+        const int cb = L.iplane(i, j), plane = L.NX1 * L.NY1;
 #pragma unroll
         for (int q = 0; q < 19; q++) {
             L.f_convec[cb + plane * q] = mul_rn(rho1, w_equ<T>(q));
@@ -201,36 +271,36 @@ __global__ void k_init_pdf(const Lattice<T> L, int outlet_convective) {
 }
 
 // =====================================================================================================
-// monitor: compute_macro_vars (src/Misc.cpp:222-274) + per-slice sums (src/Monitor.cpp:34-80) in one pass.
-// One block per z slice; sums in double (the reference sums sequentially in T).
+// monitor: compute_macro_vars (src/Misc.cpp:222-274) + per-slice sums (src/Monitor.cpp:34-80) in one pass, on the
+// device (the reference copies the whole state to the host and loops there).  One block per z slice; the fluid
+// nodes of a slice are the contiguous range [zstart[k-1], zstart[k]) of the permuted order, so every PDF read is
+// a contiguous row.  Warp-shuffle + block reduction, sums in double (the reference sums sequentially in T; see
+// DESIGN.md).
 // out layout per slice k-1: [0..6] fl1, fl2, pre, mass1, mass2, vol1, vol2, [7] max |u|^2, [8] usq1, [9] usq2, [10] nan flag
 // =====================================================================================================
 #define MFLBM_MON_N 11
 template <typename T>
-__global__ void __launch_bounds__(256) k_monitor(const Lattice<T> L, double* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_monitor(const Lattice<T> L, const int* __restrict__ zstart, double* __restrict__ out) {
     const int k = 1 + blockIdx.x;
     double acc[MFLBM_MON_N];
 #pragma unroll
     for (int n = 0; n < MFLBM_MON_N; n++) acc[n] = 0.0;
-    const int plane = L.nx * L.ny;
-    for (int t = threadIdx.x; t < plane; t += blockDim.x) {
-        const int i = 1 + t % L.nx, j = 1 + t / L.nx;
-        const int c1 = L.i1(i, j, k);
-        if (L.solid1[c1]) continue;
+    const int t0 = zstart[k - 1], t1 = zstart[k];
+    for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
+        const int u = L.fl_u[t];
         T ft[19];
 #pragma unroll
-        for (int q = 0; q < 19; q++) ft[q] = L.slot(q, 0)[c1] + L.slot(q, 1)[c1];
+        for (int q = 0; q < 19; q++) ft[q] = L.slot(q, 0)[t] + L.slot(q, 1)[t];
         T rho = ft[0];
 #pragma unroll
         for (int q = 1; q < 19; q++) rho = rho + ft[q];
-        const int c2 = L.i2(i, j, k);
-        const T tmp = lit<T>(0.5) * L.lbm_gamma * L.curv[c1] * L.c_norm[c2];
-        const T fx = tmp * L.cn_x[c2], fy = tmp * L.cn_y[c2], fz = tmp * L.cn_z[c2] + L.force_z;
-        const T u = ft[1] - ft[2] + ft[7] - ft[8] + ft[9] - ft[10] + ft[11] - ft[12] + ft[13] - ft[14] - lit<T>(0.5) * fx;
+        const T tmp = lit<T>(0.5) * L.lbm_gamma * L.curv_c[t] * L.c_norm[u];
+        const T fx = tmp * L.cn_x[u], fy = tmp * L.cn_y[u], fz = tmp * L.cn_z[u] + L.force_z;
+        const T uu = ft[1] - ft[2] + ft[7] - ft[8] + ft[9] - ft[10] + ft[11] - ft[12] + ft[13] - ft[14] - lit<T>(0.5) * fx;
         const T v = ft[3] - ft[4] + ft[7] + ft[8] - ft[9] - ft[10] + ft[15] - ft[16] + ft[17] - ft[18] - lit<T>(0.5) * fy;
         const T w = ft[5] - ft[6] + ft[11] + ft[12] - ft[13] - ft[14] + ft[15] + ft[16] - ft[17] - ft[18] - lit<T>(0.5) * fz;
-        const T ph = L.phi[L.i4(i, j, k)];
-        const T usq = u * u + v * v + w * w;
+        const T ph = L.phi[u];
+        const T usq = uu * uu + v * v + w * w;
         const double hp = (double)(lit<T>(0.5) * (lit<T>(1.) + ph)), hm = (double)(lit<T>(0.5) * (lit<T>(1.) - ph));
         acc[0] += (double)w * hp; acc[1] += (double)w * hm; acc[2] += (double)rho;
         acc[3] += (double)rho * hp; acc[4] += (double)rho * hm; acc[5] += hp; acc[6] += hm;
@@ -275,13 +345,13 @@ __global__ void k_halo_pdf(const Lattice<T> L, T* __restrict__ buf, const int co
     const int y = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
     if (y >= L.NY1) return;
     const int plane = L.NY1 * L.NZ1;
-    const int c1 = L.i1(col, y, z);
+    const int e = L.cmap[L.u(col, y, z)];
 #pragma unroll
     for (int g = 0; g < 2; g++) {
 #pragma unroll
         for (int n = 0; n < 5; n++) {
             const int q = PLUS ? slot_exp(n) : slot_exm(n);
-            T* cell = L.slot(q, g) + c1;
+            T* cell = L.slot(q, g) + e;
             T* b = buf + (long long)(g * 5 + n) * plane + (y + L.NY1 * z);
             if (PACK) *b = *cell; else *cell = *b;
         }
@@ -292,12 +362,12 @@ __global__ void k_halo_pdf(const Lattice<T> L, T* __restrict__ buf, const int co
 template <typename T, bool PACK>
 __global__ void k_halo_phi(const Lattice<T> L, T* __restrict__ buf, const int col0) {
     const int y = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;   // 0-based over the 4-ghost extents
-    if (y >= L.NY4) return;
-    const int plane = L.NY4 * L.NZ4;
+    if (y >= L.PY) return;
+    const int plane = L.PY * L.PZ;
 #pragma unroll
     for (int n = 0; n < 4; n++) {
-        T* cell = L.phi + ((col0 + n + 3) + L.NX4 * (y + L.NY4 * z));
-        T* b = buf + (long long)n * plane + (y + L.NY4 * z);
+        T* cell = L.phi + ((col0 + n + 3) + L.PX * (y + L.PY * z));
+        T* b = buf + (long long)n * plane + (y + L.PY * z);
         if (PACK) *b = *cell; else *cell = *b;
     }
 }

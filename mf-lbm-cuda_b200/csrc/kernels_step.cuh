@@ -1,6 +1,7 @@
 // kernels_step.cuh — the per-time-step kernels: AA-pattern collide+stream, colour-gradient chain, open/periodic
 // boundary kernels, porous plate.  sm_100a, plain SIMT (nothing on this path is a dense contraction).
 // Reference citations are relative to /root/reference/src/main_iteration_GPU.cu unless a file is named.
+// Index spaces (U grid, permuted PDF slots) are described in core.cuh.
 #pragma once
 #include "core.cuh"
 
@@ -9,83 +10,79 @@ namespace mflbm {
 // =====================================================================================================
 // collide + stream, AA pattern.  ODD: pull f_q from x-e_q (slot q), collide, push f_q* to x+e_q (slot opc(q))
 // (:56-388).  EVEN: read local slot opc(q) as f_q, collide, write local slot q (:395-726).
-// One thread per node, x fastest => every one of the 38 loads / 38 stores of a warp is one coalesced row segment.
+//
+// One thread per FLUID node, in the permuted site order of the PDF slots (core.cuh): thread t owns entry t of every
+// slot.  EVEN is a pure streaming kernel: 38 contiguous, 128-byte aligned row reads and 38 row writes per warp, no
+// index traffic.  ODD gathers/scatters through the site map: the 18 neighbour entries of a node are looked up once
+// (cmap is 4 B per lattice site, L2-resident) and used for both the pull (x - e_q = x + e_opc(q)) and the push.
 // Solid and ghost storage is live: fluid nodes write into / read from solid neighbours, which is how the reference
-// realises (two-step-delayed) bounce-back; this kernel keeps that data flow bit for bit.
+// realises (two-step-delayed) bounce-back; the data flow is kept bit for bit.
 // =====================================================================================================
 template <typename T, int MRT, bool ODD>
-__global__ void __launch_bounds__(128) k_collide(const Lattice<T> L, const int ilo, const int ihi) {
-    const int i = ilo + blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
-    const int k = 1 + blockIdx.z;
-    if (i > ihi || j > L.ny) return;
-    const int c1 = L.i1(i, j, k);
-    if (L.solid1[c1]) return;
-
+__global__ void __launch_bounds__(128) k_collide(const Lattice<T> L) {
+    const int t = blockIdx.x * 128 + threadIdx.x;
+    if (t >= L.n_fluid) return;
+    const int u = L.fl_u[t];
+    const long long NC = L.NC;
     T g1[19], g2[19];
-    const long long N1 = L.N1;
+    int nb[19];
     const T* __restrict__ p0 = L.pdf;
     if (ODD) {
+        nb[0] = t;
+#pragma unroll
+        for (int q = 1; q < 19; q++) nb[q] = L.cmap[u + L.off(q)];
 #pragma unroll
         for (int q = 0; q < 19; q++) {
-            const int src = c1 - (ex(q) + L.NX1 * (ey(q) + L.NY1 * ez(q)));
-            g1[q] = p0[(long long)q * N1 + src];
-            g2[q] = p0[(long long)(q + 19) * N1 + src];
+            g1[q] = p0[(long long)q * NC + nb[opc(q)]];
+            g2[q] = p0[(long long)(q + 19) * NC + nb[opc(q)]];
         }
     } else {
 #pragma unroll
         for (int q = 0; q < 19; q++) {
-            g1[q] = p0[(long long)opc(q) * N1 + c1];
-            g2[q] = p0[(long long)(opc(q) + 19) * N1 + c1];
+            g1[q] = p0[(long long)opc(q) * NC + t];
+            g2[q] = p0[(long long)(opc(q) + 19) * NC + t];
         }
     }
-    const int c2 = L.i2(i, j, k);
-    const T cnx = L.cn_x[c2], cny = L.cn_y[c2], cnz = L.cn_z[c2];
-    const T tmp = lit<T>(0.5) * L.lbm_gamma * L.curv[c1] * L.c_norm[c2];   // :147
+    const T cnx = L.cn_x[u], cny = L.cn_y[u], cnz = L.cn_z[u];
+    const T tmp = lit<T>(0.5) * L.lbm_gamma * L.curv_c[t] * L.c_norm[u];   // :147
 
     const T phi_loc = collide_node<T, MRT>(L, g1, g2, cnx, cny, cnz, tmp);
-    L.phi[L.i4(i, j, k)] = phi_loc;
+    L.phi[u] = phi_loc;
 
     T* __restrict__ po = L.pdf;
     if (ODD) {
 #pragma unroll
         for (int q = 0; q < 19; q++) {
-            const int dst = c1 + (ex(q) + L.NX1 * (ey(q) + L.NY1 * ez(q)));
-            po[(long long)opc(q) * N1 + dst] = g1[q];
-            po[(long long)(opc(q) + 19) * N1 + dst] = g2[q];
+            po[(long long)opc(q) * NC + nb[q]] = g1[q];
+            po[(long long)(opc(q) + 19) * NC + nb[q]] = g2[q];
         }
     } else {
 #pragma unroll
         for (int q = 0; q < 19; q++) {
-            po[(long long)q * N1 + c1] = g1[q];
-            po[(long long)(q + 19) * N1 + c1] = g2[q];
+            po[(long long)q * NC + t] = g1[q];
+            po[(long long)(q + 19) * NC + t] = g2[q];
         }
     }
 }
 
 // =====================================================================================================
-// colour-gradient chain (:732-1003).  Boundary-node stages run over compact index lists built once per geometry
-// (the reference scans the whole volume for them).
+// colour-gradient chain (:732-1003).  Every stage runs over a compact site list built once per geometry (the
+// reference scans the whole volume five times per step); lists are in z,y,x order so that consecutive threads
+// touch consecutive x.
 // =====================================================================================================
-// decode an s4 linear index into 1-based coordinates
-template <typename T>
-__device__ __forceinline__ void decode4(const Lattice<T>& L, int n, int& i, int& j, int& k) {
-    const int x = n % L.NX4;
-    const int r = n / L.NX4;
-    i = x - 3; j = r % L.NY4 - 3; k = r / L.NY4 - 3;
-}
 
-// phi at solid-boundary nodes <- weighted mean over D3Q18 neighbours that are fluid (:732-755)
+// phi at solid-boundary nodes <- weighted mean over the D3Q18 neighbours that are fluid (:732-755).
+// mask bit (q-1) = neighbour q has walls_type <= 0 (precomputed: replaces 18 flag loads per node and step).
 template <typename T>
-__global__ void k_extrap_phi(const Lattice<T> L, const int* __restrict__ list, const int count) {
+__global__ void k_extrap_phi(const Lattice<T> L, const int* __restrict__ list, const int* __restrict__ mask, const int count) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
     const int n = list[t];
+    const int m = mask[t];
     T phi_sum = T(0), weight_sum = T(0);
 #pragma unroll
     for (int q = 1; q < 19; q++) {
-        const int nb = n + ex(q) + L.NX4 * (ey(q) + L.NY4 * ez(q));
-        if (L.walls_type[nb] <= 0) { phi_sum += L.phi[nb] * w_equ<T>(q); weight_sum += w_equ<T>(q); }
+        if (m & (1 << (q - 1))) { phi_sum += L.phi[n + L.off(q)] * w_equ<T>(q); weight_sum += w_equ<T>(q); }
     }
     L.phi[n] = phi_sum / weight_sum;
 }
@@ -110,41 +107,44 @@ __device__ __forceinline__ T iso4(const T* __restrict__ p, const int c, const in
     return ISO4_0 * axis + ISO4_1 * s;
 }
 
-// interface normals from the phase-field gradient (:757-807), over [-1..n+2]^3 exactly (the reference's guard
-// over-runs by one; not replicated).  SKIP_SOLID: leave solid nodes untouched (they already hold 0
-// and are never read before being rewritten) instead of re-zeroing them every step.
-template <typename T, bool SKIP_SOLID>
-__global__ void __launch_bounds__(128) k_normals(const Lattice<T> L, const int ilo, const int ihi) {
-    const int i = ilo + blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = -1 + (int)(blockIdx.y * blockDim.y + threadIdx.y);
-    const int k = -1 + (int)blockIdx.z;
-    if (i > ihi || j > L.ny + 2) return;
-    const int c2 = L.i2(i, j, k);
-    const bool solid = L.walls[c2] == 1;
-    if (SKIP_SOLID && solid) return;
-    const int c4 = L.i4(i, j, k);
-    T gx = iso4<T, 0>(L.phi, c4, L.NX4, L.NX4 * L.NY4);
-    T gy = iso4<T, 1>(L.phi, c4, L.NX4, L.NX4 * L.NY4);
-    T gz = iso4<T, 2>(L.phi, c4, L.NX4, L.NX4 * L.NY4);
+// interface normals from the phase-field gradient (:757-807) at the non-solid sites of [-1..n+2]^3 (the reference's
+// guard over-runs by one; not replicated).  Solid sites hold 0 from k_zero_solid_normals and are
+// never written again, which is what the reference stores there every step.
+template <typename T>
+__global__ void __launch_bounds__(128) k_normals(const Lattice<T> L, const int* __restrict__ list, const int count) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const int u = list[t];
+    T gx = iso4<T, 0>(L.phi, u, L.sy, L.sz);
+    T gy = iso4<T, 1>(L.phi, u, L.sy, L.sz);
+    T gz = iso4<T, 2>(L.phi, u, L.sy, L.sz);
     T nrm = sqrt(gx * gx + gy * gy + gz * gz);
-    if (nrm < lit<T>(1e-6) || solid) { gx = T(0); gy = T(0); gz = T(0); nrm = T(0); }
+    if (nrm < lit<T>(1e-6)) { gx = T(0); gy = T(0); gz = T(0); nrm = T(0); }
     else { gx = gx / nrm; gy = gy / nrm; gz = gz / nrm; }
-    L.cn_x[c2] = gx; L.cn_y[c2] = gy; L.cn_z[c2] = gz; L.c_norm[c2] = nrm;
+    L.cn_x[u] = gx; L.cn_y[u] = gy; L.cn_z[u] = gz; L.c_norm[u] = nrm;
+}
+
+// cn_* = c_norm = 0 at every solid site of [-1..n+2]^3 (:795-800); run once after the arrays are (re)initialised
+template <typename T>
+__global__ void k_zero_solid_normals(const Lattice<T> L) {
+    const int i = -1 + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int j = -1 + (int)blockIdx.y, k = -1 + (int)blockIdx.z;
+    if (i > L.nx + 2) return;
+    const int u = L.u(i, j, k);
+    if (L.types[u] > 0) { L.cn_x[u] = T(0); L.cn_y[u] = T(0); L.cn_z[u] = T(0); L.c_norm[u] = T(0); }
 }
 
 // geometrical wetting model on fluid-boundary nodes: rotate cn so that n_w . cn = cos(theta), <= 4 secant
-// iterations (:809-878)
+// iterations (:809-878).  snx/sny/snz: solid-surface normals in list order.
 template <typename T>
-__global__ void k_alter(const Lattice<T> L, const int* __restrict__ list, const int count) {
+__global__ void k_alter(const Lattice<T> L, const int* __restrict__ list, const T* __restrict__ snx, const T* __restrict__ sny,
+                        const T* __restrict__ snz, const int count) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
-    const int n4 = list[t];
-    int i, j, k;
-    decode4(L, n4, i, j, k);
-    const int c2 = L.i2(i, j, k);
+    const int c2 = list[t];
     const T lambda = lit<T>(0.5), local_eps = lit<T>(1e-6), ct = L.cos_theta;
     if (!(L.c_norm[c2] > local_eps)) return;
-    const T nwx = L.s_nx[n4], nwy = L.s_ny[n4], nwz = L.s_nz[n4];
+    const T nwx = snx[t], nwy = sny[t], nwz = snz[t];
     T vcx0 = L.cn_x[c2], vcy0 = L.cn_y[c2], vcz0 = L.cn_z[c2];
     T vcx1 = vcx0 - lambda * (vcx0 + nwx), vcy1 = vcy0 - lambda * (vcy0 + nwy), vcz1 = vcz0 - lambda * (vcz0 + nwz);
     T vcx2, vcy2, vcz2, err0, err1, err2, tmp;
@@ -172,46 +172,54 @@ __global__ void k_alter(const Lattice<T> L, const int* __restrict__ list, const 
     }
 }
 
-// cn at solid-boundary nodes <- weighted mean of the fluid neighbours' cn (:880-906)
+// cn at solid-boundary nodes <- weighted mean of the fluid neighbours' cn (:880-906); mask as in k_extrap_phi
 template <typename T>
-__global__ void k_extrap_cn(const Lattice<T> L, const int* __restrict__ list, const int count) {
+__global__ void k_extrap_cn(const Lattice<T> L, const int* __restrict__ list, const int* __restrict__ mask, const int count) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
-    const int n4 = list[t];
-    int i, j, k;
-    decode4(L, n4, i, j, k);
-    const int c2 = L.i2(i, j, k);
+    const int c2 = list[t];
+    const int m = mask[t];
     T sx = T(0), sy = T(0), sz = T(0), wsum = T(0);
 #pragma unroll
     for (int q = 1; q < 19; q++) {
-        if (L.walls_type[n4 + ex(q) + L.NX4 * (ey(q) + L.NY4 * ez(q))] <= 0) {
-            const int nb = c2 + ex(q) + L.NX2 * (ey(q) + L.NY2 * ez(q));
+        if (m & (1 << (q - 1))) {
+            const int nb = c2 + L.off(q);
             sx += L.cn_x[nb] * w_equ<T>(q); sy += L.cn_y[nb] * w_equ<T>(q); sz += L.cn_z[nb] * w_equ<T>(q); wsum += w_equ<T>(q);
         }
     }
     L.cn_x[c2] = sx / wsum; L.cn_y[c2] = sy / wsum; L.cn_z[c2] = sz / wsum;
 }
 
-// interface curvature from nine derivatives of cn (:908-1003).  FLUID_ONLY: only where the value is consumed
-// (collide and the monitor read curv at fluid nodes only); the dense variant reproduces the reference array.
+// interface curvature from nine derivatives of cn (:908-1003) at U index c2.
 // cn*cn replaces the reference's pow(cn, 2) (<= 2 ulp apart in double).
-template <typename T, bool FLUID_ONLY>
-__global__ void __launch_bounds__(128) k_curvature(const Lattice<T> L, const int ilo, const int ihi) {
-    const int i = ilo + blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
-    const int k = 1 + blockIdx.z;
-    if (i > ihi || j > L.ny) return;
-    const int c1 = L.i1(i, j, k);
-    if (FLUID_ONLY && L.solid1[c1]) return;
-    const int c2 = L.i2(i, j, k);
-    const int sy = L.NX2, sz = L.NX2 * L.NY2;
+template <typename T>
+__device__ __forceinline__ T curvature_at(const Lattice<T>& L, const int c2) {
+    const int sy = L.sy, sz = L.sz;
     const T kxx = iso4<T, 0>(L.cn_x, c2, sy, sz), kyy = iso4<T, 1>(L.cn_y, c2, sy, sz), kzz = iso4<T, 2>(L.cn_z, c2, sy, sz);
     const T kxy = iso4<T, 1>(L.cn_x, c2, sy, sz), kxz = iso4<T, 2>(L.cn_x, c2, sy, sz);
     const T kyx = iso4<T, 0>(L.cn_y, c2, sy, sz), kyz = iso4<T, 2>(L.cn_y, c2, sy, sz);
     const T kzx = iso4<T, 0>(L.cn_z, c2, sy, sz), kzy = iso4<T, 1>(L.cn_z, c2, sy, sz);
     const T cx = L.cn_x[c2], cy = L.cn_y[c2], cz = L.cn_z[c2];
-    L.curv[c1] = (cx * cx - lit<T>(1.)) * kxx + (cy * cy - lit<T>(1.)) * kyy + (cz * cz - lit<T>(1.)) * kzz +
-                 cx * cy * (kxy + kyx) + cx * cz * (kxz + kzx) + cy * cz * (kzy + kyz);
+    return (cx * cx - lit<T>(1.)) * kxx + (cy * cy - lit<T>(1.)) * kyy + (cz * cz - lit<T>(1.)) * kzz +
+           cx * cy * (kxy + kyx) + cx * cz * (kxz + kzx) + cy * cz * (kzy + kyz);
+}
+
+// stepping path: curvature where it is consumed (collide and the monitor read curv at fluid nodes only), stored in
+// the fluid-node order of the PDF slots
+template <typename T>
+__global__ void __launch_bounds__(128) k_curvature(const Lattice<T> L) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= L.n_fluid) return;
+    L.curv_c[t] = curvature_at(L, L.fl_u[t]);
+}
+
+// boundary array: the reference's dense curv over [1..n]^3 in its own 1-ghost layout (download_state only)
+template <typename T>
+__global__ void __launch_bounds__(128) k_curvature_dense(const Lattice<T> L, T* __restrict__ curv_s1) {
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = 1 + blockIdx.y, k = 1 + blockIdx.z;
+    if (i > L.nx) return;
+    curv_s1[i + L.NX1 * (j + (long long)L.NY1 * k)] = curvature_at(L, L.u(i, j, k));
 }
 
 // =====================================================================================================
@@ -219,14 +227,14 @@ __global__ void __launch_bounds__(128) k_curvature(const Lattice<T> L, const int
 // variant launched after an even step (fills the ghost plane the odd pull will read); AFTER = true: launched
 // after an odd step (patches the swapped slots at k = 1 / k = nz).
 // Unknown directions at the inlet: QIN = {5,11,12,15,16} (ez = +1); at the outlet their opposites.
+// The reference blends every result with the old value by the wall flag of the boundary node,
+// new*(1-w) + old*w: for w = 1 that is the old value, so threads of solid boundary nodes only do the phi part.
 // =====================================================================================================
 __host__ __device__ constexpr int qin(int n) { constexpr int t[5] = {5, 11, 12, 15, 16}; return t[n]; }
 
-template <typename T> __device__ __forceinline__ T blend(T newv, T oldv, int wi) { return newv * (1 - wi) + oldv * wi; }
-
 template <typename T>
 __device__ __forceinline__ void inlet_phi(const Lattice<T>& L, int i, int j, int wi) {  // :1021-1024
-    const int c = L.i4(i, j, 0), sz = L.NX4 * L.NY4;
+    const int c = L.u(i, j, 0), sz = L.sz;
     const T v = L.phi_inlet * (1 - wi) + L.phi[c] * wi;
     L.phi[c] = v; L.phi[c - sz] = v; L.phi[c - 2 * sz] = v; L.phi[c - 3 * sz] = v;
 }
@@ -239,9 +247,10 @@ __device__ __forceinline__ void inlet_phi(const Lattice<T>& L, int i, int j, int
 template <typename T, bool AFTER>
 __global__ void k_inlet_velocity(const Lattice<T> L, const int ilo, const int ihi) {  // :1009-1077
     MFLBM_PLANE_IJ();
-    const int wi = L.walls[L.i2(i, j, 1)];
+    const int wi = L.solid(L.u(i, j, 1)) ? 1 : 0;
     inlet_phi(L, i, j, wi);
-    T tmp2 = L.W_in[L.i1(i, j, 0)] * L.relaxation;
+    if (wi) return;
+    T tmp2 = L.W_in[L.iplane(i, j)] * L.relaxation;
     const T tmp1 = tmp2 * L.sa_inject;
     tmp2 = tmp2 - tmp1;
 #pragma unroll
@@ -251,10 +260,10 @@ __global__ void k_inlet_velocity(const Lattice<T> L, const int ilo, const int ih
         for (int n = 0; n < 5; n++) {
             const int q = qin(n), o = opc(q);
             const T wgt = n == 0 ? T(1) / T(18) : T(1) / T(36);
-            T* gh = L.slot(q, g) + L.i1(i - ex(q), j - ey(q), 0);   // ghost plane, slot q at x - e_q
-            T* in = L.slot(o, g) + L.i1(i, j, 1);                   // first real plane, slot opc(q)
-            if (!AFTER) *gh = blend(*in + lit<T>(6.0) * wgt * t, *gh, wi);
-            else *in = blend(*gh + lit<T>(6.0) * wgt * t, *in, wi);
+            T& gh = L.f(q, g, L.u(i - ex(q), j - ey(q), 0));   // ghost plane, slot q at x - e_q
+            T& in = L.f(o, g, L.u(i, j, 1));                   // first real plane, slot opc(q)
+            if (!AFTER) gh = in + lit<T>(6.0) * wgt * t;
+            else in = gh + lit<T>(6.0) * wgt * t;
         }
     }
 }
@@ -266,7 +275,7 @@ __device__ __forceinline__ void zh_inplane(const Lattice<T>& L, int i, int j, in
 #pragma unroll
     for (int n = 0; n < 9; n++) {
         const int q = QS[n];
-        v[q] = AFTER ? L.slot(opc(q), g)[L.i1(i, j, k)] : L.slot(q, g)[L.i1(i - ex(q), j - ey(q), k)];
+        v[q] = AFTER ? L.f(opc(q), g, L.u(i, j, k)) : L.f(q, g, L.u(i - ex(q), j - ey(q), k));
     }
 }
 // operand orders of the reference's sums: the "after odd" kernels list local slots 0,2,1,4,3,8,7,10,9
@@ -282,8 +291,9 @@ template <typename T, bool AFTER> __device__ __forceinline__ T zh_tnx(const T (&
 template <typename T, bool AFTER>
 __global__ void k_inlet_pressure(const Lattice<T> L, const int ilo, const int ihi) {  // :1085-1241
     MFLBM_PLANE_IJ();
-    const int wi = L.walls[L.i2(i, j, 1)];
+    const int wi = L.solid(L.u(i, j, 1)) ? 1 : 0;
     inlet_phi(L, i, j, wi);
+    if (wi) return;
     T rho2 = L.rho_in;
     const T rho1 = L.rho_in * L.sa_inject;
     rho2 = rho2 - rho1;
@@ -294,7 +304,7 @@ __global__ void k_inlet_pressure(const Lattice<T> L, const int ilo, const int ih
 #pragma unroll
         for (int n = 0; n < 5; n++) {   // known outgoing f_opc(q): pulled from k = 2, or the swapped local slot q
             const int q = qin(n), o = opc(q);
-            out[n] = AFTER ? L.slot(q, g)[L.i1(i, j, 1)] : L.slot(o, g)[L.i1(i - ex(o), j - ey(o), 2)];
+            out[n] = AFTER ? L.f(q, g, L.u(i, j, 1)) : L.f(o, g, L.u(i - ex(o), j - ey(o), 2));
         }
         const T tr = g == 0 ? rho1 : rho2;
         const T t = (tr - (zh_sum9<T, AFTER>(v) + lit<T>(2.) * (out[0] + out[1] + out[2] + out[3] + out[4]))) * L.relaxation;
@@ -310,8 +320,8 @@ __global__ void k_inlet_pressure(const Lattice<T> L, const int ilo, const int ih
                 const T corr = (q == 11) ? -tnx : (q == 12) ? tnx : (q == 15) ? -tny : tny;
                 val = out[n] + lit<T>(0.166666666666666667) * t + corr;
             }
-            T* dst = AFTER ? L.slot(o, g) + L.i1(i, j, 1) : L.slot(q, g) + L.i1(i - ex(q), j - ey(q), 0);
-            *dst = blend(val, *dst, wi);
+            if (AFTER) L.f(o, g, L.u(i, j, 1)) = val;
+            else L.f(q, g, L.u(i - ex(q), j - ey(q), 0)) = val;
         }
     }
 }
@@ -322,8 +332,8 @@ __global__ void k_outlet_convective(const Lattice<T> L, const int ilo, const int
     const int nz = L.nz;
     const T u_convec = L.uin_avg;
     const T temp = lit<T>(1.) / (lit<T>(1.) + u_convec);
-    const int wi = L.walls[L.i2(i, j, nz)];
-    const int c = L.i4(i, j, nz), sz = L.NX4 * L.NY4, cb = L.i1(i, j, 0);
+    const int wi = L.solid(L.u(i, j, nz)) ? 1 : 0;
+    const int c = L.u(i, j, nz), sz = L.sz, cb = L.iplane(i, j);
     const T ph = ((L.phi_convec[cb] + u_convec * L.phi[c]) * temp) * (1 - wi) + L.phi[c + sz] * wi;
     L.phi[c + sz] = ph; L.phi_convec[cb] = ph; L.phi[c + 2 * sz] = ph; L.phi[c + 3 * sz] = ph; L.phi[c + 4 * sz] = ph;
     const int plane = L.NX1 * L.NY1;
@@ -334,9 +344,10 @@ __global__ void k_outlet_convective(const Lattice<T> L, const int ilo, const int
         for (int n = 0; n < 5; n++) {
             const int o = opc(qin(n));   // unknown incoming direction at the outlet (ez = -1)
             T* dst; const T* inner;
-            if (!AFTER) { dst = L.slot(o, g) + L.i1(i - ex(o), j - ey(o), nz + 1); inner = L.slot(o, g) + L.i1(i - ex(o), j - ey(o), nz); }
-            else { dst = L.slot(opc(o), g) + L.i1(i, j, nz); inner = L.slot(opc(o), g) + L.i1(i, j, nz - 1); }
-            const T val = ((buf[cb + plane * o] + u_convec * *inner) * temp) * (1 - wi) + *dst * wi;
+            if (!AFTER) { dst = &L.f(o, g, L.u(i - ex(o), j - ey(o), nz + 1)); inner = &L.f(o, g, L.u(i - ex(o), j - ey(o), nz)); }
+            else { dst = &L.f(opc(o), g, L.u(i, j, nz)); inner = &L.f(opc(o), g, L.u(i, j, nz - 1)); }
+            if (wi) { buf[cb + plane * o] = *dst; continue; }   // solid boundary node: the blend keeps *dst and records it
+            const T val = (buf[cb + plane * o] + u_convec * *inner) * temp;
             *dst = val;
             buf[cb + plane * o] = val;
         }
@@ -347,18 +358,19 @@ template <typename T, bool AFTER>
 __global__ void k_outlet_pressure(const Lattice<T> L, const int ilo, const int ihi) {  // :1363-1524
     MFLBM_PLANE_IJ();
     const int nz = L.nz;
-    const int wi = L.walls[L.i2(i, j, nz)];
-    const int c = L.i4(i, j, nz), sz = L.NX4 * L.NY4;
+    const int wi = L.solid(L.u(i, j, nz)) ? 1 : 0;
+    const int c = L.u(i, j, nz), sz = L.sz;
     const T phn = L.phi[c];
     L.phi[c + sz] = phn; L.phi[c + 2 * sz] = phn; L.phi[c + 3 * sz] = phn; L.phi[c + 4 * sz] = phn;
+    if (wi) return;
     T v0[11], v1[11], o0[5], o1[5];
     zh_inplane<T, AFTER>(L, i, j, nz, 0, v0);
     zh_inplane<T, AFTER>(L, i, j, nz, 1, v1);
 #pragma unroll
     for (int n = 0; n < 5; n++) {   // known outgoing f_q (ez = +1): pulled from k = nz-1, or the swapped local slot opc(q)
         const int q = qin(n);
-        o0[n] = AFTER ? L.slot(opc(q), 0)[L.i1(i, j, nz)] : L.slot(q, 0)[L.i1(i - ex(q), j - ey(q), nz - 1)];
-        o1[n] = AFTER ? L.slot(opc(q), 1)[L.i1(i, j, nz)] : L.slot(q, 1)[L.i1(i - ex(q), j - ey(q), nz - 1)];
+        o0[n] = AFTER ? L.f(opc(q), 0, L.u(i, j, nz)) : L.f(q, 0, L.u(i - ex(q), j - ey(q), nz - 1));
+        o1[n] = AFTER ? L.f(opc(q), 1, L.u(i, j, nz)) : L.f(q, 1, L.u(i - ex(q), j - ey(q), nz - 1));
     }
     T tmp1;
     if (!AFTER)
@@ -385,8 +397,8 @@ __global__ void k_outlet_pressure(const Lattice<T> L, const int ilo, const int i
                 const T corr = (o == 13) ? -tnx : (o == 14) ? tnx : (o == 17) ? -tny : tny;
                 val = oo[n] - lit<T>(0.166666666666666667) * t + corr;
             }
-            T* dst = AFTER ? L.slot(q, g) + L.i1(i, j, nz) : L.slot(o, g) + L.i1(i - ex(o), j - ey(o), nz + 1);
-            *dst = blend(val, *dst, wi);
+            if (AFTER) L.f(q, g, L.u(i, j, nz)) = val;
+            else L.f(o, g, L.u(i - ex(o), j - ey(o), nz + 1)) = val;
         }
     }
 }
@@ -402,17 +414,18 @@ __global__ void k_periodic_pdf(const Lattice<T> L, const int ilo, const int ihi)
     const int m = 1 + blockIdx.y * blockDim.y + threadIdx.y;
     const int n = AXIS == 1 ? L.ny : L.nz, mlim = AXIS == 1 ? L.nz : L.ny;
     if (i > ihi || m > mlim) return;
+    // the four sites involved: real layers 1 and n, ghost layers 0 and n+1
+    const int e1 = L.cmap[AXIS == 1 ? L.u(i, 1, m) : L.u(i, m, 1)], en = L.cmap[AXIS == 1 ? L.u(i, n, m) : L.u(i, m, n)];
+    const int e0 = L.cmap[AXIS == 1 ? L.u(i, 0, m) : L.u(i, m, 0)], ep = L.cmap[AXIS == 1 ? L.u(i, n + 1, m) : L.u(i, m, n + 1)];
 #pragma unroll
     for (int g = 0; g < 2; g++) {
 #pragma unroll
         for (int q = 1; q < 19; q++) {
             const int s = AXIS == 1 ? ey(q) : ez(q);
             if (s == 0) continue;
-            const int a = s < 0 ? 1 : n, b = s < 0 ? n + 1 : 0;
-            const int src = ODD ? b : a, dst = ODD ? a : b;
+            const int a = s < 0 ? e1 : en, b = s < 0 ? ep : e0;   // real layer a <-> ghost layer b
             T* p = L.slot(q, g);
-            if (AXIS == 1) p[L.i1(i, dst, m)] = p[L.i1(i, src, m)];
-            else p[L.i1(i, m, dst)] = p[L.i1(i, m, src)];
+            if (ODD) p[a] = p[b]; else p[b] = p[a];
         }
     }
 }
@@ -429,9 +442,8 @@ __global__ void k_periodic_pdf_edges(const Lattice<T> L, const int ilo, const in
             const int q = QE[n];
             const int ja = ey(q) < 0 ? 1 : L.ny, jb = ey(q) < 0 ? L.ny + 1 : 0;
             const int ka = ez(q) < 0 ? 1 : L.nz, kb = ez(q) < 0 ? L.nz + 1 : 0;
-            T* p = L.slot(q, g);
-            if (!ODD) p[L.i1(i, jb, kb)] = p[L.i1(i, ja, ka)];
-            else p[L.i1(i, ja, ka)] = p[L.i1(i, jb, kb)];
+            if (!ODD) L.f(q, g, L.u(i, jb, kb)) = L.f(q, g, L.u(i, ja, ka));
+            else L.f(q, g, L.u(i, ja, ka)) = L.f(q, g, L.u(i, jb, kb));
         }
     }
 }
@@ -447,23 +459,23 @@ __global__ void k_periodic_phi(const Lattice<T> L, const int ilo, const int ihi)
     if (WHICH == 2) {
         if (m > ny) return;
         for (int k = 1; k <= ov; k++) {
-            L.phi[L.i4(i, m, k + nz)] = L.phi[L.i4(i, m, k)];
-            L.phi[L.i4(i, m, k - ov)] = L.phi[L.i4(i, m, nz + k - ov)];
+            L.phi[L.u(i, m, k + nz)] = L.phi[L.u(i, m, k)];
+            L.phi[L.u(i, m, k - ov)] = L.phi[L.u(i, m, nz + k - ov)];
         }
     } else if (WHICH == 1) {
         if (m > nz) return;
         for (int j = 1; j <= ov; j++) {
-            L.phi[L.i4(i, j + ny, m)] = L.phi[L.i4(i, j, m)];
-            L.phi[L.i4(i, j - ov, m)] = L.phi[L.i4(i, ny + j - ov, m)];
+            L.phi[L.u(i, j + ny, m)] = L.phi[L.u(i, j, m)];
+            L.phi[L.u(i, j - ov, m)] = L.phi[L.u(i, ny + j - ov, m)];
         }
     } else {
         if (m > 1) return;
         for (int k = 1; k <= ov; k++)
             for (int j = 1; j <= ov; j++) {
-                L.phi[L.i4(i, j - ov, k - ov)] = L.phi[L.i4(i, ny + j - ov, nz + k - ov)];
-                L.phi[L.i4(i, j + ny, k - ov)] = L.phi[L.i4(i, j, nz + k - ov)];
-                L.phi[L.i4(i, j + ny, k + nz)] = L.phi[L.i4(i, j, k)];
-                L.phi[L.i4(i, j - ov, k + nz)] = L.phi[L.i4(i, ny + j - ov, k)];
+                L.phi[L.u(i, j - ov, k - ov)] = L.phi[L.u(i, ny + j - ov, nz + k - ov)];
+                L.phi[L.u(i, j + ny, k - ov)] = L.phi[L.u(i, j, nz + k - ov)];
+                L.phi[L.u(i, j + ny, k + nz)] = L.phi[L.u(i, j, k)];
+                L.phi[L.u(i, j - ov, k + nz)] = L.phi[L.u(i, ny + j - ov, k)];
             }
     }
 }
@@ -472,30 +484,36 @@ __global__ void k_periodic_phi(const Lattice<T> L, const int ilo, const int ihi)
 // porous plate at z = Z_porous_plate (:1744-1882): bounce-back across the plane for the blocked component,
 // pass-through copies for the other
 // =====================================================================================================
+// x range: the bounce-back part runs on the real columns [ilo..ihi]; the pass-through copies are local to a column
+// and also run on the ghost columns [plo..phi] that face a neighbour slab, because they change real-plane values after
+// the PDF halo of the step has been sent (mflbm/slab.py).
 template <typename T, bool AFTER>
-__global__ void k_porous_plate(const Lattice<T> L, const int ilo, const int ihi) {
-    MFLBM_PLANE_IJ();
+__global__ void k_porous_plate(const Lattice<T> L, const int ilo, const int ihi, const int plo, const int phi) {
+    const int i = plo + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (i > phi || j > L.ny) return;
     const int zp = L.Z_porous_plate, cmd = L.porous_plate_cmd;
     if (!(zp >= 1 && zp <= L.nz) || (cmd != 1 && cmd != 2)) return;
     const int gb = cmd == 1 ? 0 : 1, gp = 1 - gb;
+    const bool real_col = i >= ilo && i <= ihi;
 #pragma unroll
     for (int n = 0; n < 5; n++) {
         const int q = qin(n), o = opc(q);
-        T* sq = L.slot(q, gb); T* so = L.slot(o, gb);
-        if (!AFTER) {   // :1758-1768
-            so[L.i1(i - ex(o), j - ey(o), zp)] = sq[L.i1(i, j, zp - 1)];
-            sq[L.i1(i - ex(q), j - ey(q), zp)] = so[L.i1(i, j, zp + 1)];
-        } else {        // :1828-1838
-            sq[L.i1(i, j, zp - 1)] = so[L.i1(i - ex(o), j - ey(o), zp)];
-            so[L.i1(i, j, zp + 1)] = sq[L.i1(i - ex(q), j - ey(q), zp)];
+        if (real_col) {
+            if (!AFTER) {   // :1758-1768
+                L.f(o, gb, L.u(i - ex(o), j - ey(o), zp)) = L.f(q, gb, L.u(i, j, zp - 1));
+                L.f(q, gb, L.u(i - ex(q), j - ey(q), zp)) = L.f(o, gb, L.u(i, j, zp + 1));
+            } else {        // :1828-1838
+                L.f(q, gb, L.u(i, j, zp - 1)) = L.f(o, gb, L.u(i - ex(o), j - ey(o), zp));
+                L.f(o, gb, L.u(i, j, zp + 1)) = L.f(q, gb, L.u(i - ex(q), j - ey(q), zp));
+            }
         }
-        T* pq = L.slot(q, gp); T* po = L.slot(o, gp);
         if (!AFTER) {   // :1770-1780
-            po[L.i1(i, j, zp)] = po[L.i1(i, j, zp + 1)];
-            pq[L.i1(i, j, zp)] = pq[L.i1(i, j, zp - 1)];
-        } else {        // :1840-1850
-            pq[L.i1(i, j, zp - 1)] = pq[L.i1(i, j, zp)];
-            po[L.i1(i, j, zp + 1)] = po[L.i1(i, j, zp)];
+            L.f(o, gp, L.u(i, j, zp)) = L.f(o, gp, L.u(i, j, zp + 1));
+            L.f(q, gp, L.u(i, j, zp)) = L.f(q, gp, L.u(i, j, zp - 1));
+        } else if (real_col) {        // :1840-1850
+            L.f(q, gp, L.u(i, j, zp - 1)) = L.f(q, gp, L.u(i, j, zp));
+            L.f(o, gp, L.u(i, j, zp + 1)) = L.f(o, gp, L.u(i, j, zp));
         }
     }
 }

@@ -49,20 +49,23 @@ struct Solver {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     Lattice<T> L{};
-    long long N1 = 0, N2 = 0, N4 = 0, NP = 0;   // cells of 1/2/4-ghost arrays, cells of an (NX1*NY1) plane
-    // device memory
-    T *d_pdf = nullptr, *d_phi = nullptr, *d_cnx = nullptr, *d_cny = nullptr, *d_cnz = nullptr, *d_cnorm = nullptr, *d_curv = nullptr;
+    long long N1 = 0, N2 = 0, N4 = 0, NP = 0, PN = 0, NC = 0;   // cells of 1/2/4-ghost arrays, of an (NX1*NY1) plane, of the U grid, of a PDF slot
+    // device state (layouts: core.cuh)
+    T *d_pdf = nullptr, *d_phi = nullptr, *d_cnx = nullptr, *d_cny = nullptr, *d_cnz = nullptr, *d_cnorm = nullptr, *d_curvc = nullptr;
     T *d_Win = nullptr, *d_fconv = nullptr, *d_gconv = nullptr, *d_phiconv = nullptr;
-    int *d_walls = nullptr, *d_wtype = nullptr;
-    uint8_t* d_solid1 = nullptr;
-    T *d_snx = nullptr, *d_sny = nullptr, *d_snz = nullptr;
-    int *d_list_phi = nullptr, *d_list_alter = nullptr, *d_list_cn = nullptr;
-    int n_list_phi = 0, n_list_alter = 0, n_list_cn = 0;
+    // device geometry
+    signed char* d_types = nullptr;
+    int *d_cmap = nullptr, *d_flu = nullptr, *d_zstart = nullptr;
+    int *d_list_phi = nullptr, *d_mask_phi = nullptr, *d_list_cn = nullptr, *d_mask_cn = nullptr, *d_list_alter = nullptr, *d_list_n = nullptr;
+    T* d_sn[3] = {nullptr, nullptr, nullptr};   // solid-surface normals in d_list_alter order
+    int n_list_phi = 0, n_list_cn = 0, n_list_alter = 0, n_list_alter_all = 0, n_list_n = 0;
     long long counts[4] = {0, 0, 0, 0};
     long long n_fluid = 0;
     long long launches = 0;
     bool have_geometry = false;
-    bool solids_zeroed = false;   // cn_*/c_norm hold 0 at every solid node (allows k_normals<SKIP_SOLID>)
+    // staging buffer for layout conversion at the boundary
+    void* d_stage = nullptr;
+    size_t stage_bytes = 0;
     // monitor
     double* d_mon = nullptr;
     double* h_mon = nullptr;
@@ -71,10 +74,25 @@ struct Solver {
     T* d_recv[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
     // CUDA graph of one (odd, even) or (even, odd) step pair
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
-
-    int nx() const { return L.nx; }
+    long long pair_launches = 0;
 
     // ------------------------------------------------------------------------------------------------
+    void zalloc(void** ptr, size_t bytes) {
+        MF_CUDA(cudaMalloc(ptr, bytes ? bytes : 1));
+        MF_CUDA(cudaMemsetAsync(*ptr, 0, bytes, stream));
+    }
+    template <typename X> void dfree(X*& q) { if (q) { cudaFree(q); q = nullptr; } }
+
+    void* stage(size_t bytes) {
+        if (bytes > stage_bytes) {
+            if (d_stage) { MF_CUDA(cudaStreamSynchronize(stream)); cudaFree(d_stage); d_stage = nullptr; stage_bytes = 0; }
+            MF_CUDA(cudaMalloc(&d_stage, bytes));
+            stage_bytes = bytes;
+        }
+        return d_stage;
+    }
+    void drop_stage() { if (d_stage) { cudaStreamSynchronize(stream); cudaFree(d_stage); d_stage = nullptr; stage_bytes = 0; } }
+
     void create(const Params* p, const mflbm_slab* sl, int dev, void* strm) {
         device = dev;
         MF_CUDA(cudaSetDevice(device));
@@ -90,27 +108,27 @@ struct Solver {
         L.nx = (int)slab.nx_local; L.ny = (int)p->ny; L.nz = (int)p->nz;
         L.x0 = (int)slab.x0; L.nx_global = (int)p->nx;
         L.NX1 = L.nx + 2; L.NY1 = L.ny + 2; L.NZ1 = L.nz + 2;
-        L.NX2 = L.nx + 4; L.NY2 = L.ny + 4; L.NZ2 = L.nz + 4;
-        L.NX4 = L.nx + 8; L.NY4 = L.ny + 8; L.NZ4 = L.nz + 8;
-        N1 = (long long)L.NX1 * L.NY1 * L.NZ1; N2 = (long long)L.NX2 * L.NY2 * L.NZ2; N4 = (long long)L.NX4 * L.NY4 * L.NZ4;
+        L.PX = 16 * ceil_div(L.nx + 8, 16); L.PY = L.ny + 8; L.PZ = L.nz + 8;
+        N1 = (long long)L.NX1 * L.NY1 * L.NZ1;
+        N2 = (long long)(L.nx + 4) * (L.ny + 4) * (L.nz + 4);
+        N4 = (long long)(L.nx + 8) * (L.ny + 8) * (L.nz + 8);
         NP = (long long)L.NX1 * L.NY1;
-        if (N4 >= (1LL << 31)) MF_FAIL("lattice (or slab) exceeds 2^31 cells per field; decompose into more slabs");
-        L.N1 = N1;
-        auto zalloc = [&](void** ptr, size_t bytes) { MF_CUDA(cudaMalloc(ptr, bytes)); MF_CUDA(cudaMemsetAsync(*ptr, 0, bytes, stream)); };
-        zalloc((void**)&d_pdf, sizeof(T) * N1 * 38);
-        zalloc((void**)&d_phi, sizeof(T) * N4);
-        zalloc((void**)&d_cnx, sizeof(T) * N2); zalloc((void**)&d_cny, sizeof(T) * N2); zalloc((void**)&d_cnz, sizeof(T) * N2);
-        zalloc((void**)&d_cnorm, sizeof(T) * N2);
-        zalloc((void**)&d_curv, sizeof(T) * N1);
+        PN = (long long)L.PX * L.PY * L.PZ;
+        NC = 32 * ((N1 + 31) / 32);
+        if (PN >= (1LL << 31)) MF_FAIL("lattice (or slab) exceeds 2^31 cells per field; decompose into more slabs");
+        L.sy = L.PX; L.sz = L.PX * L.PY; L.NC = NC; L.n_fluid = 0;
+        zalloc((void**)&d_pdf, sizeof(T) * NC * 38);
+        zalloc((void**)&d_phi, sizeof(T) * PN);
+        zalloc((void**)&d_cnx, sizeof(T) * PN); zalloc((void**)&d_cny, sizeof(T) * PN); zalloc((void**)&d_cnz, sizeof(T) * PN);
+        zalloc((void**)&d_cnorm, sizeof(T) * PN);
         zalloc((void**)&d_Win, sizeof(T) * NP);
         zalloc((void**)&d_fconv, sizeof(T) * NP * 19); zalloc((void**)&d_gconv, sizeof(T) * NP * 19); zalloc((void**)&d_phiconv, sizeof(T) * NP);
-        zalloc((void**)&d_walls, sizeof(int) * N2); zalloc((void**)&d_wtype, sizeof(int) * N4);
-        zalloc((void**)&d_solid1, N1);
-        zalloc((void**)&d_snx, sizeof(T) * N4); zalloc((void**)&d_sny, sizeof(T) * N4); zalloc((void**)&d_snz, sizeof(T) * N4);
+        zalloc((void**)&d_types, PN); zalloc((void**)&d_cmap, sizeof(int) * PN);
+        zalloc((void**)&d_zstart, sizeof(int) * (L.nz + 2));
         zalloc((void**)&d_mon, sizeof(double) * MFLBM_MON_N * L.nz);
         MF_CUDA(cudaMallocHost((void**)&h_mon, sizeof(double) * MFLBM_MON_N * L.nz));
         if (is_slab) {
-            const long long npdf = 10LL * L.NY1 * L.NZ1, nphi = 4LL * L.NY4 * L.NZ4;
+            const long long npdf = 10LL * L.NY1 * L.NZ1, nphi = 4LL * L.PY * L.PZ;
             for (int kind = 0; kind < 3; kind++)
                 for (int side = 0; side < 2; side++) {
                     const long long n = kind == 2 ? nphi : npdf;
@@ -118,22 +136,28 @@ struct Solver {
                     zalloc((void**)&d_recv[kind][side], sizeof(T) * n);
                 }
         }
-        L.pdf = d_pdf; L.phi = d_phi; L.cn_x = d_cnx; L.cn_y = d_cny; L.cn_z = d_cnz; L.c_norm = d_cnorm; L.curv = d_curv;
+        L.pdf = d_pdf; L.phi = d_phi; L.cn_x = d_cnx; L.cn_y = d_cny; L.cn_z = d_cnz; L.c_norm = d_cnorm; L.curv_c = nullptr;
         L.W_in = d_Win; L.f_convec = d_fconv; L.g_convec = d_gconv; L.phi_convec = d_phiconv;
-        L.walls = d_walls; L.walls_type = d_wtype; L.solid1 = d_solid1; L.s_nx = d_snx; L.s_ny = d_sny; L.s_nz = d_snz;
+        L.types = d_types; L.cmap = d_cmap; L.fl_u = nullptr;
         set_params(p);
         MF_CUDA(cudaStreamSynchronize(stream));
     }
 
     void destroy() {
         cudaSetDevice(device);
+        if (stream) cudaStreamSynchronize(stream);
         drop_graphs();
-        void* ptrs[] = {d_pdf, d_phi, d_cnx, d_cny, d_cnz, d_cnorm, d_curv, d_Win, d_fconv, d_gconv, d_phiconv, d_walls, d_wtype,
-                        d_solid1, d_snx, d_sny, d_snz, d_list_phi, d_list_alter, d_list_cn, d_mon};
-        for (void* q : ptrs) if (q) cudaFree(q);
-        for (int kind = 0; kind < 3; kind++) for (int side = 0; side < 2; side++) { if (d_send[kind][side]) cudaFree(d_send[kind][side]); if (d_recv[kind][side]) cudaFree(d_recv[kind][side]); }
-        if (h_mon) cudaFreeHost(h_mon);
+        dfree(d_pdf); dfree(d_phi); dfree(d_cnx); dfree(d_cny); dfree(d_cnz); dfree(d_cnorm); dfree(d_curvc);
+        dfree(d_Win); dfree(d_fconv); dfree(d_gconv); dfree(d_phiconv);
+        dfree(d_types); dfree(d_cmap); dfree(d_flu); dfree(d_zstart);
+        dfree(d_list_phi); dfree(d_mask_phi); dfree(d_list_cn); dfree(d_mask_cn); dfree(d_list_alter); dfree(d_list_n);
+        for (auto& q : d_sn) dfree(q);
+        dfree(d_mon);
+        if (d_stage) { cudaFree(d_stage); d_stage = nullptr; }
+        for (int kind = 0; kind < 3; kind++) for (int side = 0; side < 2; side++) { dfree(d_send[kind][side]); dfree(d_recv[kind][side]); }
+        if (h_mon) { cudaFreeHost(h_mon); h_mon = nullptr; }
         if (own_stream && stream) cudaStreamDestroy(stream);
+        stream = nullptr;
     }
 
     void drop_graphs() {
@@ -157,54 +181,111 @@ struct Solver {
     dim3 block2() const { const int bx = std::min(128, 32 * ceil_div(L.nx + 2, 32)); return dim3(bx, std::max(1, 128 / bx), 1); }
     void count(int n = 1) { launches += n; }
     void check_launch() { MF_CUDA(cudaGetLastError()); }
+    dim3 grid_box(int G, int bx) const { return dim3(ceil_div(L.nx + 2 * G, bx), L.ny + 2 * G, L.nz + 2 * G); }
+
+    // reference-layout array (ghost width G) on the host <-> U-grid array on the device
+    template <typename S>
+    void to_u(const S* host, S* d_u, int G, long long n) {
+        S* st = (S*)stage(sizeof(S) * n);
+        MF_CUDA(cudaMemcpyAsync(st, host, sizeof(S) * n, cudaMemcpyHostToDevice, stream));
+        k_repitch<T, S, true><<<grid_box(G, 128), 128, 0, stream>>>(L, G, st, d_u); check_launch(); count();
+        MF_CUDA(cudaStreamSynchronize(stream));   // the staging buffer is reused by the next array
+    }
+    template <typename S>
+    void from_u(S* host, S* d_u, int G, long long n) {
+        S* st = (S*)stage(sizeof(S) * n);
+        k_repitch<T, S, false><<<grid_box(G, 128), 128, 0, stream>>>(L, G, st, d_u); check_launch(); count();
+        MF_CUDA(cudaMemcpyAsync(host, st, sizeof(S) * n, cudaMemcpyDeviceToHost, stream));
+        MF_CUDA(cudaStreamSynchronize(stream));
+    }
 
     // ------------------------------------------------------------------------------------------------
-    // geometry
-    void finish_geometry(const std::vector<int>& walls, const std::vector<int>& wtype) {
-        // byte copy of walls on the 1-ghost extents + fluid count
-        std::vector<uint8_t> s1((size_t)N1);
-        n_fluid = 0;
-        for (int k = 0; k <= L.nz + 1; k++) for (int j = 0; j <= L.ny + 1; j++) for (int i = 0; i <= L.nx + 1; i++) {
-            const int w = walls[(size_t)(i + 1) + (size_t)L.NX2 * ((j + 1) + (size_t)L.NY2 * (k + 1))];
-            s1[(size_t)i + (size_t)L.NX1 * (j + (size_t)L.NY1 * k)] = (uint8_t)(w != 0);
-            if (w == 0 && i >= 1 && i <= L.nx && j >= 1 && j <= L.ny && k >= 1 && k <= L.nz) n_fluid++;
-        }
-        MF_CUDA(cudaMemcpyAsync(d_solid1, s1.data(), (size_t)N1, cudaMemcpyHostToDevice, stream));
-        // compact boundary-node lists over the ranges the reference kernels scan
-        // (:737 [-2..n+3] type 2; :814 [-1..n+2] type -1; :885 [0..n+1] type 2) and the reference's counters
-        std::vector<int> lphi, lalt, lcn;
-        counts[0] = counts[1] = counts[2] = counts[3] = 0;
-        for (int k = -3; k <= L.nz + 4; k++) for (int j = -3; j <= L.ny + 4; j++) for (int i = -3; i <= L.nx + 4; i++) {
-            const int n = (i + 3) + L.NX4 * ((j + 3) + L.NY4 * (k + 3));
-            const int t = wtype[(size_t)n];
-            if (t != 2 && t != -1) continue;
-            const bool in3 = i >= -2 && i <= L.nx + 3 && j >= -2 && j <= L.ny + 3 && k >= -2 && k <= L.nz + 3;
-            const bool in2 = i >= -1 && i <= L.nx + 2 && j >= -1 && j <= L.ny + 2 && k >= -1 && k <= L.nz + 2;
-            const bool in1 = i >= 0 && i <= L.nx + 1 && j >= 0 && j <= L.ny + 1 && k >= 0 && k <= L.nz + 1;
-            if (t == 2) { counts[0]++; if (in3) { counts[2]++; lphi.push_back(n); } if (in1) lcn.push_back(n); }
-            else { counts[1]++; if (in3) counts[3]++; if (in2) lalt.push_back(n); }
-        }
-        auto up = [&](int*& d, int& cnt, const std::vector<int>& v) {
-            if (d) { MF_CUDA(cudaFree(d)); d = nullptr; }
-            cnt = (int)v.size();
-            if (cnt) { MF_CUDA(cudaMalloc((void**)&d, sizeof(int) * v.size())); MF_CUDA(cudaMemcpyAsync(d, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice, stream)); }
-        };
-        up(d_list_phi, n_list_phi, lphi); up(d_list_alter, n_list_alter, lalt); up(d_list_cn, n_list_cn, lcn);
+    // geometry.  d_wtype: walls_type in the reference's s4 layout; d_sn4: the three s4 normal arrays (device).
+    // Builds node types on the U grid, the site permutation of the PDF slots and the compact lists of every
+    // list-driven kernel.  List construction runs on the host (once per geometry).
+    void finish_geometry(const int* d_wtype, T* const d_sn4[3]) {
+        k_types_to_u<T><<<dim3(ceil_div(L.PX, 128), L.PY, L.PZ), 128, 0, stream>>>(L, d_wtype, d_types); check_launch(); count();
+        std::vector<signed char> ty((size_t)PN);
+        MF_CUDA(cudaMemcpyAsync(ty.data(), d_types, (size_t)PN, cudaMemcpyDeviceToHost, stream));
         MF_CUDA(cudaStreamSynchronize(stream));
+        const int PX = L.PX, PY = L.PY, nx = L.nx, ny = L.ny, nz = L.nz;
+        auto U = [&](int x, int y, int z) { return (x + 3) + PX * ((y + 3) + PY * (z + 3)); };
+        int offq[19];
+        for (int q = 0; q < 19; q++) offq[q] = ex(q) + PX * (ey(q) + PY * ez(q));
+        std::vector<int> cmap((size_t)PN, -1), flu, passive, lphi, mphi, lcn, mcn, lalt_in, lalt_out, ln, zstart((size_t)nz + 2, 0);
+        flu.reserve((size_t)nx * ny * nz / 2);
+        counts[0] = counts[1] = counts[2] = counts[3] = 0;
+        for (int z = -3; z <= nz + 4; z++) {
+            if (z >= 1 && z <= nz + 1) zstart[(size_t)z - 1] = (int)flu.size();   // fluid nodes with z' < z
+            for (int y = -3; y <= ny + 4; y++) for (int x = -3; x <= nx + 4; x++) {
+                const int u = U(x, y, z);
+                const int t = ty[(size_t)u];
+                const bool in3 = x >= -2 && x <= nx + 3 && y >= -2 && y <= ny + 3 && z >= -2 && z <= nz + 3;
+                const bool in2 = x >= -1 && x <= nx + 2 && y >= -1 && y <= ny + 2 && z >= -1 && z <= nz + 2;
+                const bool in1 = x >= 0 && x <= nx + 1 && y >= 0 && y <= ny + 1 && z >= 0 && z <= nz + 1;
+                const bool in0 = x >= 1 && x <= nx && y >= 1 && y <= ny && z >= 1 && z <= nz;
+                if (in1) { if (t <= 0 && in0) flu.push_back(u); else passive.push_back(u); }
+                if (t <= 0 && in2) ln.push_back(u);                      // k_normals: non-solid sites of [-1..n+2]^3 (:760-764)
+                if (t == 2) {
+                    counts[0]++;
+                    if (in3) {                                           // :737 [-2..n+3]; :885 [0..n+1]
+                        counts[2]++;
+                        int m = 0;
+                        for (int q = 1; q < 19; q++) if (ty[(size_t)(u + offq[q])] <= 0) m |= 1 << (q - 1);
+                        lphi.push_back(u); mphi.push_back(m);
+                        if (in1) { lcn.push_back(u); mcn.push_back(m); }
+                    }
+                } else if (t == -1) {
+                    counts[1]++; if (in3) counts[3]++;
+                    if (in2) lalt_in.push_back(u); else lalt_out.push_back(u);   // :814 [-1..n+2]
+                }
+            }
+        }
+        zstart[(size_t)nz + 1] = (int)flu.size();
+        // entries z = nz+1.. of the loop above never fired for z > nz+1; make the tail consistent
+        for (int z = nz; z >= 1; z--) if (zstart[(size_t)z] < zstart[(size_t)z - 1]) zstart[(size_t)z] = zstart[(size_t)z - 1];
+        n_fluid = (long long)flu.size();
+        for (size_t n = 0; n < flu.size(); n++) cmap[(size_t)flu[n]] = (int)n;
+        for (size_t n = 0; n < passive.size(); n++) cmap[(size_t)passive[n]] = (int)(flu.size() + n);
+        std::vector<int> lalt(lalt_in);
+        lalt.insert(lalt.end(), lalt_out.begin(), lalt_out.end());
+        auto up = [&](int*& d, const std::vector<int>& v) {
+            dfree(d);
+            MF_CUDA(cudaMalloc((void**)&d, sizeof(int) * std::max<size_t>(v.size(), 1)));
+            if (!v.empty()) MF_CUDA(cudaMemcpyAsync(d, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice, stream));
+        };
+        up(d_flu, flu); up(d_list_phi, lphi); up(d_mask_phi, mphi); up(d_list_cn, lcn); up(d_mask_cn, mcn); up(d_list_alter, lalt); up(d_list_n, ln);
+        n_list_phi = (int)lphi.size(); n_list_cn = (int)lcn.size(); n_list_alter = (int)lalt_in.size(); n_list_alter_all = (int)lalt.size();
+        n_list_n = (int)ln.size();
+        MF_CUDA(cudaMemcpyAsync(d_cmap, cmap.data(), sizeof(int) * (size_t)PN, cudaMemcpyHostToDevice, stream));
+        MF_CUDA(cudaMemcpyAsync(d_zstart, zstart.data(), sizeof(int) * zstart.size(), cudaMemcpyHostToDevice, stream));
+        dfree(d_curvc);
+        zalloc((void**)&d_curvc, sizeof(T) * std::max<long long>(n_fluid, 1));
+        L.n_fluid = (int)n_fluid; L.fl_u = d_flu; L.curv_c = d_curvc;
+        for (int a = 0; a < 3; a++) {
+            dfree(d_sn[a]);
+            MF_CUDA(cudaMalloc((void**)&d_sn[a], sizeof(T) * std::max(n_list_alter_all, 1)));
+            if (n_list_alter_all) { k_list_s4<T, true><<<ceil_div(n_list_alter_all, 128), 128, 0, stream>>>(L, d_list_alter, n_list_alter_all, d_sn4[a], d_sn[a]); check_launch(); count(); }
+        }
+        MF_CUDA(cudaStreamSynchronize(stream));   // host vectors go out of scope
         have_geometry = true;
-        solids_zeroed = false;
         drop_graphs();
     }
 
     void upload_geometry(const int32_t* walls, const int32_t* wtype, const T* snx, const T* sny, const T* snz) {
         if (!walls || !wtype || !snx || !sny || !snz) MF_FAIL("upload_geometry: null array");
-        MF_CUDA(cudaMemcpyAsync(d_walls, walls, sizeof(int) * N2, cudaMemcpyHostToDevice, stream));
-        MF_CUDA(cudaMemcpyAsync(d_wtype, wtype, sizeof(int) * N4, cudaMemcpyHostToDevice, stream));
-        MF_CUDA(cudaMemcpyAsync(d_snx, snx, sizeof(T) * N4, cudaMemcpyHostToDevice, stream));
-        MF_CUDA(cudaMemcpyAsync(d_sny, sny, sizeof(T) * N4, cudaMemcpyHostToDevice, stream));
-        MF_CUDA(cudaMemcpyAsync(d_snz, snz, sizeof(T) * N4, cudaMemcpyHostToDevice, stream));
-        std::vector<int> w(walls, walls + N2), t(wtype, wtype + N4);
-        finish_geometry(w, t);
+        // walls (s2) is redundant with walls_type (walls == (walls_type > 0) on its extents, Geometry_preprocessing.cpp:135-184)
+        int* d_wt = nullptr; T* d_sn4[3] = {nullptr, nullptr, nullptr};
+        MF_CUDA(cudaMalloc((void**)&d_wt, sizeof(int) * N4));
+        MF_CUDA(cudaMemcpyAsync(d_wt, wtype, sizeof(int) * N4, cudaMemcpyHostToDevice, stream));
+        const T* src[3] = {snx, sny, snz};
+        for (int a = 0; a < 3; a++) {
+            MF_CUDA(cudaMalloc((void**)&d_sn4[a], sizeof(T) * N4));
+            MF_CUDA(cudaMemcpyAsync(d_sn4[a], src[a], sizeof(T) * N4, cudaMemcpyHostToDevice, stream));
+        }
+        try { finish_geometry(d_wt, d_sn4); }
+        catch (...) { cudaFree(d_wt); for (auto q : d_sn4) cudaFree(q); throw; }
+        cudaFree(d_wt); for (auto q : d_sn4) cudaFree(q);
     }
 
     void preprocess_geometry(const int8_t* interior_global) {
@@ -215,76 +296,130 @@ struct Solver {
         const size_t TN = (size_t)D.TX * D.TY * D.TZ, NG = (size_t)P.nx * P.ny * P.nz;
         int8_t *d_in = nullptr, *d_wt = nullptr, *d_ty = nullptr;
         T *d_ws1 = nullptr, *d_ws2 = nullptr;
-        MF_CUDA(cudaMalloc((void**)&d_in, NG)); MF_CUDA(cudaMalloc((void**)&d_wt, TN)); MF_CUDA(cudaMalloc((void**)&d_ty, TN));
-        MF_CUDA(cudaMalloc((void**)&d_ws1, TN * sizeof(T))); MF_CUDA(cudaMalloc((void**)&d_ws2, TN * sizeof(T)));
-        MF_CUDA(cudaMemcpyAsync(d_in, interior_global, NG, cudaMemcpyHostToDevice, stream));
-        MF_CUDA(cudaMemsetAsync(d_ty, 0, TN, stream));
-        const int bx = 128;
-        k_geo_fill<T><<<dim3(ceil_div(D.TX, bx), D.TY, D.TZ), bx, 0, stream>>>(D, d_in, d_wt, d_ws1, d_ws2); check_launch(); count();
-        const dim3 ginner(ceil_div(D.TX - 2, bx), D.TY - 2, D.TZ - 2);
-        k_geo_classify<<<ginner, bx, 0, stream>>>(D, d_wt, d_ty); check_launch(); count();
-        for (int it = 0; it < 4; it++) {   // :187-206
-            k_geo_smooth<T><<<ginner, bx, 0, stream>>>(D, d_ws1, d_ws2); check_launch();
-            k_geo_copy_inner<T><<<ginner, bx, 0, stream>>>(D, d_ws2, d_ws1); check_launch();
-            count(2);
-        }
-        Iso8Tables tab;
-        static const signed char TX_[34][3] = {{1,0,0},{1,1,0},{1,-1,0},{1,0,1},{1,0,-1},{1,1,1},{1,1,-1},{1,-1,1},{1,-1,-1},{2,0,0},
-            {2,1,0},{2,-1,0},{2,0,1},{2,0,-1},{1,2,0},{1,-2,0},{1,0,2},{1,0,-2},
-            {2,1,1},{2,1,-1},{2,-1,1},{2,-1,-1},{1,2,1},{1,2,-1},{1,-2,1},{1,-2,-1},{1,1,2},{1,1,-2},{1,-1,2},{1,-1,-2},
-            {2,2,0},{2,-2,0},{2,0,2},{2,0,-2}};
-        static const signed char TY_[34][3] = {{0,1,0},{1,1,0},{-1,1,0},{0,1,1},{0,1,-1},{1,1,1},{1,1,-1},{-1,1,-1},{-1,1,1},{0,2,0},
-            {2,1,0},{-2,1,0},{0,2,1},{0,2,-1},{1,2,0},{-1,2,0},{0,1,2},{0,1,-2},
-            {2,1,1},{2,1,-1},{-2,1,1},{-2,1,-1},{1,2,1},{1,2,-1},{-1,2,1},{-1,2,-1},{1,1,2},{1,1,-2},{-1,1,2},{-1,1,-2},
-            {2,2,0},{-2,2,0},{0,2,2},{0,2,-2}};
-        static const signed char TZ_[34][3] = {{0,0,1},{0,1,1},{0,-1,1},{1,0,1},{-1,0,1},{1,1,1},{1,-1,1},{-1,1,1},{-1,-1,1},{0,0,2},
-            {0,1,2},{0,-1,2},{2,0,1},{-2,0,1},{0,2,1},{0,-2,1},{1,0,2},{-1,0,2},
-            {2,1,1},{2,-1,1},{-2,1,1},{-2,-1,1},{1,2,1},{1,-2,1},{-1,2,1},{-1,-2,1},{1,1,2},{1,-1,2},{-1,1,2},{-1,-1,2},
-            {0,2,2},{0,-2,2},{2,0,2},{-2,0,2}};
-        memcpy(tab.o[0], TX_, sizeof TX_); memcpy(tab.o[1], TY_, sizeof TY_); memcpy(tab.o[2], TZ_, sizeof TZ_);
-        MF_CUDA(cudaMemsetAsync(d_snx, 0, sizeof(T) * N4, stream)); MF_CUDA(cudaMemsetAsync(d_sny, 0, sizeof(T) * N4, stream));
-        MF_CUDA(cudaMemsetAsync(d_snz, 0, sizeof(T) * N4, stream));
-        const T eps = (T)1.1920928955078125e-07f;   // includes/Module.h:10-16: float epsilon in both precisions
-        k_geo_export<T><<<dim3(ceil_div(L.NX4, bx), L.NY4, L.NZ4), bx, 0, stream>>>(D, tab, d_wt, d_ty, d_ws2, d_walls, d_wtype, d_snx, d_sny, d_snz, eps);
-        check_launch(); count();
-        std::vector<int> w((size_t)N2), t((size_t)N4);
-        MF_CUDA(cudaMemcpyAsync(w.data(), d_walls, sizeof(int) * N2, cudaMemcpyDeviceToHost, stream));
-        MF_CUDA(cudaMemcpyAsync(t.data(), d_wtype, sizeof(int) * N4, cudaMemcpyDeviceToHost, stream));
-        MF_CUDA(cudaStreamSynchronize(stream));
-        cudaFree(d_in); cudaFree(d_wt); cudaFree(d_ty); cudaFree(d_ws1); cudaFree(d_ws2);
-        finish_geometry(w, t);
+        int *d_walls = nullptr, *d_wtype = nullptr;
+        T* d_sn4[3] = {nullptr, nullptr, nullptr};
+        auto cleanup = [&]() { cudaFree(d_in); cudaFree(d_wt); cudaFree(d_ty); cudaFree(d_ws1); cudaFree(d_ws2); cudaFree(d_walls); cudaFree(d_wtype); for (auto q : d_sn4) cudaFree(q); };
+        try {
+            MF_CUDA(cudaMalloc((void**)&d_in, NG)); MF_CUDA(cudaMalloc((void**)&d_wt, TN)); MF_CUDA(cudaMalloc((void**)&d_ty, TN));
+            MF_CUDA(cudaMalloc((void**)&d_ws1, TN * sizeof(T))); MF_CUDA(cudaMalloc((void**)&d_ws2, TN * sizeof(T)));
+            MF_CUDA(cudaMalloc((void**)&d_walls, sizeof(int) * N2)); MF_CUDA(cudaMalloc((void**)&d_wtype, sizeof(int) * N4));
+            for (int a = 0; a < 3; a++) { MF_CUDA(cudaMalloc((void**)&d_sn4[a], sizeof(T) * N4)); MF_CUDA(cudaMemsetAsync(d_sn4[a], 0, sizeof(T) * N4, stream)); }
+            MF_CUDA(cudaMemcpyAsync(d_in, interior_global, NG, cudaMemcpyHostToDevice, stream));
+            MF_CUDA(cudaMemsetAsync(d_ty, 0, TN, stream));
+            const int bx = 128;
+            k_geo_fill<T><<<dim3(ceil_div(D.TX, bx), D.TY, D.TZ), bx, 0, stream>>>(D, d_in, d_wt, d_ws1, d_ws2); check_launch(); count();
+            const dim3 ginner(ceil_div(D.TX - 2, bx), D.TY - 2, D.TZ - 2);
+            k_geo_classify<<<ginner, bx, 0, stream>>>(D, d_wt, d_ty); check_launch(); count();
+            for (int it = 0; it < 4; it++) {   // :187-206
+                k_geo_smooth<T><<<ginner, bx, 0, stream>>>(D, d_ws1, d_ws2); check_launch();
+                k_geo_copy_inner<T><<<ginner, bx, 0, stream>>>(D, d_ws2, d_ws1); check_launch();
+                count(2);
+            }
+            Iso8Tables tab;
+            static const signed char TX_[34][3] = {{1,0,0},{1,1,0},{1,-1,0},{1,0,1},{1,0,-1},{1,1,1},{1,1,-1},{1,-1,1},{1,-1,-1},{2,0,0},
+                {2,1,0},{2,-1,0},{2,0,1},{2,0,-1},{1,2,0},{1,-2,0},{1,0,2},{1,0,-2},
+                {2,1,1},{2,1,-1},{2,-1,1},{2,-1,-1},{1,2,1},{1,2,-1},{1,-2,1},{1,-2,-1},{1,1,2},{1,1,-2},{1,-1,2},{1,-1,-2},
+                {2,2,0},{2,-2,0},{2,0,2},{2,0,-2}};
+            static const signed char TY_[34][3] = {{0,1,0},{1,1,0},{-1,1,0},{0,1,1},{0,1,-1},{1,1,1},{1,1,-1},{-1,1,-1},{-1,1,1},{0,2,0},
+                {2,1,0},{-2,1,0},{0,2,1},{0,2,-1},{1,2,0},{-1,2,0},{0,1,2},{0,1,-2},
+                {2,1,1},{2,1,-1},{-2,1,1},{-2,1,-1},{1,2,1},{1,2,-1},{-1,2,1},{-1,2,-1},{1,1,2},{1,1,-2},{-1,1,2},{-1,1,-2},
+                {2,2,0},{-2,2,0},{0,2,2},{0,2,-2}};
+            static const signed char TZ_[34][3] = {{0,0,1},{0,1,1},{0,-1,1},{1,0,1},{-1,0,1},{1,1,1},{1,-1,1},{-1,1,1},{-1,-1,1},{0,0,2},
+                {0,1,2},{0,-1,2},{2,0,1},{-2,0,1},{0,2,1},{0,-2,1},{1,0,2},{-1,0,2},
+                {2,1,1},{2,-1,1},{-2,1,1},{-2,-1,1},{1,2,1},{1,-2,1},{-1,2,1},{-1,-2,1},{1,1,2},{1,-1,2},{-1,1,2},{-1,-1,2},
+                {0,2,2},{0,-2,2},{2,0,2},{-2,0,2}};
+            memcpy(tab.o[0], TX_, sizeof TX_); memcpy(tab.o[1], TY_, sizeof TY_); memcpy(tab.o[2], TZ_, sizeof TZ_);
+            const T eps = (T)1.1920928955078125e-07f;   // includes/Module.h:10-16: float epsilon in both precisions
+            k_geo_export<T><<<dim3(ceil_div(L.nx + 8, bx), L.ny + 8, L.nz + 8), bx, 0, stream>>>(D, tab, d_wt, d_ty, d_ws2, d_walls, d_wtype, d_sn4[0], d_sn4[1], d_sn4[2], eps);
+            check_launch(); count();
+            cudaFree(d_in); d_in = nullptr; cudaFree(d_wt); d_wt = nullptr; cudaFree(d_ty); d_ty = nullptr;
+            finish_geometry(d_wtype, d_sn4);
+        } catch (...) { cleanup(); throw; }
+        cleanup();
     }
 
     void download_geometry(int32_t* walls, int32_t* wtype, T* snx, T* sny, T* snz, int64_t* cnt) {
-        if (walls) MF_CUDA(cudaMemcpyAsync(walls, d_walls, sizeof(int) * N2, cudaMemcpyDeviceToHost, stream));
-        if (wtype) MF_CUDA(cudaMemcpyAsync(wtype, d_wtype, sizeof(int) * N4, cudaMemcpyDeviceToHost, stream));
-        if (snx) MF_CUDA(cudaMemcpyAsync(snx, d_snx, sizeof(T) * N4, cudaMemcpyDeviceToHost, stream));
-        if (sny) MF_CUDA(cudaMemcpyAsync(sny, d_sny, sizeof(T) * N4, cudaMemcpyDeviceToHost, stream));
-        if (snz) MF_CUDA(cudaMemcpyAsync(snz, d_snz, sizeof(T) * N4, cudaMemcpyDeviceToHost, stream));
-        MF_CUDA(cudaStreamSynchronize(stream));
+        if (!have_geometry) MF_FAIL("download_geometry before geometry");
+        if (walls || wtype) {
+            int* st = (int*)stage(sizeof(int) * (N2 + N4));
+            k_types_from_u<T><<<grid_box(4, 128), 128, 0, stream>>>(L, st, st + N2); check_launch(); count();
+            if (walls) MF_CUDA(cudaMemcpyAsync(walls, st, sizeof(int) * N2, cudaMemcpyDeviceToHost, stream));
+            if (wtype) MF_CUDA(cudaMemcpyAsync(wtype, st + N2, sizeof(int) * N4, cudaMemcpyDeviceToHost, stream));
+            MF_CUDA(cudaStreamSynchronize(stream));
+        }
+        T* out[3] = {snx, sny, snz};
+        for (int a = 0; a < 3; a++) {
+            if (!out[a]) continue;
+            T* st = (T*)stage(sizeof(T) * N4);
+            MF_CUDA(cudaMemsetAsync(st, 0, sizeof(T) * N4, stream));   // zero except at fluid-boundary nodes (Geometry_preprocessing.cpp:229-386)
+            if (n_list_alter_all) { k_list_s4<T, false><<<ceil_div(n_list_alter_all, 128), 128, 0, stream>>>(L, d_list_alter, n_list_alter_all, st, d_sn[a]); check_launch(); count(); }
+            MF_CUDA(cudaMemcpyAsync(out[a], st, sizeof(T) * N4, cudaMemcpyDeviceToHost, stream));
+            MF_CUDA(cudaStreamSynchronize(stream));
+        }
         if (cnt) for (int n = 0; n < 4; n++) cnt[n] = counts[n];
+        drop_stage();
     }
 
     // ------------------------------------------------------------------------------------------------
     // state
     void upload_state(const T* pdf, const T* phi, const T* cnx, const T* cny, const T* cnz, const T* cnorm, const T* curv,
                       const T* Win, const T* fconv, const T* gconv, const T* phiconv) {
+        if (!have_geometry) MF_FAIL("upload_state before geometry (the PDF site order depends on it)");
+        if (pdf) {
+            const dim3 g = grid_box(1, 128);
+            for (int s = 0; s < 38; s++) {
+                T* st = (T*)stage(sizeof(T) * N1);
+                MF_CUDA(cudaMemcpyAsync(st, pdf + (size_t)s * N1, sizeof(T) * N1, cudaMemcpyHostToDevice, stream));
+                k_pdf_slot<T, true><<<g, 128, 0, stream>>>(L, st, d_pdf + (size_t)s * NC); check_launch(); count();
+                MF_CUDA(cudaStreamSynchronize(stream));
+            }
+        }
+        if (phi) to_u<T>(phi, d_phi, 4, N4);
+        if (cnx) to_u<T>(cnx, d_cnx, 2, N2);
+        if (cny) to_u<T>(cny, d_cny, 2, N2);
+        if (cnz) to_u<T>(cnz, d_cnz, 2, N2);
+        if (cnorm) to_u<T>(cnorm, d_cnorm, 2, N2);
+        if (cnx || cny || cnz || cnorm) {   // the caller's arrays are not trusted to hold zeros in solids
+            k_zero_solid_normals<T><<<grid_box(2, 128), 128, 0, stream>>>(L); check_launch(); count();
+        }
+        if (curv) {
+            T* st = (T*)stage(sizeof(T) * N1);
+            MF_CUDA(cudaMemcpyAsync(st, curv, sizeof(T) * N1, cudaMemcpyHostToDevice, stream));
+            if (n_fluid) { k_curv_gather<T><<<ceil_div((int)n_fluid, 128), 128, 0, stream>>>(L, st); check_launch(); count(); }
+        }
         auto up = [&](T* d, const T* h, long long n) { if (h) MF_CUDA(cudaMemcpyAsync(d, h, sizeof(T) * n, cudaMemcpyHostToDevice, stream)); };
-        up(d_pdf, pdf, N1 * 38); up(d_phi, phi, N4); up(d_cnx, cnx, N2); up(d_cny, cny, N2); up(d_cnz, cnz, N2); up(d_cnorm, cnorm, N2);
-        up(d_curv, curv, N1); up(d_Win, Win, NP); up(d_fconv, fconv, NP * 19); up(d_gconv, gconv, NP * 19); up(d_phiconv, phiconv, NP);
+        up(d_Win, Win, NP); up(d_fconv, fconv, NP * 19); up(d_gconv, gconv, NP * 19); up(d_phiconv, phiconv, NP);
         MF_CUDA(cudaStreamSynchronize(stream));
-        solids_zeroed = false;   // the caller's cn arrays are not trusted to hold zeros in solids
+        drop_stage();
     }
 
     void download_state(T* pdf, T* phi, T* cnx, T* cny, T* cnz, T* cnorm, T* curv, T* fconv, T* gconv, T* phiconv) {
-        if (curv && have_geometry) {   // the stepping path keeps curv at fluid nodes only; give the caller the reference's dense array
-            const dim3 b = block2();
-            k_curvature<T, false><<<dim3(ceil_div(L.nx, b.x), ceil_div(L.ny, b.y), L.nz), b, 0, stream>>>(L, 1, L.nx); check_launch(); count();
+        if (!have_geometry) MF_FAIL("download_state before geometry");
+        if (pdf) {
+            const dim3 g = grid_box(1, 128);
+            for (int s = 0; s < 38; s++) {
+                T* st = (T*)stage(sizeof(T) * N1);
+                k_pdf_slot<T, false><<<g, 128, 0, stream>>>(L, st, d_pdf + (size_t)s * NC); check_launch(); count();
+                MF_CUDA(cudaMemcpyAsync(pdf + (size_t)s * N1, st, sizeof(T) * N1, cudaMemcpyDeviceToHost, stream));
+                MF_CUDA(cudaStreamSynchronize(stream));
+            }
+        }
+        if (phi) from_u<T>(phi, d_phi, 4, N4);
+        if (cnx) from_u<T>(cnx, d_cnx, 2, N2);
+        if (cny) from_u<T>(cny, d_cny, 2, N2);
+        if (cnz) from_u<T>(cnz, d_cnz, 2, N2);
+        if (cnorm) from_u<T>(cnorm, d_cnorm, 2, N2);
+        if (curv) {   // the stepping path keeps curv at fluid nodes only; give the caller the reference's dense array (:908-1003 over [1..n]^3)
+            T* st = (T*)stage(sizeof(T) * N1);
+            MF_CUDA(cudaMemsetAsync(st, 0, sizeof(T) * N1, stream));
+            k_curvature_dense<T><<<dim3(ceil_div(L.nx, 128), L.ny, L.nz), 128, 0, stream>>>(L, st); check_launch(); count();
+            MF_CUDA(cudaMemcpyAsync(curv, st, sizeof(T) * N1, cudaMemcpyDeviceToHost, stream));
+            MF_CUDA(cudaStreamSynchronize(stream));
         }
         auto dn = [&](T* h, const T* d, long long n) { if (h) MF_CUDA(cudaMemcpyAsync(h, d, sizeof(T) * n, cudaMemcpyDeviceToHost, stream)); };
-        dn(pdf, d_pdf, N1 * 38); dn(phi, d_phi, N4); dn(cnx, d_cnx, N2); dn(cny, d_cny, N2); dn(cnz, d_cnz, N2); dn(cnorm, d_cnorm, N2);
-        dn(curv, d_curv, N1); dn(fconv, d_fconv, NP * 19); dn(gconv, d_gconv, NP * 19); dn(phiconv, d_phiconv, NP);
+        dn(fconv, d_fconv, NP * 19); dn(gconv, d_gconv, NP * 19); dn(phiconv, d_phiconv, NP);
         MF_CUDA(cudaStreamSynchronize(stream));
+        drop_stage();
     }
 
     bool open_z() const { return P.kper == 0 && P.wall_z_min == 0 && P.wall_z_max == 0; }
@@ -293,17 +428,16 @@ struct Solver {
         if (!have_geometry) MF_FAIL("init_state before geometry");
         if (option < 1 || option > 5) MF_FAIL("initial_fluid_distribution_option %d not supported on the device (1..5)", option);
         const int bx = 128;
-        MF_CUDA(cudaMemsetAsync(d_phi, 0, sizeof(T) * N4, stream));
-        k_init_phi<T><<<dim3(ceil_div(L.NX4, bx), L.NY4, L.NZ4), bx, 0, stream>>>(L, option, interface_z0, (int)P.ny, (int)P.nz, open_z() ? 1 : 0);
+        MF_CUDA(cudaMemsetAsync(d_phi, 0, sizeof(T) * PN, stream));
+        k_init_phi<T><<<grid_box(4, bx), bx, 0, stream>>>(L, option, interface_z0, (int)P.ny, (int)P.nz, open_z() ? 1 : 0);
         check_launch();
-        k_init_pdf<T><<<dim3(ceil_div(L.NX1, bx), L.NY1, L.NZ1), bx, 0, stream>>>(L, P.outlet_BC == 1 ? 1 : 0); check_launch();
+        k_init_pdf<T><<<grid_box(1, bx), bx, 0, stream>>>(L, P.outlet_BC == 1 ? 1 : 0); check_launch();
         count(2);
         if (Win) MF_CUDA(cudaMemcpyAsync(d_Win, Win, sizeof(T) * NP, cudaMemcpyHostToDevice, stream));
-        MF_CUDA(cudaMemsetAsync(d_cnx, 0, sizeof(T) * N2, stream)); MF_CUDA(cudaMemsetAsync(d_cny, 0, sizeof(T) * N2, stream));
-        MF_CUDA(cudaMemsetAsync(d_cnz, 0, sizeof(T) * N2, stream)); MF_CUDA(cudaMemsetAsync(d_cnorm, 0, sizeof(T) * N2, stream));
-        MF_CUDA(cudaMemsetAsync(d_curv, 0, sizeof(T) * N1, stream));
-        solids_zeroed = false;
-        gradient_chain(true);
+        MF_CUDA(cudaMemsetAsync(d_cnx, 0, sizeof(T) * PN, stream)); MF_CUDA(cudaMemsetAsync(d_cny, 0, sizeof(T) * PN, stream));
+        MF_CUDA(cudaMemsetAsync(d_cnz, 0, sizeof(T) * PN, stream)); MF_CUDA(cudaMemsetAsync(d_cnorm, 0, sizeof(T) * PN, stream));
+        MF_CUDA(cudaMemsetAsync(d_curvc, 0, sizeof(T) * std::max<long long>(n_fluid, 1), stream));
+        gradient_chain();
         MF_CUDA(cudaStreamSynchronize(stream));
     }
 
@@ -313,29 +447,22 @@ struct Solver {
     int phi_() const { return slab.has_right ? L.nx + 1 : L.nx; }
 
     // the five colour-gradient kernels, call order of src/main_iteration_GPU.cu:2027-2055
-    void gradient_chain(bool dense) {
+    void gradient_chain() {
         if (!have_geometry) MF_FAIL("gradient chain before geometry");
-        const dim3 b = block2();
         const int bl = 128;
-        if (n_list_phi) { k_extrap_phi<T><<<ceil_div(n_list_phi, bl), bl, 0, stream>>>(L, d_list_phi, n_list_phi); check_launch(); count(); }
-        const dim3 gn(ceil_div(L.nx + 4, b.x), ceil_div(L.ny + 4, b.y), L.nz + 4);
-        if (dense || !solids_zeroed) { k_normals<T, false><<<gn, b, 0, stream>>>(L, -1, L.nx + 2); solids_zeroed = true; }
-        else k_normals<T, true><<<gn, b, 0, stream>>>(L, -1, L.nx + 2);
-        check_launch(); count();
-        if (n_list_alter) { k_alter<T><<<ceil_div(n_list_alter, bl), bl, 0, stream>>>(L, d_list_alter, n_list_alter); check_launch(); count(); }
-        if (n_list_cn) { k_extrap_cn<T><<<ceil_div(n_list_cn, bl), bl, 0, stream>>>(L, d_list_cn, n_list_cn); check_launch(); count(); }
-        const dim3 gc(ceil_div(L.nx, b.x), ceil_div(L.ny, b.y), L.nz);
-        if (dense) k_curvature<T, false><<<gc, b, 0, stream>>>(L, 1, L.nx);
-        else k_curvature<T, true><<<gc, b, 0, stream>>>(L, 1, L.nx);
-        check_launch(); count();
+        if (n_list_phi) { k_extrap_phi<T><<<ceil_div(n_list_phi, bl), bl, 0, stream>>>(L, d_list_phi, d_mask_phi, n_list_phi); check_launch(); count(); }
+        if (n_list_n) { k_normals<T><<<ceil_div(n_list_n, bl), bl, 0, stream>>>(L, d_list_n, n_list_n); check_launch(); count(); }
+        if (n_list_alter) { k_alter<T><<<ceil_div(n_list_alter, bl), bl, 0, stream>>>(L, d_list_alter, d_sn[0], d_sn[1], d_sn[2], n_list_alter); check_launch(); count(); }
+        if (n_list_cn) { k_extrap_cn<T><<<ceil_div(n_list_cn, bl), bl, 0, stream>>>(L, d_list_cn, d_mask_cn, n_list_cn); check_launch(); count(); }
+        if (n_fluid) { k_curvature<T><<<ceil_div((int)n_fluid, bl), bl, 0, stream>>>(L); check_launch(); count(); }
     }
 
     template <int MRT>
     void launch_collide(bool odd) {
-        const dim3 b = block2();
-        const dim3 g(ceil_div(L.nx, b.x), ceil_div(L.ny, b.y), L.nz);
-        if (odd) k_collide<T, MRT, true><<<g, b, 0, stream>>>(L, 1, L.nx);
-        else k_collide<T, MRT, false><<<g, b, 0, stream>>>(L, 1, L.nx);
+        if (!n_fluid) return;
+        const int g = ceil_div((int)n_fluid, 128);
+        if (odd) k_collide<T, MRT, true><<<g, 128, 0, stream>>>(L);
+        else k_collide<T, MRT, false><<<g, 128, 0, stream>>>(L);
         check_launch(); count();
     }
 
@@ -381,7 +508,7 @@ struct Solver {
             check_launch();
         }
         if (P.porous_plate_cmd != 0) {
-            if (odd) k_porous_plate<T, true><<<gp, b, 0, stream>>>(L, 1, L.nx); else k_porous_plate<T, false><<<gp, b, 0, stream>>>(L, 1, L.nx);
+            if (odd) k_porous_plate<T, true><<<gz, b, 0, stream>>>(L, 1, L.nx, lo, hi); else k_porous_plate<T, false><<<gz, b, 0, stream>>>(L, 1, L.nx, lo, hi);
             check_launch(); count();
         }
     }
@@ -390,7 +517,7 @@ struct Solver {
         if (!have_geometry) MF_FAIL("step before geometry");
         if (phase == 0) phase_collide(ntime);
         else if (phase == 1) phase_boundaries(ntime);
-        else if (phase == 2) gradient_chain(false);
+        else if (phase == 2) gradient_chain();
         else MF_FAIL("bad phase");
     }
 
@@ -399,9 +526,9 @@ struct Solver {
     // nsteps consecutive steps; pairs of steps are replayed from a captured CUDA graph (launch-bound small lattices)
     void run(int ntime_first, int nsteps) {
         if (nsteps <= 0) return;
+        if (!have_geometry) MF_FAIL("step before geometry");
         int nt = ntime_first, left = nsteps;
         if (left >= 4 && !is_slab) {
-            if (!solids_zeroed) { step(nt); nt++; left--; }   // first chain pass is the dense variant; keep it out of the graph
             const int par = nt & 1;
             if (!graph_exec[par]) {
                 const long long l0 = launches;
@@ -419,13 +546,12 @@ struct Solver {
         }
         for (; left > 0; left--, nt++) step(nt);
     }
-    long long pair_launches = 0;
 
     // ------------------------------------------------------------------------------------------------
     void monitor(mflbm_monitor_out* out) {
         if (!have_geometry) MF_FAIL("monitor before geometry");
         if (!out) MF_FAIL("monitor: null output");
-        k_monitor<T><<<L.nz, 256, 0, stream>>>(L, d_mon); check_launch(); count();
+        k_monitor<T><<<L.nz, 256, 0, stream>>>(L, d_zstart, d_mon); check_launch(); count();
         MF_CUDA(cudaMemcpyAsync(h_mon, d_mon, sizeof(double) * MFLBM_MON_N * L.nz, cudaMemcpyDeviceToHost, stream));
         MF_CUDA(cudaStreamSynchronize(stream));
         const int nz = L.nz;
@@ -458,12 +584,13 @@ struct Solver {
 
     // ------------------------------------------------------------------------------------------------
     // halo exchange (x slabs)
-    long long halo_count(int kind) const { return kind == 2 ? 4LL * L.NY4 * L.NZ4 : 10LL * L.NY1 * L.NZ1; }
+    long long halo_count(int kind) const { return kind == 2 ? 4LL * L.PY * L.PZ : 10LL * L.NY1 * L.NZ1; }
 
     void halo_pack(int kind) {
         if (!is_slab) MF_FAIL("halo_pack on a non-slab solver");
+        if (!have_geometry) MF_FAIL("halo_pack before geometry");
         const int bt = 128;
-        const dim3 g1(ceil_div(L.NY1, bt), L.NZ1), g4(ceil_div(L.NY4, bt), L.NZ4);
+        const dim3 g1(ceil_div(L.NY1, bt), L.NZ1), g4(ceil_div(L.PY, bt), L.PZ);
         if (kind == 0) {   // after an even step: real boundary columns -> neighbour ghost columns
             if (slab.has_left) { k_halo_pdf<T, false, true><<<g1, bt, 0, stream>>>(L, d_send[0][0], 1); count(); }          // ex=-1 slots of column 1
             if (slab.has_right) { k_halo_pdf<T, true, true><<<g1, bt, 0, stream>>>(L, d_send[0][1], L.nx); count(); }       // ex=+1 slots of column nx
@@ -479,8 +606,9 @@ struct Solver {
 
     void halo_unpack(int kind) {
         if (!is_slab) MF_FAIL("halo_unpack on a non-slab solver");
+        if (!have_geometry) MF_FAIL("halo_unpack before geometry");
         const int bt = 128;
-        const dim3 g1(ceil_div(L.NY1, bt), L.NZ1), g4(ceil_div(L.NY4, bt), L.NZ4);
+        const dim3 g1(ceil_div(L.NY1, bt), L.NZ1), g4(ceil_div(L.PY, bt), L.PZ);
         if (kind == 0) {   // neighbour's real boundary column -> my ghost column
             if (slab.has_left) { k_halo_pdf<T, true, false><<<g1, bt, 0, stream>>>(L, d_recv[0][0], 0); count(); }          // left's column nx (ex=+1) -> ghost 0
             if (slab.has_right) { k_halo_pdf<T, false, false><<<g1, bt, 0, stream>>>(L, d_recv[0][1], L.nx + 1); count(); } // right's column 1 (ex=-1) -> ghost nx+1
@@ -497,8 +625,8 @@ struct Solver {
     void* device_ptr(const char* name) {
 #define MF_PTR(n, p) if (!strcmp(name, n)) return (void*)(p)
         MF_PTR("pdf", d_pdf); MF_PTR("phi", d_phi); MF_PTR("cn_x", d_cnx); MF_PTR("cn_y", d_cny); MF_PTR("cn_z", d_cnz); MF_PTR("c_norm", d_cnorm);
-        MF_PTR("curv", d_curv); MF_PTR("W_in", d_Win); MF_PTR("f_convec", d_fconv); MF_PTR("g_convec", d_gconv); MF_PTR("phi_convec", d_phiconv);
-        MF_PTR("walls", d_walls); MF_PTR("walls_type", d_wtype); MF_PTR("s_nx", d_snx); MF_PTR("s_ny", d_sny); MF_PTR("s_nz", d_snz);
+        MF_PTR("curv", d_curvc); MF_PTR("W_in", d_Win); MF_PTR("f_convec", d_fconv); MF_PTR("g_convec", d_gconv); MF_PTR("phi_convec", d_phiconv);
+        MF_PTR("types", d_types); MF_PTR("site_map", d_cmap); MF_PTR("fluid_sites", d_flu);
 #undef MF_PTR
         return nullptr;
     }
@@ -561,7 +689,7 @@ using namespace mflbm;
     extern "C" int mflbm_##P##_run(mflbm_##P##_solver* s, int ntime_first, int nsteps) {                                                  \
         MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->run(ntime_first, nsteps); })                                                           \
     }                                                                                                                                     \
-    extern "C" int mflbm_##P##_color_gradient(mflbm_##P##_solver* s) { MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->gradient_chain(true); }) } \
+    extern "C" int mflbm_##P##_color_gradient(mflbm_##P##_solver* s) { MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->gradient_chain(); }) } \
     extern "C" int mflbm_##P##_monitor(mflbm_##P##_solver* s, mflbm_monitor_out* out) { MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->monitor(out); }) } \
     extern "C" int mflbm_##P##_sync(mflbm_##P##_solver* s) {                                                                              \
         MF_GUARD({ MF_NEED(s); MF_CUDA(cudaStreamSynchronize(MF_SOLVER(P, REAL)->stream)); })                                             \

@@ -265,20 +265,25 @@ class Solver:
                                     self._in(W_in, self.rt, (self.ny + 2, self.nx + 2)))
         self._check(rc)
 
-    def download_state(self, convective: bool | None = None) -> dict:
+    def download_state(self, convective: bool | None = None, fields=None) -> dict:
+        """fields: optional subset of ("pdf","phi","cn_x","cn_y","cn_z","c_norm","curv") to fetch (default all)"""
         if convective is None:
-            convective = self.params.outlet_BC == 1
+            convective = self.params.outlet_BC == 1 and fields is None
         s1, s2, s4 = self._shape(1), self._shape(2), self._shape(4)
         pl = (self.ny + 2, self.nx + 2)
-        out = dict(pdf=np.empty((2, 19) + s1, self.rt), phi=np.empty(s4, self.rt), cn_x=np.empty(s2, self.rt), cn_y=np.empty(s2, self.rt),
-                   cn_z=np.empty(s2, self.rt), c_norm=np.empty(s2, self.rt), curv=np.empty(s1, self.rt))
+        shapes = dict(pdf=(2, 19) + s1, phi=s4, cn_x=s2, cn_y=s2, cn_z=s2, c_norm=s2, curv=s1)
+        out = {k: np.empty(shp, self.rt) for k, shp in shapes.items() if fields is None or k in fields}
         if convective:
             out.update(f_convec=np.empty((19,) + pl, self.rt), g_convec=np.empty((19,) + pl, self.rt), phi_convec=np.empty(pl, self.rt))
+        self.download_state_into(out)
+        return out
+
+    def download_state_into(self, out: dict) -> None:
+        """fill caller-owned (e.g. pinned) numpy arrays; keys as returned by download_state, missing keys are skipped"""
         ptr = lambda k: out[k].ctypes.data if k in out else None
         rc = self._fn("download_state")(self.h, ptr("pdf"), ptr("phi"), ptr("cn_x"), ptr("cn_y"), ptr("cn_z"), ptr("c_norm"), ptr("curv"),
                                         ptr("f_convec"), ptr("g_convec"), ptr("phi_convec"))
         self._check(rc)
-        return out
 
     # -- stepping ------------------------------------------------------------------------------------
     def step(self, ntime: int):

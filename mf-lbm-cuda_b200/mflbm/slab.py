@@ -1,0 +1,283 @@
+"""x-slab domain decomposition of one lattice across the GPUs of a box: one process per GPU, NCCL over NVLink.
+
+The reference is single-GPU (README.md:119 lists multi-GPU as future work); this is new work.
+
+Partition: contiguous x ranges, full y and z.  x is never periodic and both x ends are walls
+(/root/reference/src/IO_multiphase.cpp:210-213), so the ranks form an open chain.
+
+What crosses a face and when (AA pattern, see DESIGN.md "x-slab exchange"):
+
+  even step  collide (local) -> PDF halo kind 0: my first/last REAL column, the five populations per component
+             that leave through that face (ex = -1 on the left face, ex = +1 on the right) -> neighbour's GHOST
+             column, so that the next odd pull finds them
+  odd step   collide (pull from x-e, push to x+e) -> PDF halo kind 1: what I pushed into my GHOST columns
+             -> the neighbour's REAL boundary column (the owner of those nodes)
+  both       -> boundary kernels (inlet/outlet/periodic/porous plate; they read the freshly landed columns and
+             write phi ghost planes) -> phi halo kind 2: four real columns per side -> neighbour's four phi ghost
+             columns (the colour-gradient chain depends on phi within Chebyshev radius 4) -> gradient chain, each
+             stage evaluated redundantly on the ghost columns it needs.
+
+No collective is needed on the data path; the monitor sums are combined with all_reduce.
+
+`SlabStepper` is backend-agnostic: it drives any object with the small `SlabBackend` interface below.  The product
+backend is `CudaSlab` (libmflbm.so through the C ABI, halo buffers exposed as zero-copy torch tensors); the CPU
+tests drive the same stepper over gloo with a numpy backend to check the protocol.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import time
+from dataclasses import dataclass
+
+import numpy as np
+
+KIND_PDF_EVEN, KIND_PDF_ODD, KIND_PHI = 0, 1, 2
+LEFT, RIGHT = 0, 1
+
+
+@dataclass
+class SlabRange:
+    rank: int
+    world: int
+    x0: int          # global index (1-based) of the first real column
+    nx_local: int
+
+    @property
+    def x1(self) -> int:
+        return self.x0 + self.nx_local - 1
+
+    @property
+    def has_left(self) -> bool:
+        return self.rank > 0
+
+    @property
+    def has_right(self) -> bool:
+        return self.rank < self.world - 1
+
+
+def partition(nx_global: int, world: int, rank: int) -> SlabRange:
+    """contiguous, balanced x ranges: the first nx % world ranks get one extra column"""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    base, rem = divmod(nx_global, world)
+    if base < 4 and world > 1:
+        raise ValueError(f"{nx_global} columns over {world} slabs: a slab must be at least 4 columns wide (phi halo)")
+    nx_local = base + (1 if rank < rem else 0)
+    x0 = 1 + rank * base + min(rank, rem)
+    return SlabRange(rank, world, x0, nx_local)
+
+
+class SlabStepper:
+    """Per-step sequencing of one slab: compute phases interleaved with the two halo exchanges.
+
+    backend interface:
+        step_phase(ntime, phase)            phase 0 collide, 1 boundary kernels, 2 gradient chain
+        halo_pack(kind) / halo_unpack(kind)
+        halo_tensors(kind, side) -> (send, recv) torch tensors (device of the backend)
+    """
+
+    def __init__(self, backend, rng: SlabRange, group=None):
+        import torch.distributed as dist
+        self.b, self.rng, self.dist, self.group = backend, rng, dist, group
+        self.exchanges = 0
+        self.last_ntime = None
+
+    def exchange(self, kind: int) -> None:
+        dist, r = self.dist, self.rng
+        if r.world == 1:
+            return
+        self.b.halo_pack(kind)
+        ops = []
+        # a message sent through my right face lands in my right neighbour's "left" receive buffer and vice versa
+        if r.has_left:
+            s, v = self.b.halo_tensors(kind, LEFT)
+            ops += [dist.P2POp(dist.isend, s, r.rank - 1, self.group), dist.P2POp(dist.irecv, v, r.rank - 1, self.group)]
+        if r.has_right:
+            s, v = self.b.halo_tensors(kind, RIGHT)
+            ops += [dist.P2POp(dist.isend, s, r.rank + 1, self.group), dist.P2POp(dist.irecv, v, r.rank + 1, self.group)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        self.b.halo_unpack(kind)
+        self.exchanges += 1
+
+    def step(self, ntime: int) -> None:
+        self.b.step_phase(ntime, 0)
+        self.exchange(KIND_PDF_ODD if ntime % 2 else KIND_PDF_EVEN)
+        self.b.step_phase(ntime, 1)
+        self.exchange(KIND_PHI)
+        self.b.step_phase(ntime, 2)
+        self.last_ntime = ntime
+
+    def run(self, ntime_first: int, nsteps: int) -> None:
+        for n in range(nsteps):
+            self.step(ntime_first + n)
+
+    def settle(self) -> None:
+        """Make every rank's OWN columns complete before they are gathered (checkpoint, field output).
+
+        After an even step the "before odd" boundary kernels (inlet, outlet, porous plate) of my neighbour write the
+        populations its next pull needs into ITS ghost copy of my boundary column (planes k = 0, nz+1, Z_porous_plate);
+        nothing on my side ever reads those entries, so my copy is stale.  Sending the ghost columns back to their owner
+        (the kind-1 message) makes the owner's copy equal to the single-domain array.  After an odd step the regular
+        kind-1 exchange has already done this."""
+        if self.last_ntime is not None and self.last_ntime % 2 == 0:
+            self.exchange(KIND_PDF_ODD)
+            self.exchanges -= 1
+
+
+class _DeviceArray:
+    """zero-copy view of a device buffer owned by libmflbm.so, for torch.as_tensor (CUDA array interface v2)"""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class CudaSlab:
+    """SlabBackend over libmflbm.so: one mflbm.Solver created with an mflbm_slab, on the current torch CUDA stream."""
+
+    def __init__(self, params, prec: str, rng: SlabRange, device: int, stream=None):
+        import torch
+        import mflbm
+        self.torch = torch
+        self.rng = rng
+        self.stream = stream if stream is not None else torch.cuda.Stream(device=device)
+        slab = mflbm.Slab(rng.x0, rng.nx_local, int(rng.has_left), int(rng.has_right)) if rng.world > 1 else None
+        self.solver = mflbm.Solver(params, prec, slab=slab, device=device, stream=self.stream.cuda_stream)
+        self.prec = prec
+        self._t = {}
+        if rng.world > 1:
+            typestr = "<f8" if prec == "f64" else "<f4"
+            with torch.cuda.device(device):
+                for kind in (0, 1, 2):
+                    for side in (LEFT, RIGHT):
+                        if (side == LEFT and not rng.has_left) or (side == RIGHT and not rng.has_right):
+                            continue
+                        s, r, n = self.solver.halo_buffers(kind, side)
+                        self._t[(kind, side)] = (torch.as_tensor(_DeviceArray(s, n, typestr), device=f"cuda:{device}"),
+                                                 torch.as_tensor(_DeviceArray(r, n, typestr), device=f"cuda:{device}"))
+
+    def step_phase(self, ntime, phase):
+        self.solver.step_phase(ntime, phase)
+
+    def halo_pack(self, kind):
+        self.solver.halo_pack(kind)
+
+    def halo_unpack(self, kind):
+        self.solver.halo_unpack(kind)
+
+    def halo_tensors(self, kind, side):
+        return self._t[(kind, side)]
+
+
+def reduce_monitor(m: dict, rng: SlabRange, params, dist, device=None) -> dict:
+    """combine per-slab monitor sums into the global figures of src/Monitor.cpp:111-171 (SUM / MAX all_reduce)"""
+    import torch
+    keys = ["vol1_sum", "vol2_sum", "mass1_sum", "mass2_sum", "vol1_full", "vol2_full", "mass1_full", "mass2_full",
+            "fl1_avg", "fl2_avg", "fl1_avg_whole", "fl2_avg_whole"]
+    sums = torch.tensor([m[k] for k in keys] + list(m["kinetic_energy"]), dtype=torch.float64, device=device)
+    mx = torch.tensor([m["umax"], float(m["nan_detected"])], dtype=torch.float64, device=device)
+    if rng.world > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    out = dict(zip(keys, sums[:len(keys)].tolist()))
+    out["kinetic_energy"] = sums[len(keys):].tolist()
+    out["umax"], out["nan_detected"] = float(mx[0]), int(mx[1])
+    out["saturation"] = out["vol1_sum"] / (out["vol1_sum"] + out["vol2_sum"])
+    out["saturation_full_domain"] = out["vol1_full"] / (out["vol1_full"] + out["vol2_full"])
+    out["ca"] = ((out["fl1_avg"] + out["fl2_avg"]) / float(params.A_xy)) * float(params.la_nu1) / float(params.lbm_gamma)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# bench leg for N > 1 (called by bench.py under torchrun): weak scaling, (S*N) x S x S cut into N slabs
+# ----------------------------------------------------------------------------------------------------------
+def bench_slabs(args, rank: int, world: int, local: int) -> dict | None:
+    import torch
+    import torch.distributed as dist
+    import bench as B
+    import mflbm
+    S, prec = args.size, args.prec
+    nxg = S * world
+    ctl = B.workload_control(nxg, S, S)
+    rng = partition(nxg, world, rank)
+    params = mflbm.derive_params(ctl, prec)
+    stream = torch.cuda.Stream(device=local)
+    with torch.cuda.stream(stream):
+        slab = CudaSlab(params, prec, rng, local, stream=stream)
+        t0 = time.perf_counter()
+        solid = B.workload_geometry_window(nxg, S, S, rng.x0 - 12, rng.x1 + 12, kind=args.geometry)
+        slab.solver.preprocess_geometry(solid)
+        t_geo = time.perf_counter() - t0
+        W = B.inlet_profile(ctl, prec)
+        W_local = np.ascontiguousarray(W[:, rng.x0 - 1:rng.x1 + 2])   # local columns 0..nx+1 of the global profile
+        slab.solver.init_state(1, ctl["initial_interface_position"], W_in=W_local)
+        stepper = SlabStepper(slab, rng)
+        stepper.run(1, args.warmup)
+        nt = 1 + args.warmup
+        torch.cuda.synchronize()
+        dist.barrier()
+        l0 = slab.solver.kernel_launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with B.ClockSampler(local) as clk:
+            torch.cuda.synchronize()
+            e0.record(stream)
+            stepper.run(nt, args.steps)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            dist.barrier()
+        nt += args.steps
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms[0])
+        launches = slab.solver.kernel_launches - l0
+        nf = torch.tensor([slab.solver.num_fluid_nodes], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(nf, op=dist.ReduceOp.SUM)
+        n_fluid = int(nf[0])
+        mon = reduce_monitor(slab.solver.monitor(), rng, params, dist, device=f"cuda:{local}")
+        # ---- end to end through the C ABI: pinned host state -> device, K steps, monitor + state back ----------
+        st = slab.solver.download_state()
+        pinned = {k: torch.from_numpy(v).pin_memory() for k, v in st.items()}
+        host = {k: v.numpy() for k, v in pinned.items()}
+        h2d = sum(v.nbytes for v in host.values())
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        slab.solver.upload_state(**{k: host[k] for k in ("pdf", "phi", "cn_x", "cn_y", "cn_z", "c_norm", "curv")},
+                                 f_convec=host.get("f_convec"), g_convec=host.get("g_convec"), phi_convec=host.get("phi_convec"))
+        stepper.run(nt, args.steps)
+        reduce_monitor(slab.solver.monitor(), rng, params, dist, device=f"cuda:{local}")
+        slab.solver.download_state_into(host)
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        t_e2e = float(te[0])
+    n_site = nxg * S * S
+    s_bytes = 8 if prec == "f64" else 4
+    bytes_step = 78 * s_bytes * n_fluid + n_site
+    peak, peak_src = B.hbm_peak()
+    ms_step = ms / args.steps
+    achieved = bytes_step / world / (ms_step * 1e-3) / 1e9    # per GPU
+    out = None
+    if rank == 0:
+        assert mon["nan_detected"] == 0, "simulation produced non-finite values"
+        out = {
+            "metric": "multiphase MLUPS (all lattice sites, reference definition src/main.cpp:270)", "value": n_site * args.steps / 1e6 / (ms * 1e-3),
+            "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": prec, "data": "synthetic",
+            "config": {"workload": f"{nxg}x{S}x{S} random sphere pack (radius 12, porosity ~0.4) = {S}^3 per GPU, drainage, velocity inlet + convective outlet, theta 45, {prec}",
+                       "lattice": [nxg, S, S], "fluid_nodes": n_fluid, "porosity": n_fluid / n_site, "parallelism": f"{world} x-slabs, NCCL send/recv halos",
+                       "l2": "state per GPU >> 126 MB L2 (inputs larger than L2, no flush needed)",
+                       "fluid_mlups": n_fluid * args.steps / 1e6 / (ms * 1e-3), "geometry_preprocess_s": t_geo,
+                       "saturation_full_domain": mon["saturation_full_domain"], "halo_exchanges_per_step": 2},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "bytes_model": "78*sizeof(real)*N_fluid + N_site per step, per GPU", "bytes_per_step": bytes_step / world},
+            "e2e": {"value": n_site * args.steps / 1e6 / t_e2e, "unit": "MLUPS", "h2d_bytes_per_step": h2d * world / args.steps,
+                    "d2h_bytes_per_step": h2d * world / args.steps,
+                    "what": "per rank: upload_state from pinned host + K steps + monitor (all_reduce) + download_state, through the C ABI"},
+            "gpu_launches": int(launches) * world,
+            "clocks": clk.summary(),
+        }
+    slab.solver.close()
+    return out

@@ -31,19 +31,26 @@ def launches(path):
     rows = [r for r in csv.reader(open(path, newline="")) if len(r) > 5]
     start = next(i for i, r in enumerate(rows) if r[0] == "ID")
     hdr = rows[start]
-    agg = collections.OrderedDict()
+    tim, rd, wr = collections.OrderedDict(), collections.defaultdict(float), collections.defaultdict(float)
+    scale = {"ns": 1.0, "nsecond": 1.0, "us": 1e3, "usecond": 1e3, "ms": 1e6, "msecond": 1e6, "s": 1e9, "second": 1e9,
+             "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     for r in rows[start + 1:]:
         d = dict(zip(hdr, r))
-        v = float(d["Metric Value"].replace(",", ""))
-        if d.get("Metric Unit", "ns") in ("us", "usecond"):
-            v *= 1e3
-        elif d.get("Metric Unit", "ns") in ("ms", "msecond"):
-            v *= 1e6
-        agg.setdefault(d["Kernel Name"], []).append(v)
-    tot = sum(sum(v) for v in agg.values())
-    print(f"{'kernel':90s} {'n':>5s} {'avg us':>10s} {'total us':>11s} {'share':>7s}")
-    for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
-        print(f"{k[:90]:90s} {len(v):5d} {sum(v) / len(v) / 1e3:10.1f} {sum(v) / 1e3:11.1f} {100 * sum(v) / tot:6.1f}%")
+        v = float(d["Metric Value"].replace(",", "")) * scale.get(d.get("Metric Unit", ""), 1.0)
+        k = d["Kernel Name"]
+        if d["Metric Name"] == "gpu__time_duration.sum":
+            tim.setdefault(k, []).append(v)
+        elif d["Metric Name"] == "dram__bytes_read.sum":
+            rd[k] += v
+        elif d["Metric Name"] == "dram__bytes_write.sum":
+            wr[k] += v
+    tot = sum(sum(v) for v in tim.values())
+    print(f"{'kernel':88s} {'n':>4s} {'avg us':>9s} {'total us':>10s} {'share':>6s} {'rd MB/launch':>13s} {'wr MB/launch':>13s} {'GB/s':>7s}")
+    for k, v in sorted(tim.items(), key=lambda kv: -sum(kv[1])):
+        n = len(v)
+        r_, w_ = rd.get(k, 0.0) / n / 1e6, wr.get(k, 0.0) / n / 1e6
+        bw = (r_ + w_) * 1e6 / (sum(v) / n) if (r_ + w_) else 0.0
+        print(f"{k[:88]:88s} {n:4d} {sum(v) / n / 1e3:9.1f} {sum(v) / 1e3:10.1f} {100 * sum(v) / tot:5.1f}% {r_:13.1f} {w_:13.1f} {bw:7.0f}")
 
 
 def full(path):
