@@ -41,7 +41,8 @@ template <typename T> __host__ __device__ constexpr T w_equ(int q) { return q ==
 //    The collide kernels run one thread per entry of the fluid range: warps are full, the even (local) step reads and
 //    writes perfectly contiguous, aligned rows, and no DRAM sector is shared between fluid and solid sites.  Solid
 //    and ghost sites keep their storage (the reference realises bounce-back through it).
-//  * curv is only ever consumed at fluid nodes: stored in the same compact order (curv_c[t]).
+//  * curv is not stored: the collide kernel (and the monitor) evaluate it from cn_* where it is consumed; the
+//    reference's dense curv array is produced on demand by download_state.
 template <typename T>
 struct Lattice {
     int nx, ny, nz;          // real nodes of this lattice (slab-local nx)
@@ -53,7 +54,7 @@ struct Lattice {
     int n_fluid;             // real fluid nodes = threads of the collide kernels
     long long NC;            // entries per PDF slot (>= (nx+2)(ny+2)(nz+2), multiple of 32)
     // state
-    T* pdf; T* phi; T* cn_x; T* cn_y; T* cn_z; T* c_norm; T* curv_c;
+    T* pdf; T* phi; T* cn_x; T* cn_y; T* cn_z; T* c_norm;
     T* W_in; T* f_convec; T* g_convec; T* phi_convec;
     // geometry
     const signed char* types;   // U: 0 fluid, -1 fluid boundary, 1 solid, 2 solid boundary (walls_type, Geometry_preprocessing.cpp:154-175)

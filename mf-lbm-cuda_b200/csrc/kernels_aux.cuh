@@ -201,16 +201,6 @@ __global__ void k_pdf_slot(const Lattice<T> L, T* __restrict__ dense_s1, T* __re
     if (TO_SLOT) slot[e] = dense_s1[c1]; else dense_s1[c1] = slot[e];
 }
 
-// curv: reference 1-ghost array -> fluid-node order (upload_state)
-template <typename T>
-__global__ void k_curv_gather(const Lattice<T> L, const T* __restrict__ curv_s1) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= L.n_fluid) return;
-    const int u = L.fl_u[t];
-    const int px = u % L.PX, r = u / L.PX, py = r % L.PY, pz = r / L.PY;   // = x+3, y+3, z+3
-    L.curv_c[t] = curv_s1[(px - 3) + (long long)L.NX1 * ((py - 3) + (long long)L.NY1 * (pz - 3))];
-}
-
 // =====================================================================================================
 // initial state: src/Init_multiphase.cpp:299-496 (options 1-5), u = v = w = 0, rho = 1
 // =====================================================================================================
@@ -294,7 +284,7 @@ __global__ void __launch_bounds__(256) k_monitor(const Lattice<T> L, const int* 
         T rho = ft[0];
 #pragma unroll
         for (int q = 1; q < 19; q++) rho = rho + ft[q];
-        const T tmp = lit<T>(0.5) * L.lbm_gamma * L.curv_c[t] * L.c_norm[u];
+        const T tmp = lit<T>(0.5) * L.lbm_gamma * curvature_at(L, u) * L.c_norm[u];
         const T fx = tmp * L.cn_x[u], fy = tmp * L.cn_y[u], fz = tmp * L.cn_z[u] + L.force_z;
         const T uu = ft[1] - ft[2] + ft[7] - ft[8] + ft[9] - ft[10] + ft[11] - ft[12] + ft[13] - ft[14] - lit<T>(0.5) * fx;
         const T v = ft[3] - ft[4] + ft[7] + ft[8] - ft[9] - ft[10] + ft[15] - ft[16] + ft[17] - ft[18] - lit<T>(0.5) * fy;

@@ -7,6 +7,40 @@
 
 namespace mflbm {
 
+// the three 18-point isotropic first-derivative patterns used by :765-791 and :916-996
+template <typename T, int A>
+__device__ __forceinline__ T iso4(const T* __restrict__ p, const int c, const int sy, const int sz) {
+    constexpr int D[3][4][3] = {{{1, 1, 0}, {1, -1, 0}, {1, 0, 1}, {1, 0, -1}},
+                                {{1, 1, 0}, {-1, 1, 0}, {0, 1, 1}, {0, 1, -1}},
+                                {{1, 0, 1}, {-1, 0, 1}, {0, 1, 1}, {0, -1, 1}}};
+    constexpr int a0 = (A == 0) ? 1 : 0, a1 = (A == 1) ? 1 : 0, a2 = (A == 2) ? 1 : 0;
+    const int oa = a0 + sy * a1 + sz * a2;
+    const T axis = p[c + oa] - p[c - oa];
+    T s = T(0);
+#pragma unroll
+    for (int n = 0; n < 4; n++) {
+        const int o = D[A][n][0] + sy * D[A][n][1] + sz * D[A][n][2];
+        const T plus = p[c + o], minus = p[c - o];
+        s = (n == 0) ? (plus - minus) : (s + plus - minus);
+    }
+    constexpr T ISO4_0 = T(1) / T(6), ISO4_1 = T(1) / T(12);   // includes/Fluid_multiphase.h:34
+    return ISO4_0 * axis + ISO4_1 * s;
+}
+
+// interface curvature from nine derivatives of cn (:908-1003) at U index c2.
+// cn*cn replaces the reference's pow(cn, 2) (<= 2 ulp apart in double, see DESIGN.md).
+template <typename T>
+__device__ __forceinline__ T curvature_at(const Lattice<T>& L, const int c2) {
+    const int sy = L.sy, sz = L.sz;
+    const T kxx = iso4<T, 0>(L.cn_x, c2, sy, sz), kyy = iso4<T, 1>(L.cn_y, c2, sy, sz), kzz = iso4<T, 2>(L.cn_z, c2, sy, sz);
+    const T kxy = iso4<T, 1>(L.cn_x, c2, sy, sz), kxz = iso4<T, 2>(L.cn_x, c2, sy, sz);
+    const T kyx = iso4<T, 0>(L.cn_y, c2, sy, sz), kyz = iso4<T, 2>(L.cn_y, c2, sy, sz);
+    const T kzx = iso4<T, 0>(L.cn_z, c2, sy, sz), kzy = iso4<T, 1>(L.cn_z, c2, sy, sz);
+    const T cx = L.cn_x[c2], cy = L.cn_y[c2], cz = L.cn_z[c2];
+    return (cx * cx - lit<T>(1.)) * kxx + (cy * cy - lit<T>(1.)) * kyy + (cz * cz - lit<T>(1.)) * kzz +
+           cx * cy * (kxy + kyx) + cx * cz * (kxz + kzx) + cy * cz * (kzy + kyz);
+}
+
 // =====================================================================================================
 // collide + stream, AA pattern.  ODD: pull f_q from x-e_q (slot q), collide, push f_q* to x+e_q (slot opc(q))
 // (:56-388).  EVEN: read local slot opc(q) as f_q, collide, write local slot q (:395-726).
@@ -17,9 +51,16 @@ namespace mflbm {
 // (cmap is 4 B per lattice site, L2-resident) and used for both the pull (x - e_q = x + e_opc(q)) and the push.
 // Solid and ghost storage is live: fluid nodes write into / read from solid neighbours, which is how the reference
 // realises (two-step-delayed) bounce-back; the data flow is kept bit for bit.
+//
+// The interface curvature (the reference's CSF_Forces kernel, :908-1003) is evaluated here, by the thread that
+// consumes it, from the cn_* arrays of the previous step: its 57 stencil loads hit L1/L2 and hide under the DRAM
+// time of the 76 PDF rows, and the curv array (one write + one read per fluid node and step, one launch) disappears.
 // =====================================================================================================
-template <typename T, int MRT, bool ODD>
-__global__ void __launch_bounds__(128) k_collide(const Lattice<T> L) {
+// VAR selects the instruction schedule (same arithmetic): bit 0 = the 38 PDF rows are requested first and the
+// curvature stencil is evaluated while they are in flight (compiler barrier); VAR >> 1 = CTAs per SM the register
+// budget is sized for (0 = unspecified).
+template <typename T, int MRT, bool ODD, int VAR>
+__global__ void __launch_bounds__(128, (VAR >> 1)) k_collide(const Lattice<T> L) {
     const int t = blockIdx.x * 128 + threadIdx.x;
     if (t >= L.n_fluid) return;
     const int u = L.fl_u[t];
@@ -43,8 +84,9 @@ __global__ void __launch_bounds__(128) k_collide(const Lattice<T> L) {
             g2[q] = p0[(long long)(opc(q) + 19) * NC + t];
         }
     }
+    if (VAR & 1) asm volatile("" ::: "memory");
     const T cnx = L.cn_x[u], cny = L.cn_y[u], cnz = L.cn_z[u];
-    const T tmp = lit<T>(0.5) * L.lbm_gamma * L.curv_c[t] * L.c_norm[u];   // :147
+    const T tmp = lit<T>(0.5) * L.lbm_gamma * curvature_at(L, u) * L.c_norm[u];   // :147
 
     const T phi_loc = collide_node<T, MRT>(L, g1, g2, cnx, cny, cnz, tmp);
     L.phi[u] = phi_loc;
@@ -87,26 +129,6 @@ __global__ void k_extrap_phi(const Lattice<T> L, const int* __restrict__ list, c
     L.phi[n] = phi_sum / weight_sum;
 }
 
-// the three 18-point isotropic first-derivative patterns used by :765-791 and :916-996
-template <typename T, int A>
-__device__ __forceinline__ T iso4(const T* __restrict__ p, const int c, const int sy, const int sz) {
-    constexpr int D[3][4][3] = {{{1, 1, 0}, {1, -1, 0}, {1, 0, 1}, {1, 0, -1}},
-                                {{1, 1, 0}, {-1, 1, 0}, {0, 1, 1}, {0, 1, -1}},
-                                {{1, 0, 1}, {-1, 0, 1}, {0, 1, 1}, {0, -1, 1}}};
-    constexpr int a0 = (A == 0) ? 1 : 0, a1 = (A == 1) ? 1 : 0, a2 = (A == 2) ? 1 : 0;
-    const int oa = a0 + sy * a1 + sz * a2;
-    const T axis = p[c + oa] - p[c - oa];
-    T s = T(0);
-#pragma unroll
-    for (int n = 0; n < 4; n++) {
-        const int o = D[A][n][0] + sy * D[A][n][1] + sz * D[A][n][2];
-        const T plus = p[c + o], minus = p[c - o];
-        s = (n == 0) ? (plus - minus) : (s + plus - minus);
-    }
-    constexpr T ISO4_0 = T(1) / T(6), ISO4_1 = T(1) / T(12);   // includes/Fluid_multiphase.h:34
-    return ISO4_0 * axis + ISO4_1 * s;
-}
-
 // interface normals from the phase-field gradient (:757-807) at the non-solid sites of [-1..n+2]^3 (the reference's
 // guard over-runs by one; not replicated).  Solid sites hold 0 from k_zero_solid_normals and are
 // never written again, which is what the reference stores there every step.
@@ -124,14 +146,21 @@ __global__ void __launch_bounds__(128) k_normals(const Lattice<T> L, const int* 
     L.cn_x[u] = gx; L.cn_y[u] = gy; L.cn_z[u] = gz; L.c_norm[u] = nrm;
 }
 
-// cn_* = c_norm = 0 at every solid site of [-1..n+2]^3 (:795-800); run once after the arrays are (re)initialised
+// State of the solid sites of [-1..n+2]^3 after one pass of the reference chain: normalDirectionsOfInterfaces zeroes
+// cn_* and c_norm at every solid site (:795-800), then extrapolateNormalToSolid overwrites cn_* at the solid-boundary
+// sites of [0..n+1]^3 (:880-906).  Run once after arrays were uploaded, so that k_normals never has to touch solids:
+// zero everything the chain leaves at zero, keep the extrapolated normals (the next collide's curvature reads them).
 template <typename T>
 __global__ void k_zero_solid_normals(const Lattice<T> L) {
     const int i = -1 + (int)(blockIdx.x * blockDim.x + threadIdx.x);
     const int j = -1 + (int)blockIdx.y, k = -1 + (int)blockIdx.z;
     if (i > L.nx + 2) return;
     const int u = L.u(i, j, k);
-    if (L.types[u] > 0) { L.cn_x[u] = T(0); L.cn_y[u] = T(0); L.cn_z[u] = T(0); L.c_norm[u] = T(0); }
+    const int ty = L.types[u];
+    if (ty <= 0) return;
+    L.c_norm[u] = T(0);
+    const bool extrapolated = ty == 2 && i >= 0 && i <= L.nx + 1 && j >= 0 && j <= L.ny + 1 && k >= 0 && k <= L.nz + 1;
+    if (!extrapolated) { L.cn_x[u] = T(0); L.cn_y[u] = T(0); L.cn_z[u] = T(0); }
 }
 
 // geometrical wetting model on fluid-boundary nodes: rotate cn so that n_w . cn = cos(theta), <= 4 secant
@@ -188,29 +217,6 @@ __global__ void k_extrap_cn(const Lattice<T> L, const int* __restrict__ list, co
         }
     }
     L.cn_x[c2] = sx / wsum; L.cn_y[c2] = sy / wsum; L.cn_z[c2] = sz / wsum;
-}
-
-// interface curvature from nine derivatives of cn (:908-1003) at U index c2.
-// cn*cn replaces the reference's pow(cn, 2) (<= 2 ulp apart in double, see DESIGN.md).
-template <typename T>
-__device__ __forceinline__ T curvature_at(const Lattice<T>& L, const int c2) {
-    const int sy = L.sy, sz = L.sz;
-    const T kxx = iso4<T, 0>(L.cn_x, c2, sy, sz), kyy = iso4<T, 1>(L.cn_y, c2, sy, sz), kzz = iso4<T, 2>(L.cn_z, c2, sy, sz);
-    const T kxy = iso4<T, 1>(L.cn_x, c2, sy, sz), kxz = iso4<T, 2>(L.cn_x, c2, sy, sz);
-    const T kyx = iso4<T, 0>(L.cn_y, c2, sy, sz), kyz = iso4<T, 2>(L.cn_y, c2, sy, sz);
-    const T kzx = iso4<T, 0>(L.cn_z, c2, sy, sz), kzy = iso4<T, 1>(L.cn_z, c2, sy, sz);
-    const T cx = L.cn_x[c2], cy = L.cn_y[c2], cz = L.cn_z[c2];
-    return (cx * cx - lit<T>(1.)) * kxx + (cy * cy - lit<T>(1.)) * kyy + (cz * cz - lit<T>(1.)) * kzz +
-           cx * cy * (kxy + kyx) + cx * cz * (kxz + kzx) + cy * cz * (kzy + kyz);
-}
-
-// stepping path: curvature where it is consumed (collide and the monitor read curv at fluid nodes only), stored in
-// the fluid-node order of the PDF slots
-template <typename T>
-__global__ void __launch_bounds__(128) k_curvature(const Lattice<T> L) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= L.n_fluid) return;
-    L.curv_c[t] = curvature_at(L, L.fl_u[t]);
 }
 
 // boundary array: the reference's dense curv over [1..n]^3 in its own 1-ghost layout (download_state only)

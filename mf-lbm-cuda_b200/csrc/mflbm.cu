@@ -5,14 +5,15 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "../../include/mflbm.h"
 #include "core.cuh"
-#include "kernels_aux.cuh"
 #include "kernels_step.cuh"
+#include "kernels_aux.cuh"
 
 namespace mflbm {
 
@@ -51,7 +52,7 @@ struct Solver {
     Lattice<T> L{};
     long long N1 = 0, N2 = 0, N4 = 0, NP = 0, PN = 0, NC = 0;   // cells of 1/2/4-ghost arrays, of an (NX1*NY1) plane, of the U grid, of a PDF slot
     // device state (layouts: core.cuh)
-    T *d_pdf = nullptr, *d_phi = nullptr, *d_cnx = nullptr, *d_cny = nullptr, *d_cnz = nullptr, *d_cnorm = nullptr, *d_curvc = nullptr;
+    T *d_pdf = nullptr, *d_phi = nullptr, *d_cnx = nullptr, *d_cny = nullptr, *d_cnz = nullptr, *d_cnorm = nullptr;
     T *d_Win = nullptr, *d_fconv = nullptr, *d_gconv = nullptr, *d_phiconv = nullptr;
     // device geometry
     signed char* d_types = nullptr;
@@ -75,6 +76,7 @@ struct Solver {
     // CUDA graph of one (odd, even) or (even, odd) step pair
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
     long long pair_launches = 0;
+    int variant = 0;   // kernel schedule variant (MFLBM_VARIANT, tuning only; results are identical)
 
     // ------------------------------------------------------------------------------------------------
     void zalloc(void** ptr, size_t bytes) {
@@ -95,6 +97,7 @@ struct Solver {
 
     void create(const Params* p, const mflbm_slab* sl, int dev, void* strm) {
         device = dev;
+        if (const char* v = getenv("MFLBM_VARIANT")) variant = atoi(v);
         MF_CUDA(cudaSetDevice(device));
         if (strm) { stream = (cudaStream_t)strm; own_stream = false; }
         else { MF_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true; }
@@ -136,7 +139,7 @@ struct Solver {
                     zalloc((void**)&d_recv[kind][side], sizeof(T) * n);
                 }
         }
-        L.pdf = d_pdf; L.phi = d_phi; L.cn_x = d_cnx; L.cn_y = d_cny; L.cn_z = d_cnz; L.c_norm = d_cnorm; L.curv_c = nullptr;
+        L.pdf = d_pdf; L.phi = d_phi; L.cn_x = d_cnx; L.cn_y = d_cny; L.cn_z = d_cnz; L.c_norm = d_cnorm;
         L.W_in = d_Win; L.f_convec = d_fconv; L.g_convec = d_gconv; L.phi_convec = d_phiconv;
         L.types = d_types; L.cmap = d_cmap; L.fl_u = nullptr;
         set_params(p);
@@ -147,7 +150,7 @@ struct Solver {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
         drop_graphs();
-        dfree(d_pdf); dfree(d_phi); dfree(d_cnx); dfree(d_cny); dfree(d_cnz); dfree(d_cnorm); dfree(d_curvc);
+        dfree(d_pdf); dfree(d_phi); dfree(d_cnx); dfree(d_cny); dfree(d_cnz); dfree(d_cnorm);
         dfree(d_Win); dfree(d_fconv); dfree(d_gconv); dfree(d_phiconv);
         dfree(d_types); dfree(d_cmap); dfree(d_flu); dfree(d_zstart);
         dfree(d_list_phi); dfree(d_mask_phi); dfree(d_list_cn); dfree(d_mask_cn); dfree(d_list_alter); dfree(d_list_n);
@@ -259,9 +262,7 @@ struct Solver {
         n_list_n = (int)ln.size();
         MF_CUDA(cudaMemcpyAsync(d_cmap, cmap.data(), sizeof(int) * (size_t)PN, cudaMemcpyHostToDevice, stream));
         MF_CUDA(cudaMemcpyAsync(d_zstart, zstart.data(), sizeof(int) * zstart.size(), cudaMemcpyHostToDevice, stream));
-        dfree(d_curvc);
-        zalloc((void**)&d_curvc, sizeof(T) * std::max<long long>(n_fluid, 1));
-        L.n_fluid = (int)n_fluid; L.fl_u = d_flu; L.curv_c = d_curvc;
+        L.n_fluid = (int)n_fluid; L.fl_u = d_flu;
         for (int a = 0; a < 3; a++) {
             dfree(d_sn[a]);
             MF_CUDA(cudaMalloc((void**)&d_sn[a], sizeof(T) * std::max(n_list_alter_all, 1)));
@@ -382,11 +383,7 @@ struct Solver {
         if (cnx || cny || cnz || cnorm) {   // the caller's arrays are not trusted to hold zeros in solids
             k_zero_solid_normals<T><<<grid_box(2, 128), 128, 0, stream>>>(L); check_launch(); count();
         }
-        if (curv) {
-            T* st = (T*)stage(sizeof(T) * N1);
-            MF_CUDA(cudaMemcpyAsync(st, curv, sizeof(T) * N1, cudaMemcpyHostToDevice, stream));
-            if (n_fluid) { k_curv_gather<T><<<ceil_div((int)n_fluid, 128), 128, 0, stream>>>(L, st); check_launch(); count(); }
-        }
+        (void)curv;   // curv is a pure function of cn_* (CSF_Forces, :908-1003): recomputed where it is consumed, never stored
         auto up = [&](T* d, const T* h, long long n) { if (h) MF_CUDA(cudaMemcpyAsync(d, h, sizeof(T) * n, cudaMemcpyHostToDevice, stream)); };
         up(d_Win, Win, NP); up(d_fconv, fconv, NP * 19); up(d_gconv, gconv, NP * 19); up(d_phiconv, phiconv, NP);
         MF_CUDA(cudaStreamSynchronize(stream));
@@ -436,7 +433,6 @@ struct Solver {
         if (Win) MF_CUDA(cudaMemcpyAsync(d_Win, Win, sizeof(T) * NP, cudaMemcpyHostToDevice, stream));
         MF_CUDA(cudaMemsetAsync(d_cnx, 0, sizeof(T) * PN, stream)); MF_CUDA(cudaMemsetAsync(d_cny, 0, sizeof(T) * PN, stream));
         MF_CUDA(cudaMemsetAsync(d_cnz, 0, sizeof(T) * PN, stream)); MF_CUDA(cudaMemsetAsync(d_cnorm, 0, sizeof(T) * PN, stream));
-        MF_CUDA(cudaMemsetAsync(d_curvc, 0, sizeof(T) * std::max<long long>(n_fluid, 1), stream));
         gradient_chain();
         MF_CUDA(cudaStreamSynchronize(stream));
     }
@@ -446,7 +442,8 @@ struct Solver {
     int plo() const { return slab.has_left ? 0 : 1; }
     int phi_() const { return slab.has_right ? L.nx + 1 : L.nx; }
 
-    // the five colour-gradient kernels, call order of src/main_iteration_GPU.cu:2027-2055
+    // the colour-gradient kernels, call order of src/main_iteration_GPU.cu:2027-2049; the fifth (CSF_Forces, :2052) is
+    // fused into the collide kernel of the next step
     void gradient_chain() {
         if (!have_geometry) MF_FAIL("gradient chain before geometry");
         const int bl = 128;
@@ -454,25 +451,34 @@ struct Solver {
         if (n_list_n) { k_normals<T><<<ceil_div(n_list_n, bl), bl, 0, stream>>>(L, d_list_n, n_list_n); check_launch(); count(); }
         if (n_list_alter) { k_alter<T><<<ceil_div(n_list_alter, bl), bl, 0, stream>>>(L, d_list_alter, d_sn[0], d_sn[1], d_sn[2], n_list_alter); check_launch(); count(); }
         if (n_list_cn) { k_extrap_cn<T><<<ceil_div(n_list_cn, bl), bl, 0, stream>>>(L, d_list_cn, d_mask_cn, n_list_cn); check_launch(); count(); }
-        if (n_fluid) { k_curvature<T><<<ceil_div((int)n_fluid, bl), bl, 0, stream>>>(L); check_launch(); count(); }
     }
 
-    template <int MRT>
+    template <int MRT, int VAR>
     void launch_collide(bool odd) {
         if (!n_fluid) return;
         const int g = ceil_div((int)n_fluid, 128);
-        if (odd) k_collide<T, MRT, true><<<g, 128, 0, stream>>>(L);
-        else k_collide<T, MRT, false><<<g, 128, 0, stream>>>(L);
+        if (odd) k_collide<T, MRT, true, VAR><<<g, 128, 0, stream>>>(L);
+        else k_collide<T, MRT, false, VAR><<<g, 128, 0, stream>>>(L);
         check_launch(); count();
     }
 
     void phase_collide(int ntime) {
         const bool odd = (ntime % 2) != 0;
         switch (P.mrt) {
-            case 1: launch_collide<1>(odd); break;
-            case 3: launch_collide<3>(odd); break;
-            case 4: launch_collide<4>(odd); break;
-            default: launch_collide<2>(odd); break;
+            case 1: launch_collide<1, 0>(odd); break;
+            case 3: launch_collide<3, 0>(odd); break;
+            case 4: launch_collide<4, 0>(odd); break;
+            default:
+                switch (variant) {
+                    case 1: launch_collide<2, 1>(odd); break;
+                    case 4: launch_collide<2, 4>(odd); break;
+                    case 5: launch_collide<2, 5>(odd); break;
+                    case 6: launch_collide<2, 6>(odd); break;
+                    case 7: launch_collide<2, 7>(odd); break;
+                    case 9: launch_collide<2, 9>(odd); break;
+                    default: launch_collide<2, 0>(odd); break;
+                }
+                break;
         }
     }
 
@@ -625,7 +631,7 @@ struct Solver {
     void* device_ptr(const char* name) {
 #define MF_PTR(n, p) if (!strcmp(name, n)) return (void*)(p)
         MF_PTR("pdf", d_pdf); MF_PTR("phi", d_phi); MF_PTR("cn_x", d_cnx); MF_PTR("cn_y", d_cny); MF_PTR("cn_z", d_cnz); MF_PTR("c_norm", d_cnorm);
-        MF_PTR("curv", d_curvc); MF_PTR("W_in", d_Win); MF_PTR("f_convec", d_fconv); MF_PTR("g_convec", d_gconv); MF_PTR("phi_convec", d_phiconv);
+        MF_PTR("W_in", d_Win); MF_PTR("f_convec", d_fconv); MF_PTR("g_convec", d_gconv); MF_PTR("phi_convec", d_phiconv);
         MF_PTR("types", d_types); MF_PTR("site_map", d_cmap); MF_PTR("fluid_sites", d_flu);
 #undef MF_PTR
         return nullptr;
