@@ -62,6 +62,10 @@ typedef struct mflbm_monitor_out {
     int32_t nan_detected;          /* any non-finite value met while reducing                               Monitor.cpp:244 */
     int32_t reserved;
     double* fl1;  double* fl2;  double* pre;  double* mass1;  double* mass2;  double* vol1;  double* vol2;   /* per z slice, may be NULL */
+    /* steady-state monitors and breakthrough test (src/Monitor.cpp:357-411, 447-466) */
+    double pre_w_sum, pre_nw_sum;          /* sum of rho over fluid nodes with phi < -0.99 / phi > 0.99             Monitor.cpp:379-388 */
+    int64_t n_w, n_nw;                     /* their counts */
+    int64_t outlet_phase1_count;           /* fluid nodes of slice nz-1 with phi > 0                                Monitor.cpp:452-459 */
 } mflbm_monitor_out;
 
 #define MFLBM_DECLARE_API(P, REAL)                                                                                        \
@@ -125,6 +129,13 @@ typedef struct mflbm_monitor_out {
     int mflbm_##P##_color_gradient(mflbm_##P##_solver* s);                                                               \
     /* monitor() reductions on the device; valid after an even ntime (PDFs in natural slots).  Synchronises.       */ \
     int mflbm_##P##_monitor(mflbm_##P##_solver* s, mflbm_monitor_out* out);                                              \
+    /* monitor_multiphase_steady_phasefield (src/Monitor.cpp:279-312): max |phi - phi_old| over fluid nodes, then   */ \
+    /* phi_old <- phi.  phi_old starts as the phi of the first call's predecessor: zero (the reference's calloc) or */ \
+    /* the initial phi when seed_from_current != 0 was passed once before (Init_multiphase.cpp:381-391).            */ \
+    int mflbm_##P##_phi_change(mflbm_##P##_solver* s, int seed_from_current, double* d_phi_max);                         \
+    /* compute_macro_vars (src/Misc.cpp:222-274) on the device: rho, u, v, w in the 1-ghost layout (zero at solid   */ \
+    /* nodes and ghosts), valid after an even ntime.  NULL skips an array.                                          */ \
+    int mflbm_##P##_download_macro(mflbm_##P##_solver* s, REAL* rho, REAL* u, REAL* v, REAL* w);                         \
     int mflbm_##P##_sync(mflbm_##P##_solver* s);                                                                         \
                                                                                                                          \
     /* ---- x-slab halo exchange (new).  The caller moves the packed buffers between neighbours (NCCL send/recv,   */ \

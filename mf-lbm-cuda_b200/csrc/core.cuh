@@ -41,6 +41,17 @@ template <typename T> __host__ __device__ constexpr T w_equ(int q) { return q ==
 //    The collide kernels run one thread per entry of the fluid range: warps are full, the even (local) step reads and
 //    writes perfectly contiguous, aligned rows, and no DRAM sector is shared between fluid and solid sites.  Solid
 //    and ghost sites keep their storage (the reference realises bounce-back through it).
+//  * Wall-link mailboxes.  In the reference a fluid node x next to a solid site s = x + e_o pushes f_o* into
+//    (s, slot opc(o)) on an odd step and pulls it back as f_opc(o) two steps later; no other thread ever touches that
+//    cell (its only reader and writer is the node at s + e_slot = x).  At porosity 0.44 there are 1.2 such links per
+//    fluid node, and as isolated 4/8-byte accesses into solid storage they cost a third of the odd step's DRAM traffic
+//    (32 B sector fetched for the read, fetched again to merge the partial write).  They live in a compact region at
+//    the END of the slot instead: entry mb0 + rank_o(x) of slot opc(o) (the slot the cell has in the reference; a slot
+//    only ever hosts links of one direction), rank_o = number of fluid entries before x that have a link in direction
+//    o, = wbase[(t>>5)*18 + o-1] + popc(ballot & lanes below) inside the odd kernel.  Consecutive threads hit
+//    consecutive elements, and a wall link is addressed exactly like a fluid neighbour (slot base + entry).  Every
+//    other kernel reaches the same cells through Lattice::f(); the arrays handed back by download_state place them
+//    at the reference's addresses.
 //  * curv is not stored: the collide kernel (and the monitor) evaluate it from cn_* where it is consumed; the
 //    reference's dense curv array is produced on demand by download_state.
 template <typename T>
@@ -52,14 +63,18 @@ struct Lattice {
     int x0;                  // global x of local column 1 (1 for a full lattice)
     int nx_global;
     int n_fluid;             // real fluid nodes = threads of the collide kernels
-    long long NC;            // entries per PDF slot (>= (nx+2)(ny+2)(nz+2), multiple of 32)
+    long long NC;            // entries per PDF slot: fluid nodes, other sites of the 1-ghost box, wall-link mailboxes (multiple of 128)
     // state
     T* pdf; T* phi; T* cn_x; T* cn_y; T* cn_z; T* c_norm;
     T* W_in; T* f_convec; T* g_convec; T* phi_convec;
     // geometry
     const signed char* types;   // U: 0 fluid, -1 fluid boundary, 1 solid, 2 solid boundary (walls_type, Geometry_preprocessing.cpp:154-175)
-    const int* cmap;            // U: index of the site inside a PDF slot, -1 outside the 1-ghost box
+    const int* cmap;            // U: entry of the site inside a PDF slot: e >= 0 for non-solid sites, -(e + 2) for solid-type
+                                //    sites (they keep an entry, see f()), -1 outside the 1-ghost box
     const int* fl_u;            // [n_fluid] U index of the t-th fluid node
+    // wall-link mailboxes (see above)
+    int mb0;                    // first mailbox entry of every slot
+    const int* wbase;           // [ceil(n_fluid/32)][18] rank of the first link of each 32-entry group
     // constants uploaded by copyConstantData in the reference (src/main_iteration_GPU.cu:14-47)
     T lbm_gamma, force_z, la_nui1, la_nui2, lbm_beta, RK_weight2, phi_inlet, relaxation, sa_inject, uin_avg, cos_theta;
     T rho_in, rho_out;
@@ -70,8 +85,26 @@ struct Lattice {
     __device__ __forceinline__ int iplane(int x, int y) const { return x + NX1 * y; }          // W_in, *_convec
     __device__ __forceinline__ bool solid(int uu) const { return types[uu] > 0; }
     __device__ __forceinline__ T* slot(int q, int g) const { return pdf + (long long)(q + 19 * g) * NC; }
-    // PDF of slot (q,g) at the site with U index uu (must lie in the 1-ghost box)
-    __device__ __forceinline__ T& f(int q, int g, int uu) const { return pdf[(long long)(q + 19 * g) * NC + cmap[uu]]; }
+    __device__ __forceinline__ static int entry_of(int c) { return c >= 0 ? c : -c - 2; }
+    // entry of the mailbox of link (fluid entry t, direction o) in slot opc(o); slow path (walks the 32-entry group),
+    // for the plane kernels and layout conversion only
+    __device__ int mail_index(int t, int o) const {
+        int r = mb0 + wbase[(t >> 5) * 18 + (o - 1)];
+        for (int tt = t & ~31; tt < t; tt++) r += cmap[fl_u[tt] + off(o)] < -1 ? 1 : 0;
+        return r;
+    }
+    // PDF of slot (q,g) at the site with U index uu (must lie in the 1-ghost box), wherever it is stored
+    __device__ __forceinline__ T& f(int q, int g, int uu) const {
+        const int c = cmap[uu];
+        if (c >= 0) return pdf[(long long)(q + 19 * g) * NC + c];
+        if (q != 0) {   // solid-type site: the cell may be the private mailbox of the fluid node at uu + e_q
+            const int co = cmap[uu + off(q)];
+            if (co >= 0 && co < n_fluid) return pdf[(long long)(q + 19 * g) * NC + mail_index(co, opc(q))];
+        }
+        return pdf[(long long)(q + 19 * g) * NC + (-c - 2)];
+    }
+    // the cell in slot storage proper, never a mailbox (x-slab halo columns, see k_halo_pdf)
+    __device__ __forceinline__ T& f_raw(int q, int g, int uu) const { return pdf[(long long)(q + 19 * g) * NC + entry_of(cmap[uu])]; }
 };
 
 // MRT relaxation rates, src/main_iteration_GPU.cu:157-186.  MRT is a template parameter so that the compiler folds

@@ -190,15 +190,15 @@ __global__ void k_list_s4(const Lattice<T> L, const int* __restrict__ list, cons
     if (GATHER) compact[t] = s4[c4]; else s4[c4] = compact[t];
 }
 
-// one PDF slot: dense 1-ghost array (reference order) <-> permuted slot
+// one PDF slot: dense 1-ghost array (reference order) <-> internal storage (permuted slot / wall-link mailboxes)
 template <typename T, bool TO_SLOT>
-__global__ void k_pdf_slot(const Lattice<T> L, T* __restrict__ dense_s1, T* __restrict__ slot) {
+__global__ void k_pdf_slot(const Lattice<T> L, T* __restrict__ dense_s1, const int slot) {
     const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     const int y = (int)blockIdx.y, z = (int)blockIdx.z;
     if (x > L.nx + 1) return;
     const long long c1 = x + (long long)L.NX1 * (y + (long long)L.NY1 * z);
-    const int e = L.cmap[L.u(x, y, z)];
-    if (TO_SLOT) slot[e] = dense_s1[c1]; else dense_s1[c1] = slot[e];
+    T& cell = L.f(slot % 19, slot / 19, L.u(x, y, z));
+    if (TO_SLOT) cell = dense_s1[c1]; else dense_s1[c1] = cell;
 }
 
 // =====================================================================================================
@@ -243,11 +243,10 @@ __global__ void k_init_pdf(const Lattice<T> L, int outlet_convective) {
     const T ph = L.phi[u];
     const T rho1 = mul_rn(mul_rn(T(1), add_rn(T(1), ph)), lit<T>(0.5));
     const T rho2 = mul_rn(mul_rn(T(1), sub_rn(T(1), ph)), lit<T>(0.5));
-    const int e = L.cmap[u];
-#pragma unroll
+#pragma unroll 1
     for (int q = 0; q < 19; q++) {
-        L.slot(q, 0)[e] = mul_rn(rho1, w_equ<T>(q));
-        L.slot(q, 1)[e] = mul_rn(rho2, w_equ<T>(q));
+        L.f(q, 0, u) = mul_rn(rho1, w_equ<T>(q));
+        L.f(q, 1, u) = mul_rn(rho2, w_equ<T>(q));
     }
     if (outlet_convective && k == L.nz) {   // :445-494
         const int cb = L.iplane(i, j), plane = L.NX1 * L.NY1;
@@ -266,9 +265,11 @@ __global__ void k_init_pdf(const Lattice<T> L, int outlet_convective) {
 // nodes of a slice are the contiguous range [zstart[k-1], zstart[k]) of the permuted order, so every PDF read is
 // a contiguous row.  Warp-shuffle + block reduction, sums in double (the reference sums sequentially in T; see
 // DESIGN.md).
-// out layout per slice k-1: [0..6] fl1, fl2, pre, mass1, mass2, vol1, vol2, [7] max |u|^2, [8] usq1, [9] usq2, [10] nan flag
+// out layout per slice k-1: [0..6] fl1, fl2, pre, mass1, mass2, vol1, vol2, [7] max |u|^2, [8] usq1, [9] usq2, [10] nan flag,
+// [11] sum rho where phi < -0.99, [12] their count, [13] sum rho where phi > 0.99, [14] their count, [15] count phi > 0
+// (src/Monitor.cpp:376-390, 452-459)
 // =====================================================================================================
-#define MFLBM_MON_N 11
+#define MFLBM_MON_N 16
 template <typename T>
 __global__ void __launch_bounds__(256) k_monitor(const Lattice<T> L, const int* __restrict__ zstart, double* __restrict__ out) {
     const int k = 1 + blockIdx.x;
@@ -297,6 +298,9 @@ __global__ void __launch_bounds__(256) k_monitor(const Lattice<T> L, const int* 
         acc[7] = fmax(acc[7], (double)usq);
         if (ph > lit<T>(0.999)) acc[8] += (double)usq; else if (ph < lit<T>(-0.999)) acc[9] += (double)usq;
         if (!(isfinite((double)usq) && isfinite((double)rho) && isfinite((double)ph))) acc[10] = 1.0;
+        if (ph < lit<T>(-0.99)) { acc[11] += (double)rho; acc[12] += 1.0; }
+        if (ph > lit<T>(0.99)) { acc[13] += (double)rho; acc[14] += 1.0; }
+        if (ph > lit<T>(0.)) acc[15] += 1.0;
     }
     __shared__ double sm[MFLBM_MON_N][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -321,6 +325,58 @@ __global__ void __launch_bounds__(256) k_monitor(const Lattice<T> L, const int* 
     }
 }
 
+// monitor_multiphase_steady_phasefield (src/Monitor.cpp:288-312): max |phi - phi_old| over the real fluid nodes, then
+// phi_old <- phi there.  phi_old is indexed by fluid entry (the reference's dense copy is only ever read at fluid nodes).
+// MODE 0: reduce + update, MODE 1: seed phi_old from the current phi (Init_multiphase.cpp:381-391).
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) k_phi_change(const Lattice<T> L, T* __restrict__ phi_old, double* __restrict__ out) {
+    double m = 0.0;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < L.n_fluid; t += gridDim.x * blockDim.x) {
+        const T ph = L.phi[L.fl_u[t]];
+        if (MODE == 0) {
+            const T d = fabs(ph - phi_old[t]);
+            // the reference's `d_phi_max < tmp2` never selects a NaN; report it instead of hiding it
+            m = (d != d) ? (double)d : fmax(m, (double)d);
+        }
+        phi_old[t] = ph;
+    }
+    if (MODE != 0) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const double other = __shfl_xor_sync(0xffffffffu, m, o); m = (other != other || m != m) ? (m != m ? m : other) : fmax(m, other); }
+    __shared__ double sm[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) sm[warp] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = sm[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) v = (sm[w] != sm[w] || v != v) ? (v != v ? v : sm[w]) : fmax(v, sm[w]);
+        out[blockIdx.x] = v;
+    }
+}
+
+// compute_macro_vars (src/Misc.cpp:222-274) for field output: rho, u, v, w at the real fluid nodes, written into dense
+// 1-ghost arrays (pre-zeroed: the reference multiplies by (1 - wall_indicator) and never touches ghosts).
+template <typename T>
+__global__ void __launch_bounds__(128) k_macro(const Lattice<T> L, T* __restrict__ rho_s1, T* __restrict__ u_s1, T* __restrict__ v_s1, T* __restrict__ w_s1) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= L.n_fluid) return;
+    const int u = L.fl_u[t];
+    T ft[19];
+#pragma unroll
+    for (int q = 0; q < 19; q++) ft[q] = L.slot(q, 0)[t] + L.slot(q, 1)[t];
+    T rho = ft[0];
+#pragma unroll
+    for (int q = 1; q < 19; q++) rho = rho + ft[q];
+    const T tmp = lit<T>(0.5) * L.lbm_gamma * curvature_at(L, u) * L.c_norm[u];
+    const T fx = tmp * L.cn_x[u], fy = tmp * L.cn_y[u], fz = tmp * L.cn_z[u] + L.force_z;
+    const int px = u % L.PX, r = u / L.PX, py = r % L.PY, pz = r / L.PY;   // U -> (x+3, y+3, z+3)
+    const long long c1 = (px - 3) + (long long)L.NX1 * ((py - 3) + (long long)L.NY1 * (pz - 3));
+    if (rho_s1) rho_s1[c1] = rho;
+    if (u_s1) u_s1[c1] = ft[1] - ft[2] + ft[7] - ft[8] + ft[9] - ft[10] + ft[11] - ft[12] + ft[13] - ft[14] - lit<T>(0.5) * fx;
+    if (v_s1) v_s1[c1] = ft[3] - ft[4] + ft[7] + ft[8] - ft[9] - ft[10] + ft[15] - ft[16] + ft[17] - ft[18] - lit<T>(0.5) * fy;
+    if (w_s1) w_s1[c1] = ft[5] - ft[6] + ft[11] + ft[12] - ft[13] - ft[14] + ft[15] + ft[16] - ft[17] - ft[18] - lit<T>(0.5) * fz;
+}
+
 // =====================================================================================================
 // x-slab halo exchange (new).  Buffers are dense [item][z][y] planes.
 // PDF halos carry the ten populations with ex = +1 (slots 1,7,9,11,13) or ex = -1 (2,8,10,12,14) of both
@@ -335,13 +391,17 @@ __global__ void k_halo_pdf(const Lattice<T> L, T* __restrict__ buf, const int co
     const int y = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
     if (y >= L.NY1) return;
     const int plane = L.NY1 * L.NZ1;
-    const int e = L.cmap[L.u(col, y, z)];
+    // slot storage proper (f_raw).  Wall links that end in a neighbour-facing ghost column are not mailboxes (Solver::
+    // finish_geometry), so everything a neighbour slab reads or writes lives in slot storage and is exchanged as is; a
+    // solid site of the real boundary column can additionally be the far end of a link of THIS slab's nodes, which keep
+    // that cell in a mailbox the exchange must not touch.
+    const int uu = L.u(col, y, z);
 #pragma unroll
     for (int g = 0; g < 2; g++) {
 #pragma unroll
         for (int n = 0; n < 5; n++) {
             const int q = PLUS ? slot_exp(n) : slot_exm(n);
-            T* cell = L.slot(q, g) + e;
+            T* cell = &L.f_raw(q, g, uu);
             T* b = buf + (long long)(g * 5 + n) * plane + (y + L.NY1 * z);
             if (PACK) *b = *cell; else *cell = *b;
         }

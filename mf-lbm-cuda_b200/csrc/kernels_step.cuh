@@ -41,71 +41,7 @@ __device__ __forceinline__ T curvature_at(const Lattice<T>& L, const int c2) {
            cx * cy * (kxy + kyx) + cx * cz * (kxz + kzx) + cy * cz * (kzy + kyz);
 }
 
-// =====================================================================================================
-// collide + stream, AA pattern.  ODD: pull f_q from x-e_q (slot q), collide, push f_q* to x+e_q (slot opc(q))
-// (:56-388).  EVEN: read local slot opc(q) as f_q, collide, write local slot q (:395-726).
-//
-// One thread per FLUID node, in the permuted site order of the PDF slots (core.cuh): thread t owns entry t of every
-// slot.  EVEN is a pure streaming kernel: 38 contiguous, 128-byte aligned row reads and 38 row writes per warp, no
-// index traffic.  ODD gathers/scatters through the site map: the 18 neighbour entries of a node are looked up once
-// (cmap is 4 B per lattice site, L2-resident) and used for both the pull (x - e_q = x + e_opc(q)) and the push.
-// Solid and ghost storage is live: fluid nodes write into / read from solid neighbours, which is how the reference
-// realises (two-step-delayed) bounce-back; the data flow is kept bit for bit.
-//
-// The interface curvature (the reference's CSF_Forces kernel, :908-1003) is evaluated here, by the thread that
-// consumes it, from the cn_* arrays of the previous step: its 57 stencil loads hit L1/L2 and hide under the DRAM
-// time of the 76 PDF rows, and the curv array (one write + one read per fluid node and step, one launch) disappears.
-// =====================================================================================================
-// VAR selects the instruction schedule (same arithmetic): bit 0 = the 38 PDF rows are requested first and the
-// curvature stencil is evaluated while they are in flight (compiler barrier); VAR >> 1 = CTAs per SM the register
-// budget is sized for (0 = unspecified).
-template <typename T, int MRT, bool ODD, int VAR>
-__global__ void __launch_bounds__(128, (VAR >> 1)) k_collide(const Lattice<T> L) {
-    const int t = blockIdx.x * 128 + threadIdx.x;
-    if (t >= L.n_fluid) return;
-    const int u = L.fl_u[t];
-    const long long NC = L.NC;
-    T g1[19], g2[19];
-    int nb[19];
-    const T* __restrict__ p0 = L.pdf;
-    if (ODD) {
-        nb[0] = t;
-#pragma unroll
-        for (int q = 1; q < 19; q++) nb[q] = L.cmap[u + L.off(q)];
-#pragma unroll
-        for (int q = 0; q < 19; q++) {
-            g1[q] = p0[(long long)q * NC + nb[opc(q)]];
-            g2[q] = p0[(long long)(q + 19) * NC + nb[opc(q)]];
-        }
-    } else {
-#pragma unroll
-        for (int q = 0; q < 19; q++) {
-            g1[q] = p0[(long long)opc(q) * NC + t];
-            g2[q] = p0[(long long)(opc(q) + 19) * NC + t];
-        }
-    }
-    if (VAR & 1) asm volatile("" ::: "memory");
-    const T cnx = L.cn_x[u], cny = L.cn_y[u], cnz = L.cn_z[u];
-    const T tmp = lit<T>(0.5) * L.lbm_gamma * curvature_at(L, u) * L.c_norm[u];   // :147
-
-    const T phi_loc = collide_node<T, MRT>(L, g1, g2, cnx, cny, cnz, tmp);
-    L.phi[u] = phi_loc;
-
-    T* __restrict__ po = L.pdf;
-    if (ODD) {
-#pragma unroll
-        for (int q = 0; q < 19; q++) {
-            po[(long long)opc(q) * NC + nb[q]] = g1[q];
-            po[(long long)(opc(q) + 19) * NC + nb[q]] = g2[q];
-        }
-    } else {
-#pragma unroll
-        for (int q = 0; q < 19; q++) {
-            po[(long long)q * NC + t] = g1[q];
-            po[(long long)(q + 19) * NC + t] = g2[q];
-        }
-    }
-}
+// (the AA collide + stream kernels are in kernels_collide.cuh)
 
 // =====================================================================================================
 // colour-gradient chain (:732-1003).  Every stage runs over a compact site list built once per geometry (the
@@ -421,17 +357,16 @@ __global__ void k_periodic_pdf(const Lattice<T> L, const int ilo, const int ihi)
     const int n = AXIS == 1 ? L.ny : L.nz, mlim = AXIS == 1 ? L.nz : L.ny;
     if (i > ihi || m > mlim) return;
     // the four sites involved: real layers 1 and n, ghost layers 0 and n+1
-    const int e1 = L.cmap[AXIS == 1 ? L.u(i, 1, m) : L.u(i, m, 1)], en = L.cmap[AXIS == 1 ? L.u(i, n, m) : L.u(i, m, n)];
-    const int e0 = L.cmap[AXIS == 1 ? L.u(i, 0, m) : L.u(i, m, 0)], ep = L.cmap[AXIS == 1 ? L.u(i, n + 1, m) : L.u(i, m, n + 1)];
+    const int u1 = AXIS == 1 ? L.u(i, 1, m) : L.u(i, m, 1), un = AXIS == 1 ? L.u(i, n, m) : L.u(i, m, n);
+    const int u0 = AXIS == 1 ? L.u(i, 0, m) : L.u(i, m, 0), up = AXIS == 1 ? L.u(i, n + 1, m) : L.u(i, m, n + 1);
 #pragma unroll
     for (int g = 0; g < 2; g++) {
 #pragma unroll
         for (int q = 1; q < 19; q++) {
             const int s = AXIS == 1 ? ey(q) : ez(q);
             if (s == 0) continue;
-            const int a = s < 0 ? e1 : en, b = s < 0 ? ep : e0;   // real layer a <-> ghost layer b
-            T* p = L.slot(q, g);
-            if (ODD) p[a] = p[b]; else p[b] = p[a];
+            const int a = s < 0 ? u1 : un, b = s < 0 ? up : u0;   // real layer a <-> ghost layer b
+            if (ODD) L.f(q, g, a) = L.f(q, g, b); else L.f(q, g, b) = L.f(q, g, a);
         }
     }
 }

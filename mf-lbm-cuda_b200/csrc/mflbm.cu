@@ -13,6 +13,7 @@
 #include "../../include/mflbm.h"
 #include "core.cuh"
 #include "kernels_step.cuh"
+#include "kernels_collide.cuh"
 #include "kernels_aux.cuh"
 
 namespace mflbm {
@@ -56,7 +57,8 @@ struct Solver {
     T *d_Win = nullptr, *d_fconv = nullptr, *d_gconv = nullptr, *d_phiconv = nullptr;
     // device geometry
     signed char* d_types = nullptr;
-    int *d_cmap = nullptr, *d_flu = nullptr, *d_zstart = nullptr;
+    int *d_cmap = nullptr, *d_flu = nullptr, *d_zstart = nullptr, *d_wbase = nullptr;
+    long long n_links = 0;   // wall links (core.cuh)
     int *d_list_phi = nullptr, *d_mask_phi = nullptr, *d_list_cn = nullptr, *d_mask_cn = nullptr, *d_list_alter = nullptr, *d_list_n = nullptr;
     T* d_sn[3] = {nullptr, nullptr, nullptr};   // solid-surface normals in d_list_alter order
     int n_list_phi = 0, n_list_cn = 0, n_list_alter = 0, n_list_alter_all = 0, n_list_n = 0;
@@ -70,6 +72,7 @@ struct Solver {
     // monitor
     double* d_mon = nullptr;
     double* h_mon = nullptr;
+    T* d_phi_old = nullptr;   // steady-state monitor 2 (src/Monitor.cpp:279), per fluid entry, allocated on first use
     // halo buffers: [kind 0..2][side 0..1]
     T* d_send[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
     T* d_recv[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
@@ -77,6 +80,10 @@ struct Solver {
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
     long long pair_launches = 0;
     int variant = 0;   // kernel schedule variant (MFLBM_VARIANT, tuning only; results are identical)
+    int num_sms = 148;
+    // true when c_norm == 0 implies cn_* == 0 at every fluid node: established by k_normals (every gradient_chain), not
+    // guaranteed for arrays handed in through upload_state.  Lets the collide kernels skip cn/curvature in the bulk.
+    bool cn_consistent = false;
 
     // ------------------------------------------------------------------------------------------------
     void zalloc(void** ptr, size_t bytes) {
@@ -99,6 +106,7 @@ struct Solver {
         device = dev;
         if (const char* v = getenv("MFLBM_VARIANT")) variant = atoi(v);
         MF_CUDA(cudaSetDevice(device));
+        MF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
         if (strm) { stream = (cudaStream_t)strm; own_stream = false; }
         else { MF_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true; }
         if (p->nx < 3 || p->ny < 3 || p->nz < 3) MF_FAIL("lattice too small");
@@ -117,10 +125,8 @@ struct Solver {
         N4 = (long long)(L.nx + 8) * (L.ny + 8) * (L.nz + 8);
         NP = (long long)L.NX1 * L.NY1;
         PN = (long long)L.PX * L.PY * L.PZ;
-        NC = 32 * ((N1 + 31) / 32);
         if (PN >= (1LL << 31)) MF_FAIL("lattice (or slab) exceeds 2^31 cells per field; decompose into more slabs");
-        L.sy = L.PX; L.sz = L.PX * L.PY; L.NC = NC; L.n_fluid = 0;
-        zalloc((void**)&d_pdf, sizeof(T) * NC * 38);
+        L.sy = L.PX; L.sz = L.PX * L.PY; L.NC = 0; L.n_fluid = 0;   // the PDF slots are sized by the geometry (finish_geometry)
         zalloc((void**)&d_phi, sizeof(T) * PN);
         zalloc((void**)&d_cnx, sizeof(T) * PN); zalloc((void**)&d_cny, sizeof(T) * PN); zalloc((void**)&d_cnz, sizeof(T) * PN);
         zalloc((void**)&d_cnorm, sizeof(T) * PN);
@@ -152,10 +158,10 @@ struct Solver {
         drop_graphs();
         dfree(d_pdf); dfree(d_phi); dfree(d_cnx); dfree(d_cny); dfree(d_cnz); dfree(d_cnorm);
         dfree(d_Win); dfree(d_fconv); dfree(d_gconv); dfree(d_phiconv);
-        dfree(d_types); dfree(d_cmap); dfree(d_flu); dfree(d_zstart);
+        dfree(d_types); dfree(d_cmap); dfree(d_flu); dfree(d_zstart); dfree(d_wbase);
         dfree(d_list_phi); dfree(d_mask_phi); dfree(d_list_cn); dfree(d_mask_cn); dfree(d_list_alter); dfree(d_list_n);
         for (auto& q : d_sn) dfree(q);
-        dfree(d_mon);
+        dfree(d_mon); dfree(d_phi_old);
         if (d_stage) { cudaFree(d_stage); d_stage = nullptr; }
         for (int kind = 0; kind < 3; kind++) for (int side = 0; side < 2; side++) { dfree(d_send[kind][side]); dfree(d_recv[kind][side]); }
         if (h_mon) { cudaFreeHost(h_mon); h_mon = nullptr; }
@@ -208,6 +214,7 @@ struct Solver {
     // list-driven kernel.  List construction runs on the host (once per geometry).
     void finish_geometry(const int* d_wtype, T* const d_sn4[3]) {
         k_types_to_u<T><<<dim3(ceil_div(L.PX, 128), L.PY, L.PZ), 128, 0, stream>>>(L, d_wtype, d_types); check_launch(); count();
+        dfree(d_phi_old);   // indexed by fluid entry: invalid for a new geometry
         std::vector<signed char> ty((size_t)PN);
         MF_CUDA(cudaMemcpyAsync(ty.data(), d_types, (size_t)PN, cudaMemcpyDeviceToHost, stream));
         MF_CUDA(cudaStreamSynchronize(stream));
@@ -249,7 +256,33 @@ struct Solver {
         for (int z = nz; z >= 1; z--) if (zstart[(size_t)z] < zstart[(size_t)z - 1]) zstart[(size_t)z] = zstart[(size_t)z - 1];
         n_fluid = (long long)flu.size();
         for (size_t n = 0; n < flu.size(); n++) cmap[(size_t)flu[n]] = (int)n;
-        for (size_t n = 0; n < passive.size(); n++) cmap[(size_t)passive[n]] = (int)(flu.size() + n);
+        for (size_t n = 0; n < passive.size(); n++) {
+            const int e = (int)(flu.size() + n);
+            // solid-type sites are marked (Lattice::f) - except in a ghost column that mirrors a neighbour slab: links that
+            // end there stay in slot storage, which is what the halo messages carry
+            const int px = passive[n] % PX - 3;
+            const bool halo_col = (px == 0 && slab.has_left) || (px == nx + 1 && slab.has_right);
+            cmap[(size_t)passive[n]] = (ty[(size_t)passive[n]] > 0 && !halo_col) ? -(e + 2) : e;
+        }
+        // wall links: rank of every link inside its direction, per 32-entry group (core.cuh)
+        std::vector<int> wbase(((flu.size() + 31) / 32) * 18 + 18, 0);
+        long long cnt[19] = {0};
+        for (size_t n = 0; n < flu.size(); n++) {
+            if ((n & 31) == 0) for (int q = 1; q < 19; q++) wbase[(n >> 5) * 18 + (q - 1)] = (int)cnt[q];
+            for (int q = 1; q < 19; q++) if (cmap[(size_t)(flu[n] + offq[q])] < -1) cnt[q]++;
+        }
+        n_links = 0;
+        long long max_links = 0;
+        for (int q = 1; q < 19; q++) { n_links += cnt[q]; max_links = std::max(max_links, cnt[q]); }
+        // slot = [fluid nodes | other sites of the 1-ghost box | pad to whole 128-entry tiles (+1: the TMA row copies of the
+        // last fluid tile stay inside the slot) | mailboxes of the one link direction the slot hosts]
+        const long long mb0 = 128 * ((N1 + 127) / 128) + 128;
+        NC = mb0 + 128 * ((max_links + 127) / 128);
+        if (NC >= (1LL << 31) - 2) MF_FAIL("PDF slot exceeds 2^31 entries; decompose into more slabs");
+        L.mb0 = (int)mb0; L.NC = NC;
+        dfree(d_pdf);
+        zalloc((void**)&d_pdf, sizeof(T) * NC * 38);
+        L.pdf = d_pdf;
         std::vector<int> lalt(lalt_in);
         lalt.insert(lalt.end(), lalt_out.begin(), lalt_out.end());
         auto up = [&](int*& d, const std::vector<int>& v) {
@@ -257,6 +290,7 @@ struct Solver {
             MF_CUDA(cudaMalloc((void**)&d, sizeof(int) * std::max<size_t>(v.size(), 1)));
             if (!v.empty()) MF_CUDA(cudaMemcpyAsync(d, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice, stream));
         };
+        up(d_wbase, wbase); L.wbase = d_wbase;
         up(d_flu, flu); up(d_list_phi, lphi); up(d_mask_phi, mphi); up(d_list_cn, lcn); up(d_mask_cn, mcn); up(d_list_alter, lalt); up(d_list_n, ln);
         n_list_phi = (int)lphi.size(); n_list_cn = (int)lcn.size(); n_list_alter = (int)lalt_in.size(); n_list_alter_all = (int)lalt.size();
         n_list_n = (int)ln.size();
@@ -371,7 +405,7 @@ struct Solver {
             for (int s = 0; s < 38; s++) {
                 T* st = (T*)stage(sizeof(T) * N1);
                 MF_CUDA(cudaMemcpyAsync(st, pdf + (size_t)s * N1, sizeof(T) * N1, cudaMemcpyHostToDevice, stream));
-                k_pdf_slot<T, true><<<g, 128, 0, stream>>>(L, st, d_pdf + (size_t)s * NC); check_launch(); count();
+                k_pdf_slot<T, true><<<g, 128, 0, stream>>>(L, st, s); check_launch(); count();
                 MF_CUDA(cudaStreamSynchronize(stream));
             }
         }
@@ -380,6 +414,7 @@ struct Solver {
         if (cny) to_u<T>(cny, d_cny, 2, N2);
         if (cnz) to_u<T>(cnz, d_cnz, 2, N2);
         if (cnorm) to_u<T>(cnorm, d_cnorm, 2, N2);
+        if (cnx || cny || cnz || cnorm) cn_consistent = false;
         if (cnx || cny || cnz || cnorm) {   // the caller's arrays are not trusted to hold zeros in solids
             k_zero_solid_normals<T><<<grid_box(2, 128), 128, 0, stream>>>(L); check_launch(); count();
         }
@@ -396,7 +431,7 @@ struct Solver {
             const dim3 g = grid_box(1, 128);
             for (int s = 0; s < 38; s++) {
                 T* st = (T*)stage(sizeof(T) * N1);
-                k_pdf_slot<T, false><<<g, 128, 0, stream>>>(L, st, d_pdf + (size_t)s * NC); check_launch(); count();
+                k_pdf_slot<T, false><<<g, 128, 0, stream>>>(L, st, s); check_launch(); count();
                 MF_CUDA(cudaMemcpyAsync(pdf + (size_t)s * N1, st, sizeof(T) * N1, cudaMemcpyDeviceToHost, stream));
                 MF_CUDA(cudaStreamSynchronize(stream));
             }
@@ -451,34 +486,54 @@ struct Solver {
         if (n_list_n) { k_normals<T><<<ceil_div(n_list_n, bl), bl, 0, stream>>>(L, d_list_n, n_list_n); check_launch(); count(); }
         if (n_list_alter) { k_alter<T><<<ceil_div(n_list_alter, bl), bl, 0, stream>>>(L, d_list_alter, d_sn[0], d_sn[1], d_sn[2], n_list_alter); check_launch(); count(); }
         if (n_list_cn) { k_extrap_cn<T><<<ceil_div(n_list_cn, bl), bl, 0, stream>>>(L, d_list_cn, d_mask_cn, n_list_cn); check_launch(); count(); }
+        cn_consistent = true;
     }
 
-    template <int MRT, int VAR>
-    void launch_collide(bool odd) {
+    // pipelined kernels (kernels_collide.cuh): persistent CTAs, TMA / cp.async staged PDF rows
+    template <int MRT, int NST, int D, int CTAS>
+    void launch_collide_pipe(bool odd) {
         if (!n_fluid) return;
-        const int g = ceil_div((int)n_fluid, 128);
-        if (odd) k_collide<T, MRT, true, VAR><<<g, 128, 0, stream>>>(L);
-        else k_collide<T, MRT, false, VAR><<<g, 128, 0, stream>>>(L);
+        const int ntiles = ceil_div((int)n_fluid, COLLIDE_TILE);
+        const int grid = std::min(ntiles, num_sms * CTAS);
+        const int skip = cn_consistent ? 1 : 0;
+        if (odd) {
+            auto kern = k_collide_odd_pipe<T, MRT, D, CTAS>;
+            constexpr size_t smem = collide_odd_smem<T, D>();
+            static thread_local int configured = -1;
+            if (configured != device) { MF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = device; }
+            kern<<<grid, COLLIDE_TILE, smem, stream>>>(L, ntiles, skip);
+        } else {
+            auto kern = k_collide_even_tma<T, MRT, NST, CTAS>;
+            constexpr size_t smem = collide_even_smem<T, NST>();
+            static thread_local int configured = -1;
+            if (configured != device) { MF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = device; }
+            kern<<<grid, COLLIDE_TILE, smem, stream>>>(L, ntiles, skip);
+        }
         check_launch(); count();
+    }
+    template <int MRT>
+    void launch_collide_default(bool odd) {
+        // stage counts sized for two CTAs per SM inside 227 KB of shared memory; the other
+        // configurations exist for tuning runs (MFLBM_VARIANT) and only for the shipped MRT model
+        if constexpr (MRT == 2) {
+            if (sizeof(T) == 8) {
+                if (variant == 201) return launch_collide_pipe<MRT, 2, 2, 1>(odd);
+            } else {
+                if (variant == 201) return launch_collide_pipe<MRT, 2, 1, 3>(odd);
+                if (variant == 202) return launch_collide_pipe<MRT, 4, 3, 1>(odd);
+            }
+        }
+        if (sizeof(T) == 8) launch_collide_pipe<MRT, 2, 1, 2>(odd);
+        else launch_collide_pipe<MRT, 4, 2, 2>(odd);
     }
 
     void phase_collide(int ntime) {
         const bool odd = (ntime % 2) != 0;
         switch (P.mrt) {
-            case 1: launch_collide<1, 0>(odd); break;
-            case 3: launch_collide<3, 0>(odd); break;
-            case 4: launch_collide<4, 0>(odd); break;
-            default:
-                switch (variant) {
-                    case 1: launch_collide<2, 1>(odd); break;
-                    case 4: launch_collide<2, 4>(odd); break;
-                    case 5: launch_collide<2, 5>(odd); break;
-                    case 6: launch_collide<2, 6>(odd); break;
-                    case 7: launch_collide<2, 7>(odd); break;
-                    case 9: launch_collide<2, 9>(odd); break;
-                    default: launch_collide<2, 0>(odd); break;
-                }
-                break;
+            case 1: launch_collide_default<1>(odd); break;
+            case 3: launch_collide_default<3>(odd); break;
+            case 4: launch_collide_default<4>(odd); break;
+            default: launch_collide_default<2>(odd); break;
         }
     }
 
@@ -563,11 +618,13 @@ struct Solver {
         const int nz = L.nz;
         auto at = [&](int k, int n) { return h_mon[(size_t)(k - 1) * MFLBM_MON_N + n]; };
         double v1 = 0, v2 = 0, m1 = 0, m2 = 0, v1f = 0, v2f = 0, m1f = 0, m2f = 0, f1 = 0, f2 = 0, f1w = 0, f2w = 0, umax = 0, k1 = 0, k2 = 0, nanf = 0;
+        double pw = 0, nw = 0, pnw = 0, nnw = 0;
         for (int k = 1; k <= nz; k++) {
             const bool in = k >= P.n_exclude_inlet + 1 && k <= nz - P.n_exclude_outlet;
             if (in) { m1 += at(k, 3); m2 += at(k, 4); v1 += at(k, 5); v2 += at(k, 6); f1 += at(k, 0); f2 += at(k, 1); }
             m1f += at(k, 3); m2f += at(k, 4); v1f += at(k, 5); v2f += at(k, 6); f1w += at(k, 0); f2w += at(k, 1);
             umax = std::max(umax, at(k, 7)); k1 += at(k, 8); k2 += at(k, 9); nanf = std::max(nanf, at(k, 10));
+            pw += at(k, 11); nw += at(k, 12); pnw += at(k, 13); nnw += at(k, 14);
             if (out->fl1) out->fl1[k - 1] = at(k, 0);
             if (out->fl2) out->fl2[k - 1] = at(k, 1);
             if (out->pre) out->pre[k - 1] = at(k, 2);
@@ -586,6 +643,42 @@ struct Solver {
         out->umax = std::sqrt(umax);
         out->kinetic_energy[0] = 0.5 * k1; out->kinetic_energy[1] = 0.5 * k2;
         out->nan_detected = (nanf != 0.0) || std::isnan(out->saturation_full_domain) || std::isnan(out->ca);
+        out->pre_w_sum = pw; out->pre_nw_sum = pnw; out->n_w = (int64_t)nw; out->n_nw = (int64_t)nnw;
+        out->outlet_phase1_count = nz >= 2 ? (int64_t)at(nz - 1, 15) : 0;   // obs_z = nzGlobal - 1, Monitor.cpp:452
+    }
+
+    void phi_change(int seed, double* d_phi_max) {
+        if (!have_geometry) MF_FAIL("phi_change before geometry");
+        const bool fresh = d_phi_old == nullptr;
+        if (fresh) zalloc((void**)&d_phi_old, sizeof(T) * std::max<long long>(n_fluid, 1));
+        if (seed) {
+            if (n_fluid) { k_phi_change<T, 1><<<std::min(ceil_div((int)n_fluid, 256), 148 * 8), 256, 0, stream>>>(L, d_phi_old, nullptr); check_launch(); count(); }
+            if (d_phi_max) *d_phi_max = 0.0;
+            return;
+        }
+        const int nb = std::max(1, std::min(ceil_div((int)n_fluid, 256), MFLBM_MON_N * L.nz));   // partials reuse the monitor buffers
+        k_phi_change<T, 0><<<nb, 256, 0, stream>>>(L, d_phi_old, d_mon); check_launch(); count();
+        MF_CUDA(cudaMemcpyAsync(h_mon, d_mon, sizeof(double) * nb, cudaMemcpyDeviceToHost, stream));
+        MF_CUDA(cudaStreamSynchronize(stream));
+        double m = 0.0;
+        for (int b = 0; b < nb; b++) m = (h_mon[b] != h_mon[b] || m != m) ? (m != m ? m : h_mon[b]) : std::max(m, h_mon[b]);
+        if (d_phi_max) *d_phi_max = m;
+    }
+
+    void download_macro(T* rho, T* u, T* v, T* w) {
+        if (!have_geometry) MF_FAIL("download_macro before geometry");
+        T* out[4] = {rho, u, v, w};
+        int n = 0;
+        for (auto q : out) n += q != nullptr;
+        if (!n) return;
+        T* st = (T*)stage(sizeof(T) * N1 * n);
+        MF_CUDA(cudaMemsetAsync(st, 0, sizeof(T) * N1 * n, stream));
+        T* dev[4] = {nullptr, nullptr, nullptr, nullptr};
+        for (int a = 0, m = 0; a < 4; a++) if (out[a]) dev[a] = st + (size_t)N1 * m++;
+        if (n_fluid) { k_macro<T><<<ceil_div((int)n_fluid, 128), 128, 0, stream>>>(L, dev[0], dev[1], dev[2], dev[3]); check_launch(); count(); }
+        for (int a = 0; a < 4; a++) if (out[a]) MF_CUDA(cudaMemcpyAsync(out[a], dev[a], sizeof(T) * N1, cudaMemcpyDeviceToHost, stream));
+        MF_CUDA(cudaStreamSynchronize(stream));
+        drop_stage();
     }
 
     // ------------------------------------------------------------------------------------------------
@@ -697,6 +790,12 @@ using namespace mflbm;
     }                                                                                                                                     \
     extern "C" int mflbm_##P##_color_gradient(mflbm_##P##_solver* s) { MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->gradient_chain(); }) } \
     extern "C" int mflbm_##P##_monitor(mflbm_##P##_solver* s, mflbm_monitor_out* out) { MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->monitor(out); }) } \
+    extern "C" int mflbm_##P##_phi_change(mflbm_##P##_solver* s, int seed, double* d_phi_max) {                                           \
+        MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->phi_change(seed, d_phi_max); })                                                        \
+    }                                                                                                                                     \
+    extern "C" int mflbm_##P##_download_macro(mflbm_##P##_solver* s, REAL* rho, REAL* u, REAL* v, REAL* w) {                              \
+        MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->download_macro(rho, u, v, w); })                                                       \
+    }                                                                                                                                     \
     extern "C" int mflbm_##P##_sync(mflbm_##P##_solver* s) {                                                                              \
         MF_GUARD({ MF_NEED(s); MF_CUDA(cudaStreamSynchronize(MF_SOLVER(P, REAL)->stream)); })                                             \
     }                                                                                                                                     \

@@ -44,6 +44,7 @@ class MonitorOut(C.Structure):
         ("nan_detected", C.c_int32), ("reserved", C.c_int32),
         ("fl1", C.c_void_p), ("fl2", C.c_void_p), ("pre", C.c_void_p), ("mass1", C.c_void_p), ("mass2", C.c_void_p),
         ("vol1", C.c_void_p), ("vol2", C.c_void_p),
+        ("pre_w_sum", C.c_double), ("pre_nw_sum", C.c_double), ("n_w", C.c_int64), ("n_nw", C.c_int64), ("outlet_phase1_count", C.c_int64),
     ]
 
 
@@ -101,6 +102,8 @@ def load_library() -> C.CDLL:
             "color_gradient": [vp],
             "monitor": [vp, C.POINTER(MonitorOut)],
             "sync": [vp],
+            "phi_change": [vp, i32, C.POINTER(C.c_double)],
+            "download_macro": [vp, vp, vp, vp, vp],
             "halo_buffers": [vp, i32, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)],
             "halo_pack": [vp, i32],
             "halo_unpack": [vp, i32],
@@ -123,7 +126,7 @@ def load_library() -> C.CDLL:
 
 
 EXPORTED = ["create", "destroy", "set_params", "upload_geometry", "preprocess_geometry", "download_geometry", "upload_state",
-            "init_state", "download_state", "step", "run", "color_gradient", "monitor", "sync", "halo_buffers", "halo_pack",
+            "init_state", "download_state", "step", "run", "color_gradient", "monitor", "sync", "phi_change", "download_macro", "halo_buffers", "halo_pack",
             "halo_unpack", "step_phase", "num_fluid_nodes", "kernel_launches", "stream", "device_ptr"]
 
 
@@ -315,10 +318,23 @@ class Solver:
         self._check(self._fn("monitor")(self.h, C.byref(m)))
         out = {k: getattr(m, k) for k in ("saturation", "saturation_full_domain", "vol1_sum", "vol2_sum", "mass1_sum", "mass2_sum",
                                           "vol1_full", "vol2_full", "mass1_full", "mass2_full", "fl1_avg", "fl2_avg", "fl1_avg_whole",
-                                          "fl2_avg_whole", "ca", "umax", "nan_detected")}
+                                          "fl2_avg_whole", "ca", "umax", "nan_detected", "pre_w_sum", "pre_nw_sum", "n_w", "n_nw",
+                                          "outlet_phase1_count")}
         out["kinetic_energy"] = [m.kinetic_energy[0], m.kinetic_energy[1]]
         if prof is not None:
             out["profiles"] = prof
+        return out
+
+    def phi_change(self, seed: bool = False) -> float:
+        """max |phi - phi_old| over fluid nodes, then phi_old <- phi (src/Monitor.cpp:279-312)"""
+        d = C.c_double(0.0)
+        self._check(self._fn("phi_change")(self.h, int(seed), C.byref(d)))
+        return d.value
+
+    def download_macro(self) -> dict:
+        """rho, u, v, w of compute_macro_vars (src/Misc.cpp:222-274), [nz+2, ny+2, nx+2]"""
+        out = {k: np.zeros(self._shape(1), self.rt) for k in ("rho", "u", "v", "w")}
+        self._check(self._fn("download_macro")(self.h, *[out[k].ctypes.data for k in ("rho", "u", "v", "w")]))
         return out
 
     # -- halo exchange -------------------------------------------------------------------------------
