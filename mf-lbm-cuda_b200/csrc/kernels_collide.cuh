@@ -74,7 +74,7 @@ __device__ __forceinline__ void node_force(const Lattice<T>& L, const int u, con
 template <typename T, int NST>
 constexpr size_t collide_even_smem() { return sizeof(T) * NST * 38 * COLLIDE_TILE + 8 * NST; }
 template <typename T, int D>
-constexpr size_t collide_odd_smem() { return (sizeof(T) * 38 + sizeof(int) * 18) * (D + 1) * COLLIDE_TILE; }
+constexpr size_t collide_odd_smem() { return (sizeof(T) * 38 * (D + 1) + sizeof(int) * 19 * (D + 2)) * COLLIDE_TILE; }
 
 // ---------------------------------------------------------------------------------------------------------
 // EVEN step: f_q = local slot opc(q); collide; local slot q = f_q*     (:395-726)
@@ -118,11 +118,14 @@ __global__ void __launch_bounds__(COLLIDE_TILE, CTAS) k_collide_even_tma(const L
     for (; tile < ntiles; tile += gridDim.x) {
         const int t = tile * COLLIDE_TILE + tid;
         const bool live = u >= 0;
-        const T cnormN = uN >= 0 ? L.c_norm[uN] : T(0);
-        const int uNN = site(tile + 2 * (int)gridDim.x);
         T cnx = T(0), cny = T(0), cnz = T(0), tmp = T(0);
         if (live) node_force(L, u, cnorm, bulk_skip != 0, cnx, cny, cnz, tmp);   // interface nodes only: cn + curvature stencil
         pipe::mbar_wait(&full[s], phase);
+        // c_norm / site id of my next tiles, issued after the uses above (a load issued before them would share their
+        // scoreboard and expose its full latency there); they land during the collision
+        asm volatile("" ::: "memory");
+        const T cnormN = uN >= 0 ? L.c_norm[uN] : T(0);
+        const int uNN = site(tile + 2 * (int)gridDim.x);
         T g1[19], g2[19];
 #pragma unroll
         for (int q = 0; q < 19; q++) { g1[q] = buf[s][opc(q)][tid]; g2[q] = buf[s][opc(q) + 19][tid]; }
@@ -145,53 +148,68 @@ __global__ void __launch_bounds__(COLLIDE_TILE, CTAS) k_collide_even_tma(const L
 
 // ---------------------------------------------------------------------------------------------------------
 // ODD step: f_q pulled from x - e_q (slot q); collide; f_q* pushed to x + e_q (slot opc(q))     (:56-388)
-// D = how many tiles ahead the PDF gathers are issued (D + 1 shared-memory stages).
+// D = how many tiles ahead the PDF gathers are issued (D + 1 value stages, D + 2 index stages).
+//
+// Per iteration k of a CTA (tiles k, k+1, ... are the CTA's own tiles, `stride` apart):
+//   wait     index(k+D) has landed                                   (cp.async group B of iteration k-1)
+//   resolve  map entries of tile k+D -> slot entries (wall links -> mailbox entries), parked for the scatter
+//   issue    index(k+D+1): 18 map entries per thread, cp.async 4 B   (group B_k)
+//   issue    gathers(k+D): 38 PDFs per thread, cp.async 4/8 B        (group A_k)
+//   wait     gathers(k) have landed;  collide tile k;  scatter through the parked entries of tile k
+// Nothing a later tile needs is held in registers across the collision (the plain-load version kept 18 map entries
+// live and ptxas tied constant-bank reloads to the scoreboard of the outstanding loads: 28 % of all stall samples).
 // ---------------------------------------------------------------------------------------------------------
 template <typename T, int MRT, int D, int CTAS>
 __global__ void __launch_bounds__(COLLIDE_TILE, CTAS) k_collide_odd_pipe(const Lattice<T> L, const int ntiles, const int bulk_skip) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int NST = D + 1;
+    constexpr int NST = D + 1, NNB = D + 2;
     typedef T Stage[38][COLLIDE_TILE];
     typedef int NbStage[18][COLLIDE_TILE];
     Stage* vals = reinterpret_cast<Stage*>(smem_raw);
     NbStage* nbS = reinterpret_cast<NbStage*>(smem_raw + sizeof(Stage) * NST);
+    typedef int WbStage[COLLIDE_TILE / 32][32];
+    WbStage* wbS = reinterpret_cast<WbStage*>(smem_raw + sizeof(Stage) * NST + sizeof(NbStage) * NNB);
     const int tid = threadIdx.x;
     const long long NC = L.NC;
     const int stride = gridDim.x;
     const T* __restrict__ p0 = L.pdf;
+    const int* __restrict__ cmap = L.cmap;
+    const unsigned lanes_below = (1u << (tid & 31)) - 1u;
 
     // site id of my entry in a tile (-1: no such entry)
     auto site = [&](const int tile) -> int {
         const int t = tile * COLLIDE_TILE + tid;
         return (tile < ntiles && t < L.n_fluid) ? L.fl_u[t] : -1;
     };
-    // The 18 neighbour cells of my entry.  load_index fetches the raw map entries (ordinary loads, consumed one
-    // iteration later); resolve_index turns them into slot entries: the map entry itself for a non-solid neighbour, the
-    // mailbox entry mb0 + rank for a wall link (core.cuh).  Both run in whole warps, `tile` is warp-uniform.
-    const unsigned lanes_below = (1u << (tid & 31)) - 1u;
-    auto load_index = [&](const int tile, const int u, int (&nb)[18], int& wb) {
-        if (tile >= ntiles) return;
-        const int lane = tid & 31;
-        wb = lane < 18 ? L.wbase[(tile * (COLLIDE_TILE / 32) + (tid >> 5)) * 18 + lane] : 0;
+    // raw map entries of my 18 neighbours -> my column of index stage sb, link ranks of my warp's 32-entry group ->
+    // lanes 0..17; always commits one group
+    auto issue_index = [&](const int tile, const int u, const int sb) {
+        if (tile < ntiles && (tid & 31) < 18)
+            pipe::cp_async<4>(&wbS[sb][tid >> 5][tid & 31], L.wbase + ((tile * (COLLIDE_TILE / 32) + (tid >> 5)) * 18 + (tid & 31)));
+        if (u >= 0) {
 #pragma unroll
-        for (int q = 1; q < 19; q++) nb[q - 1] = u >= 0 ? L.cmap[u + L.off(q)] : 0;
+            for (int q = 1; q < 19; q++) pipe::cp_async<4>(&nbS[sb][q - 1][tid], cmap + (u + L.off(q)));
+        }
+        pipe::cp_async_commit();
     };
-    auto resolve_index = [&](const int tile, int (&nb)[18], const int wb) {
+    // slot entries of the 18 neighbour cells: the map entry itself for a non-solid neighbour, the mailbox entry
+    // mb0 + rank for a wall link (core.cuh).  Whole warps (`tile` is warp-uniform); parked in place for the scatter.
+    auto resolve_index = [&](const int tile, const int u, const int sb, int (&nb)[18]) {
         if (tile >= ntiles) return;
+        const int wb = (tid & 31) < 18 ? wbS[sb][tid >> 5][tid & 31] : 0;
 #pragma unroll
         for (int q = 1; q < 19; q++) {
-            const int c = nb[q - 1];
+            const int c = u >= 0 ? nbS[sb][q - 1][tid] : 0;
             const unsigned walls = __ballot_sync(0xffffffffu, c < 0);
             const int base = __shfl_sync(0xffffffffu, wb, q - 1);
-            if (c < 0) nb[q - 1] = L.mb0 + base + __popc(walls & lanes_below);
+            nb[q - 1] = c >= 0 ? c : L.mb0 + base + __popc(walls & lanes_below);
+            if (c < 0) nbS[sb][q - 1][tid] = nb[q - 1];
         }
     };
-    // park the entries for the scatter and start the 38 gathers of that tile; always commits one group
+    // the 38 gathers of a tile; always commits one group
     auto issue_gather = [&](const int tile, const int u, const int (&nb)[18], const int st) {
         if (u >= 0) {
             const int t = tile * COLLIDE_TILE + tid;
-#pragma unroll
-            for (int q = 1; q < 19; q++) nbS[st][q - 1][tid] = nb[q - 1];
 #pragma unroll
             for (int q = 0; q < 19; q++) {
                 const int src = (q == 0) ? t : nb[opc(q) - 1];   // x - e_q = x + e_opc(q), slot q there
@@ -207,34 +225,39 @@ __global__ void __launch_bounds__(COLLIDE_TILE, CTAS) k_collide_odd_pipe(const L
     int uR[D + 3];
 #pragma unroll
     for (int j = 0; j < D + 3; j++) uR[j] = site(tile + j * stride);
-    // prologue: gathers of my first D tiles, map entries of tile D
-    int nbN[18], wbN = 0;
+    // prologue: index + gathers of my first D tiles (groups B, A per tile, as in the loop), index of tile D
+    int nb[18];
 #pragma unroll
     for (int j = 0; j < D; j++) {
-        load_index(tile + j * stride, uR[j], nbN, wbN);
-        resolve_index(tile + j * stride, nbN, wbN);
-        issue_gather(tile + j * stride, uR[j], nbN, j % NST);
+        issue_index(tile + j * stride, uR[j], j % NNB);
+        pipe::cp_async_wait<0>();
+        resolve_index(tile + j * stride, uR[j], j % NNB, nb);
+        issue_gather(tile + j * stride, uR[j], nb, j % NST);
     }
-    load_index(tile + D * stride, uR[D], nbN, wbN);
+    issue_index(tile + D * stride, uR[D], D % NNB);
+    pipe::cp_async_commit();   // keeps the group pattern of the loop: (B, A) per iteration
     T cnorm = uR[0] >= 0 ? L.c_norm[uR[0]] : T(0);
 
-    int st = 0;   // stage of the current tile
+    int st = 0, sb = 0;   // value / index stage of the current tile
     for (; tile < ntiles; tile += stride) {
-        // 1. gathers of tile + D (its map entries arrived during the previous collision)
         int stD = st + D; if (stD >= NST) stD -= NST;
-        resolve_index(tile + D * stride, nbN, wbN);
-        issue_gather(tile + D * stride, uR[D], nbN, stD);
-        // 2. map entries of tile + D + 1, c_norm of tile + 1, site id of tile + D + 3: land during this collision
-        load_index(tile + (D + 1) * stride, uR[D + 1], nbN, wbN);
-        const T cnormN = uR[1] >= 0 ? L.c_norm[uR[1]] : T(0);
-        const int uNew = site(tile + (D + 3) * stride);
-        // 3. this tile
+        int sbD = sb + D; if (sbD >= NNB) sbD -= NNB;
+        int sbD1 = sbD + 1; if (sbD1 >= NNB) sbD1 -= NNB;
+        pipe::cp_async_wait<1>();   // index(tile + D) has landed (all but the newest group, the gathers of tile + D - 1)
+        resolve_index(tile + D * stride, uR[D], sbD, nb);
+        issue_index(tile + (D + 1) * stride, uR[D + 1], sbD1);
+        issue_gather(tile + D * stride, uR[D], nb, stD);
         const int t = tile * COLLIDE_TILE + tid;
         const int u = uR[0];
         const bool live = u >= 0;
         T cnx = T(0), cny = T(0), cnz = T(0), tmp = T(0);
         if (live) node_force(L, u, cnorm, bulk_skip != 0, cnx, cny, cnz, tmp);
-        pipe::cp_async_wait<D>();   // all but the D most recent groups: the gathers of this tile have landed
+        pipe::cp_async_wait<2 * D>();   // all but the 2D newest groups: the gathers of this tile have landed
+        // c_norm of tile + 1 and site id of tile + D + 3: ordinary loads that land during this collision.  Issued only
+        // now: a load issued before the uses above would share their scoreboard and expose its full latency there.
+        asm volatile("" ::: "memory");
+        const T cnormN = uR[1] >= 0 ? L.c_norm[uR[1]] : T(0);
+        const int uNew = site(tile + (D + 3) * stride);
         if (live) {
             T g1[19], g2[19];
 #pragma unroll
@@ -246,7 +269,7 @@ __global__ void __launch_bounds__(COLLIDE_TILE, CTAS) k_collide_odd_pipe(const L
             po[19 * NC + t] = g2[0];
 #pragma unroll
             for (int q = 1; q < 19; q++) {
-                const int dst = nbS[st][q - 1][tid];
+                const int dst = nbS[sb][q - 1][tid];
                 po[(long long)opc(q) * NC + dst] = g1[q];
                 po[(long long)(opc(q) + 19) * NC + dst] = g2[q];
             }
@@ -256,6 +279,7 @@ __global__ void __launch_bounds__(COLLIDE_TILE, CTAS) k_collide_odd_pipe(const L
         uR[D + 2] = uNew;
         cnorm = cnormN;
         if (++st == NST) st = 0;
+        if (++sb == NNB) sb = 0;
     }
     pipe::cp_async_wait<0>();
 }

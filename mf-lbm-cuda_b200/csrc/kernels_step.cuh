@@ -68,8 +68,12 @@ __global__ void k_extrap_phi(const Lattice<T> L, const int* __restrict__ list, c
 // interface normals from the phase-field gradient (:757-807) at the non-solid sites of [-1..n+2]^3 (the reference's
 // guard over-runs by one; not replicated).  Solid sites hold 0 from k_zero_solid_normals and are
 // never written again, which is what the reference stores there every step.
+//
+// live[t] != 0 says that the four outputs of list entry t may be non-zero in memory.  Away from interfaces the result is
+// zero step after step (the reference rewrites those zeros every step, 4 stores per site); here an entry that was zero
+// and stays zero stores nothing.  Arrays that came from outside (upload_state) start with live = 1 everywhere.
 template <typename T>
-__global__ void __launch_bounds__(128) k_normals(const Lattice<T> L, const int* __restrict__ list, const int count) {
+__global__ void __launch_bounds__(128) k_normals(const Lattice<T> L, const int* __restrict__ list, unsigned char* __restrict__ live, const int count) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
     const int u = list[t];
@@ -77,8 +81,14 @@ __global__ void __launch_bounds__(128) k_normals(const Lattice<T> L, const int* 
     T gy = iso4<T, 1>(L.phi, u, L.sy, L.sz);
     T gz = iso4<T, 2>(L.phi, u, L.sy, L.sz);
     T nrm = sqrt(gx * gx + gy * gy + gz * gz);
-    if (nrm < lit<T>(1e-6)) { gx = T(0); gy = T(0); gz = T(0); nrm = T(0); }
-    else { gx = gx / nrm; gy = gy / nrm; gz = gz / nrm; }
+    if (nrm < lit<T>(1e-6)) {
+        if (!live[t]) return;
+        live[t] = 0;
+        gx = T(0); gy = T(0); gz = T(0); nrm = T(0);
+    } else {
+        gx = gx / nrm; gy = gy / nrm; gz = gz / nrm;
+        live[t] = 1;
+    }
     L.cn_x[u] = gx; L.cn_y[u] = gy; L.cn_z[u] = gz; L.c_norm[u] = nrm;
 }
 
@@ -137,13 +147,26 @@ __global__ void k_alter(const Lattice<T> L, const int* __restrict__ list, const 
     }
 }
 
-// cn at solid-boundary nodes <- weighted mean of the fluid neighbours' cn (:880-906); mask as in k_extrap_phi
+// cn at solid-boundary nodes <- weighted mean of the fluid neighbours' cn (:880-906); mask as in k_extrap_phi.
+// A neighbour with c_norm == 0 has cn == 0 (k_normals), so where every contributing neighbour is interface-free the mean
+// is exactly +0: 18 c_norm loads decide that, and an entry that was zero and stays zero stores nothing (live, as above).
 template <typename T>
-__global__ void k_extrap_cn(const Lattice<T> L, const int* __restrict__ list, const int* __restrict__ mask, const int count) {
+__global__ void k_extrap_cn(const Lattice<T> L, const int* __restrict__ list, const int* __restrict__ mask, unsigned char* __restrict__ live,
+                            const int count) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
     const int c2 = list[t];
     const int m = mask[t];
+    bool any = false;
+#pragma unroll
+    for (int q = 1; q < 19; q++)
+        if (m & (1 << (q - 1))) any = any || (L.c_norm[c2 + L.off(q)] != T(0));
+    if (!any) {
+        if (!live[t]) return;
+        live[t] = 0;
+        L.cn_x[c2] = T(0); L.cn_y[c2] = T(0); L.cn_z[c2] = T(0);
+        return;
+    }
     T sx = T(0), sy = T(0), sz = T(0), wsum = T(0);
 #pragma unroll
     for (int q = 1; q < 19; q++) {
@@ -152,6 +175,7 @@ __global__ void k_extrap_cn(const Lattice<T> L, const int* __restrict__ list, co
             sx += L.cn_x[nb] * w_equ<T>(q); sy += L.cn_y[nb] * w_equ<T>(q); sz += L.cn_z[nb] * w_equ<T>(q); wsum += w_equ<T>(q);
         }
     }
+    live[t] = 1;
     L.cn_x[c2] = sx / wsum; L.cn_y[c2] = sy / wsum; L.cn_z[c2] = sz / wsum;
 }
 

@@ -61,6 +61,7 @@ struct Solver {
     long long n_links = 0;   // wall links (core.cuh)
     int *d_list_phi = nullptr, *d_mask_phi = nullptr, *d_list_cn = nullptr, *d_mask_cn = nullptr, *d_list_alter = nullptr, *d_list_n = nullptr;
     T* d_sn[3] = {nullptr, nullptr, nullptr};   // solid-surface normals in d_list_alter order
+    unsigned char *d_live_n = nullptr, *d_live_cn = nullptr;   // per list entry: outputs may be non-zero (k_normals, k_extrap_cn)
     int n_list_phi = 0, n_list_cn = 0, n_list_alter = 0, n_list_alter_all = 0, n_list_n = 0;
     long long counts[4] = {0, 0, 0, 0};
     long long n_fluid = 0;
@@ -161,6 +162,7 @@ struct Solver {
         dfree(d_types); dfree(d_cmap); dfree(d_flu); dfree(d_zstart); dfree(d_wbase);
         dfree(d_list_phi); dfree(d_mask_phi); dfree(d_list_cn); dfree(d_mask_cn); dfree(d_list_alter); dfree(d_list_n);
         for (auto& q : d_sn) dfree(q);
+        dfree(d_live_n); dfree(d_live_cn);
         dfree(d_mon); dfree(d_phi_old);
         if (d_stage) { cudaFree(d_stage); d_stage = nullptr; }
         for (int kind = 0; kind < 3; kind++) for (int side = 0; side < 2; side++) { dfree(d_send[kind][side]); dfree(d_recv[kind][side]); }
@@ -294,6 +296,9 @@ struct Solver {
         up(d_flu, flu); up(d_list_phi, lphi); up(d_mask_phi, mphi); up(d_list_cn, lcn); up(d_mask_cn, mcn); up(d_list_alter, lalt); up(d_list_n, ln);
         n_list_phi = (int)lphi.size(); n_list_cn = (int)lcn.size(); n_list_alter = (int)lalt_in.size(); n_list_alter_all = (int)lalt.size();
         n_list_n = (int)ln.size();
+        dfree(d_live_n); dfree(d_live_cn);
+        MF_CUDA(cudaMalloc((void**)&d_live_n, std::max(n_list_n, 1))); MF_CUDA(cudaMalloc((void**)&d_live_cn, std::max(n_list_cn, 1)));
+        mark_all_live();
         MF_CUDA(cudaMemcpyAsync(d_cmap, cmap.data(), sizeof(int) * (size_t)PN, cudaMemcpyHostToDevice, stream));
         MF_CUDA(cudaMemcpyAsync(d_zstart, zstart.data(), sizeof(int) * zstart.size(), cudaMemcpyHostToDevice, stream));
         L.n_fluid = (int)n_fluid; L.fl_u = d_flu;
@@ -414,7 +419,7 @@ struct Solver {
         if (cny) to_u<T>(cny, d_cny, 2, N2);
         if (cnz) to_u<T>(cnz, d_cnz, 2, N2);
         if (cnorm) to_u<T>(cnorm, d_cnorm, 2, N2);
-        if (cnx || cny || cnz || cnorm) cn_consistent = false;
+        if (cnx || cny || cnz || cnorm) { cn_consistent = false; mark_all_live(); }
         if (cnx || cny || cnz || cnorm) {   // the caller's arrays are not trusted to hold zeros in solids
             k_zero_solid_normals<T><<<grid_box(2, 128), 128, 0, stream>>>(L); check_launch(); count();
         }
@@ -454,6 +459,12 @@ struct Solver {
         drop_stage();
     }
 
+    // the cn_* / c_norm arrays hold values the chain did not write (fresh geometry, upload, init): every entry must be stored once
+    void mark_all_live() {
+        if (d_live_n) MF_CUDA(cudaMemsetAsync(d_live_n, 1, std::max(n_list_n, 1), stream));
+        if (d_live_cn) MF_CUDA(cudaMemsetAsync(d_live_cn, 1, std::max(n_list_cn, 1), stream));
+    }
+
     bool open_z() const { return P.kper == 0 && P.wall_z_min == 0 && P.wall_z_max == 0; }
 
     void init_state(int option, T interface_z0, const T* Win) {
@@ -468,6 +479,7 @@ struct Solver {
         if (Win) MF_CUDA(cudaMemcpyAsync(d_Win, Win, sizeof(T) * NP, cudaMemcpyHostToDevice, stream));
         MF_CUDA(cudaMemsetAsync(d_cnx, 0, sizeof(T) * PN, stream)); MF_CUDA(cudaMemsetAsync(d_cny, 0, sizeof(T) * PN, stream));
         MF_CUDA(cudaMemsetAsync(d_cnz, 0, sizeof(T) * PN, stream)); MF_CUDA(cudaMemsetAsync(d_cnorm, 0, sizeof(T) * PN, stream));
+        mark_all_live();
         gradient_chain();
         MF_CUDA(cudaStreamSynchronize(stream));
     }
@@ -483,48 +495,72 @@ struct Solver {
         if (!have_geometry) MF_FAIL("gradient chain before geometry");
         const int bl = 128;
         if (n_list_phi) { k_extrap_phi<T><<<ceil_div(n_list_phi, bl), bl, 0, stream>>>(L, d_list_phi, d_mask_phi, n_list_phi); check_launch(); count(); }
-        if (n_list_n) { k_normals<T><<<ceil_div(n_list_n, bl), bl, 0, stream>>>(L, d_list_n, n_list_n); check_launch(); count(); }
+        if (n_list_n) { k_normals<T><<<ceil_div(n_list_n, bl), bl, 0, stream>>>(L, d_list_n, d_live_n, n_list_n); check_launch(); count(); }
         if (n_list_alter) { k_alter<T><<<ceil_div(n_list_alter, bl), bl, 0, stream>>>(L, d_list_alter, d_sn[0], d_sn[1], d_sn[2], n_list_alter); check_launch(); count(); }
-        if (n_list_cn) { k_extrap_cn<T><<<ceil_div(n_list_cn, bl), bl, 0, stream>>>(L, d_list_cn, d_mask_cn, n_list_cn); check_launch(); count(); }
+        if (n_list_cn) { k_extrap_cn<T><<<ceil_div(n_list_cn, bl), bl, 0, stream>>>(L, d_list_cn, d_mask_cn, d_live_cn, n_list_cn); check_launch(); count(); }
         cn_consistent = true;
     }
 
     // pipelined kernels (kernels_collide.cuh): persistent CTAs, TMA / cp.async staged PDF rows
-    template <int MRT, int NST, int D, int CTAS>
-    void launch_collide_pipe(bool odd) {
-        if (!n_fluid) return;
+    template <int MRT, int NST, int CTAS>
+    void launch_even() {
         const int ntiles = ceil_div((int)n_fluid, COLLIDE_TILE);
-        const int grid = std::min(ntiles, num_sms * CTAS);
-        const int skip = cn_consistent ? 1 : 0;
-        if (odd) {
-            auto kern = k_collide_odd_pipe<T, MRT, D, CTAS>;
-            constexpr size_t smem = collide_odd_smem<T, D>();
-            static thread_local int configured = -1;
-            if (configured != device) { MF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = device; }
-            kern<<<grid, COLLIDE_TILE, smem, stream>>>(L, ntiles, skip);
-        } else {
-            auto kern = k_collide_even_tma<T, MRT, NST, CTAS>;
-            constexpr size_t smem = collide_even_smem<T, NST>();
-            static thread_local int configured = -1;
-            if (configured != device) { MF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = device; }
-            kern<<<grid, COLLIDE_TILE, smem, stream>>>(L, ntiles, skip);
-        }
-        check_launch(); count();
+        auto kern = k_collide_even_tma<T, MRT, NST, CTAS>;
+        constexpr size_t smem = collide_even_smem<T, NST>();
+        static thread_local int configured = -1;
+        if (configured != device) { MF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = device; }
+        kern<<<std::min(ntiles, num_sms * CTAS), COLLIDE_TILE, smem, stream>>>(L, ntiles, cn_consistent ? 1 : 0);
     }
+    template <int MRT, int D, int CTAS>
+    void launch_odd() {
+        const int ntiles = ceil_div((int)n_fluid, COLLIDE_TILE);
+        auto kern = k_collide_odd_pipe<T, MRT, D, CTAS>;
+        constexpr size_t smem = collide_odd_smem<T, D>();
+        static thread_local int configured = -1;
+        if (configured != device) { MF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = device; }
+        kern<<<std::min(ntiles, num_sms * CTAS), COLLIDE_TILE, smem, stream>>>(L, ntiles, cn_consistent ? 1 : 0);
+    }
+    // Stage counts are sized for the 227 KB of shared memory of an SM.  MFLBM_VARIANT = 100*e + o
+    // selects other (even, odd) configurations for tuning runs, for the shipped MRT model only.
     template <int MRT>
     void launch_collide_default(bool odd) {
-        // stage counts sized for two CTAs per SM inside 227 KB of shared memory; the other
-        // configurations exist for tuning runs (MFLBM_VARIANT) and only for the shipped MRT model
-        if constexpr (MRT == 2) {
-            if (sizeof(T) == 8) {
-                if (variant == 201) return launch_collide_pipe<MRT, 2, 2, 1>(odd);
+        if (!n_fluid) return;
+        const int e = variant / 100, o = variant % 100;
+        if (sizeof(T) == 8) {
+            if (odd) {
+                if constexpr (MRT == 2) {
+                    if (o == 1) { launch_odd<MRT, 1, 2>(); goto done; }
+                    if (o == 2) { launch_odd<MRT, 3, 1>(); goto done; }
+                    if (o == 3) { launch_odd<MRT, 1, 1>(); goto done; }
+                }
+                launch_odd<MRT, 2, 1>();   // measured best on the 256^3 pack (profiles/README.md)
             } else {
-                if (variant == 201) return launch_collide_pipe<MRT, 2, 1, 3>(odd);
-                if (variant == 202) return launch_collide_pipe<MRT, 4, 3, 1>(odd);
+                if constexpr (MRT == 2) {
+                    if (e == 1) { launch_even<MRT, 4, 1>(); goto done; }
+                    if (e == 2) { launch_even<MRT, 3, 1>(); goto done; }
+                }
+                launch_even<MRT, 2, 2>();
+            }
+        } else {
+            if (odd) {
+                if constexpr (MRT == 2) {
+                    if (o == 1) { launch_odd<MRT, 1, 3>(); goto done; }
+                    if (o == 2) { launch_odd<MRT, 4, 1>(); goto done; }
+                    if (o == 3) { launch_odd<MRT, 2, 1>(); goto done; }
+                    if (o == 4) { launch_odd<MRT, 3, 1>(); goto done; }
+                }
+                launch_odd<MRT, 2, 2>();
+            } else {
+                if constexpr (MRT == 2) {
+                    if (e == 1) { launch_even<MRT, 8, 1>(); goto done; }
+                    if (e == 2) { launch_even<MRT, 2, 4>(); goto done; }
+                    if (e == 3) { launch_even<MRT, 3, 3>(); goto done; }
+                }
+                launch_even<MRT, 4, 2>();
             }
         }
-        if (sizeof(T) == 8) launch_collide_pipe<MRT, 2, 1, 2>(odd);
-        else launch_collide_pipe<MRT, 4, 2, 2>(odd);
+    done:
+        check_launch(); count();
     }
 
     void phase_collide(int ntime) {
