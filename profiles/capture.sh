@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # GPU-box capture: tests, bench (both precisions, both arms), ncu launch list and full capture of the collide kernels.
-# usage (under gpurun): bash profiles/capture.sh <tag> [notest]
+# usage (under gpurun): bash profiles/capture.sh <tag> [notest] [nochain]
 TAG=${1:-r01x}
 O=gpurun_out
 mkdir -p $O
@@ -16,13 +16,13 @@ done
 cat $O/${TAG}_bench_f64.json $O/${TAG}_bench_f32.json
 for p in f64 f32; do
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches_$p.csv \
-      python bench.py --prec $p --steps 6 --warmup 3 --no-cpu-baseline > $O/${TAG}_ncu_launch_$p.log 2>&1
+      python bench.py --prec $p --steps 6 --warmup 3 --no-cpu-baseline --no-e2e > $O/${TAG}_ncu_launch_$p.log 2>&1
 done
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_collide -s 4 -c 2 -o $O/${TAG}_collide_f64 -f \
-    python bench.py --prec f64 --steps 6 --warmup 3 --no-cpu-baseline > $O/${TAG}_ncu_full_f64.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_collide -s 4 -c 2 -o $O/${TAG}_collide_f32 -f \
-    python bench.py --prec f32 --steps 6 --warmup 3 --no-cpu-baseline > $O/${TAG}_ncu_full_f32.log 2>&1
+for p in f64 f32; do
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_collide -s 4 -c 2 -o $O/${TAG}_collide_$p -f \
+    python bench.py --prec $p --steps 6 --warmup 3 --no-cpu-baseline --no-e2e > $O/${TAG}_ncu_full_$p.log 2>&1
+done
+if [ "$3" != "nochain" ]; then
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_normals|k_extrap|k_alter' -s 8 -c 4 -o $O/${TAG}_chain_f64 -f \
-    python bench.py --prec f64 --steps 6 --warmup 3 --no-cpu-baseline > $O/${TAG}_ncu_chain_f64.log 2>&1
-bash profiles/sweep_variants.sh > $O/${TAG}_variants.txt 2>&1
-cat $O/${TAG}_variants.txt
+    python bench.py --prec f64 --steps 6 --warmup 3 --no-cpu-baseline --no-e2e > $O/${TAG}_ncu_chain_f64.log 2>&1
+fi
