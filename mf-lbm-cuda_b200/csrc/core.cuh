@@ -121,8 +121,12 @@ __device__ __forceinline__ void mrt_rates(T omega, T& s_e, T& s_e2, T& s_q, T& s
 // Follows src/main_iteration_GPU.cu:115-345 operation by operation (same association, so that nvcc's FMA
 // contraction sees the same expression trees).  g1/g2: component PDFs in natural direction order, overwritten with
 // the post-collision values.  Returns phi.
-template <typename T, int MRT>
-__device__ __forceinline__ T collide_node(const Lattice<T>& L, T (&g1)[19], T (&g2)[19], T cnx, T cny, T cnz, T curv_cnorm_half_gamma) {
+struct NoHook { __device__ __forceinline__ void operator()(float) const {} __device__ __forceinline__ void operator()(double) const {} };
+
+// after_phi(phi) runs as soon as the order parameter is known, i.e. once all 38 inputs have been consumed by real
+// arithmetic (the even kernel stores phi and hands its shared-memory stage back from there).
+template <typename T, int MRT, typename Hook = NoHook>
+__device__ __forceinline__ T collide_node(const Lattice<T>& L, T (&g1)[19], T (&g2)[19], T cnx, T cny, T cnz, T curv_cnorm_half_gamma, Hook after_phi = Hook()) {
     T f[19];
 #pragma unroll
     for (int q = 0; q < 19; q++) f[q] = g1[q] + g2[q];
@@ -130,6 +134,7 @@ __device__ __forceinline__ T collide_node(const Lattice<T>& L, T (&g1)[19], T (&
 #pragma unroll
     for (int q = 1; q < 19; q++) { rho1 = rho1 + g1[q]; rho2 = rho2 + g2[q]; }
     const T phi_loc = (rho1 - rho2) / (rho1 + rho2);
+    after_phi(phi_loc);
 
     T tmp = curv_cnorm_half_gamma;  // 0.5 * gamma * curv * c_norm, formed by the caller in the reference's order
     const T fx = tmp * cnx, fy = tmp * cny, fz = tmp * cnz + L.force_z;

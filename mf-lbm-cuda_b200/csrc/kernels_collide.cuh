@@ -71,77 +71,119 @@ __device__ __forceinline__ void node_force(const Lattice<T>& L, const int u, con
     tmp = lit<T>(0.5) * L.lbm_gamma * curvature_at(L, u) * cnorm;   // :147
 }
 
-template <typename T, int NST>
-constexpr size_t collide_even_smem() { return sizeof(T) * NST * 38 * COLLIDE_TILE + 8 * NST; }
+// odd kernel: D + 1 value stages, D + 2 index stages (18 map entries + link ranks), one site id and one c_norm per thread
 template <typename T, int D>
-constexpr size_t collide_odd_smem() { return (sizeof(T) * 38 * (D + 1) + sizeof(int) * 19 * (D + 2)) * COLLIDE_TILE; }
+constexpr size_t collide_odd_smem() { return (sizeof(T) * 38 * (D + 1) + sizeof(int) * 19 * (D + 2) + 2 * (sizeof(int) + sizeof(T))) * COLLIDE_TILE; }
 
 // ---------------------------------------------------------------------------------------------------------
 // EVEN step: f_q = local slot opc(q); collide; local slot q = f_q*     (:395-726)
 // ---------------------------------------------------------------------------------------------------------
+// Block = 4 consumer warps (one thread per entry of a 128-entry tile) + 1 producer warp.  Per stage two mbarriers:
+//   full[s]   1 arrival (the producer's expect_tx) + 38 rows * 128 * sizeof(T) bytes of TMA traffic
+//   empty[s]  4 arrivals, one per consumer warp once its lanes hold their columns in registers
+// so a stage is refilled as soon as its last reader is done and no CTA-wide barrier sits between the tiles (the
+// __syncthreads of the first version took 19 % / 26 % of all stall samples, profiles/r01d_collide_*_stalls.txt).
+constexpr int COLLIDE_EVEN_THREADS = COLLIDE_TILE + 32;
+template <typename T, int NST>
+constexpr size_t collide_even_smem() { return sizeof(T) * NST * 38 * COLLIDE_TILE + 16 * NST + 2 * (sizeof(T) + sizeof(int)) * COLLIDE_TILE; }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pipe::smem_u32(bar)) : "memory");
+}
+
 template <typename T, int MRT, int NST, int CTAS>
-__global__ void __launch_bounds__(COLLIDE_TILE, CTAS) k_collide_even_tma(const Lattice<T> L, const int ntiles, const int bulk_skip) {
+__global__ void __launch_bounds__(COLLIDE_EVEN_THREADS, CTAS) k_collide_even_tma(const Lattice<T> L, const int ntiles, const int bulk_skip) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     typedef T Stage[38][COLLIDE_TILE];
     Stage* buf = reinterpret_cast<Stage*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + sizeof(Stage) * NST);
+    uint64_t* empty = full + NST;
+    T* cS = reinterpret_cast<T*>(empty + NST);                 // [2][tile] c_norm of my entry in the next tile
+    int* uS = reinterpret_cast<int*>(cS + 2 * COLLIDE_TILE);   // [2][tile] site id of my entry two tiles ahead
     const int tid = threadIdx.x;
+    const int stride = gridDim.x;
     const long long NC = L.NC;
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < NST; s++) pipe::mbar_init(&full[s], 1);
+        for (int s = 0; s < NST; s++) { pipe::mbar_init(&full[s], 1); pipe::mbar_init(&empty[s], COLLIDE_TILE / 32); }
         pipe::fence_mbar_init();
     }
     __syncthreads();
-    // threads 0..37 each copy one slot row of the tile (one UBLKCP per thread instead of 38 serial ones in one thread);
-    // thread 0 posts the byte count.  The phase cannot complete before that arrival, whatever the order.
-    auto issue = [&](const int tile, const int s) {
-        if (tid == 0) pipe::mbar_expect_tx(&full[s], (uint32_t)sizeof(Stage));
-        if (tid < 38) pipe::bulk_g2s(&buf[s][tid][0], L.pdf + (long long)tid * NC + (long long)tile * COLLIDE_TILE, (uint32_t)(sizeof(T) * COLLIDE_TILE), &full[s]);
-    };
-    int tile = blockIdx.x;
-#pragma unroll
-    for (int s = 0; s < NST; s++) {
-        const int tl = tile + s * (int)gridDim.x;
-        if (tl < ntiles) issue(tl, s);
+
+    if (tid >= COLLIDE_TILE) {
+        // ---- producer warp: lane l copies slot rows l and l + 32 of every tile of this CTA ----
+        const int lane = tid - COLLIDE_TILE;
+        int s = 0;
+        uint32_t phase = 0;   // parity of the empty-phase a refill of stage s has to see completed
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += stride, it++) {
+            if (it >= NST) pipe::mbar_wait(&empty[s], phase);
+            if (lane == 0) pipe::mbar_expect_tx(&full[s], (uint32_t)sizeof(Stage));
+            const T* src = L.pdf + (long long)tile * COLLIDE_TILE;
+            pipe::bulk_g2s(&buf[s][lane][0], src + (long long)lane * NC, (uint32_t)(sizeof(T) * COLLIDE_TILE), &full[s]);
+            if (lane < 6) pipe::bulk_g2s(&buf[s][lane + 32][0], src + (long long)(lane + 32) * NC, (uint32_t)(sizeof(T) * COLLIDE_TILE), &full[s]);
+            if (++s == NST) { s = 0; if (it >= NST) phase ^= 1; }
+        }
+        return;
     }
-    // site id and c_norm of my entry, fetched one / two tiles ahead (a dependent pair of loads: exposed, they were
-    // half of all stall samples)
+
+    // ---- consumer warps ----
     auto site = [&](const int tl) -> int {
         const int t = tl * COLLIDE_TILE + tid;
         return (tl < ntiles && t < L.n_fluid) ? L.fl_u[t] : -1;
     };
-    int u = site(tile), uN = site(tile + (int)gridDim.x);
-    T cnorm = u >= 0 ? L.c_norm[u] : T(0);
-    int s = 0;
+    // site id two tiles ahead and c_norm of the next tile's site: cp.async, so that no scoreboard is outstanding when the
+    // collision calls the division subroutine (a CALL waits for all of them; 11.5 % of the stall samples)
+    auto prefetch = [&](const int tile_site, const int u_cn, const int slot) {
+        if (tile_site < ntiles && tile_site * COLLIDE_TILE + tid < L.n_fluid) pipe::cp_async<4>(&uS[slot * COLLIDE_TILE + tid], L.fl_u + (tile_site * COLLIDE_TILE + tid));
+        if (u_cn >= 0) pipe::cp_async<sizeof(T)>(&cS[slot * COLLIDE_TILE + tid], L.c_norm + u_cn);
+        pipe::cp_async_commit();
+    };
+    int tile = blockIdx.x;
+    int u = site(tile), uN = site(tile + stride);
+    prefetch(tile + 2 * stride, u, 0);   // c_norm of the first tile, site of the third
+    int s = 0, slot = 0;                 // slot: the pair (cS, uS) half this iteration reads; the other half is being filled
     uint32_t phase = 0;
-    for (; tile < ntiles; tile += gridDim.x) {
+    for (; tile < ntiles; tile += stride) {
         const int t = tile * COLLIDE_TILE + tid;
         const bool live = u >= 0;
+        pipe::cp_async_wait<0>();
+        const T cnorm = live ? cS[slot * COLLIDE_TILE + tid] : T(0);
+        int uNN = -1;
+        { const int tl = tile + 2 * stride; if (tl < ntiles && tl * COLLIDE_TILE + tid < L.n_fluid) uNN = uS[slot * COLLIDE_TILE + tid]; }
+        slot ^= 1;
+        prefetch(tile + 3 * stride, uN, slot);   // lands during this collision
         T cnx = T(0), cny = T(0), cnz = T(0), tmp = T(0);
         if (live) node_force(L, u, cnorm, bulk_skip != 0, cnx, cny, cnz, tmp);   // interface nodes only: cn + curvature stencil
         pipe::mbar_wait(&full[s], phase);
-        // c_norm / site id of my next tiles, issued after the uses above (a load issued before them would share their
-        // scoreboard and expose its full latency there); they land during the collision
-        asm volatile("" ::: "memory");
-        const T cnormN = uN >= 0 ? L.c_norm[uN] : T(0);
-        const int uNN = site(tile + 2 * (int)gridDim.x);
         T g1[19], g2[19];
 #pragma unroll
         for (int q = 0; q < 19; q++) { g1[q] = buf[s][opc(q)][tid]; g2[q] = buf[s][opc(q) + 19][tid]; }
-        __syncthreads();   // every thread has its column: the stage goes back to the TMA
-        {
-            const int tn = tile + NST * (int)gridDim.x;
-            if (tn < ntiles) issue(tn, s);
-        }
+        // The columns must BE in registers before the stage is released: an LDS that is merely issued can still be queued
+        // in the shared-memory pipe when the arrive below becomes visible, and the refill then overwrites what it was
+        // about to read (seen once per ~10^5 warp-tiles at 256^3).  An empty asm that consumes the values makes the
+        // compiler wait for their scoreboard here.
+        // Handing the stage back.  An LDS that is merely ISSUED can still be pending when a later mbarrier arrive becomes
+        // visible: releasing right after the loads let the refill overwrite columns that had not been read yet (about
+        // one warp-tile in 10^5 at 256^3; compute-sanitizer racecheck reports the same pair).  The release therefore
+        // follows the store of phi, the first instruction that needs all 38 values: STG(phi) cannot issue before the loads
+        // have returned, and the arrive (release semantics) cannot pass the store.
+        const unsigned live_mask = __ballot_sync(0xffffffffu, live);
         if (live) {
-            const T phi_loc = collide_node<T, MRT>(L, g1, g2, cnx, cny, cnz, tmp);
-            L.phi[u] = phi_loc;
+            uint64_t* const bar = &empty[s];
+            const int leader = __ffs(live_mask) - 1;
+            collide_node<T, MRT>(L, g1, g2, cnx, cny, cnz, tmp, [&](const T phi_loc) {
+                L.phi[u] = phi_loc;
+                __syncwarp(live_mask);
+                if ((tid & 31) == leader) mbar_arrive(bar);
+            });
             T* __restrict__ po = L.pdf + t;
 #pragma unroll
             for (int q = 0; q < 19; q++) { po[(long long)q * NC] = g1[q]; po[(long long)(q + 19) * NC] = g2[q]; }
+        } else if (live_mask == 0u && (tid & 31) == 0) {
+            mbar_arrive(&empty[s]);   // a warp past the last fluid entry
         }
-        u = uN; uN = uNN; cnorm = cnormN;
+        u = uN; uN = uNN;
         if (++s == NST) { s = 0; phase ^= 1; }
     }
 }
@@ -169,6 +211,9 @@ __global__ void __launch_bounds__(COLLIDE_TILE, CTAS) k_collide_odd_pipe(const L
     NbStage* nbS = reinterpret_cast<NbStage*>(smem_raw + sizeof(Stage) * NST);
     typedef int WbStage[COLLIDE_TILE / 32][32];
     WbStage* wbS = reinterpret_cast<WbStage*>(smem_raw + sizeof(Stage) * NST + sizeof(NbStage) * NNB);
+    // [2][tile] each, one half read while the other is being filled: c_norm of my entry in the next tile, site id D + 2 tiles ahead
+    T* cS = reinterpret_cast<T*>(smem_raw + sizeof(Stage) * NST + (sizeof(NbStage) + sizeof(WbStage)) * NNB);
+    int* uS = reinterpret_cast<int*>(cS + 2 * COLLIDE_TILE);
     const int tid = threadIdx.x;
     const long long NC = L.NC;
     const int stride = gridDim.x;
@@ -182,14 +227,19 @@ __global__ void __launch_bounds__(COLLIDE_TILE, CTAS) k_collide_odd_pipe(const L
         return (tile < ntiles && t < L.n_fluid) ? L.fl_u[t] : -1;
     };
     // raw map entries of my 18 neighbours -> my column of index stage sb, link ranks of my warp's 32-entry group ->
-    // lanes 0..17; always commits one group
-    auto issue_index = [&](const int tile, const int u, const int sb) {
+    // lanes 0..17.  Rides in the same group: the site id of my entry in tile `tile_site` and the c_norm at site u_cn (the
+    // next tile's).  As cp.async none of these occupies a scoreboard: the collision's division subroutine is a real CALL
+    // and a call waits for every outstanding load (23 % of all stall samples sat there, profiles/r01d_*_stalls.txt).
+    // Always commits one group.
+    auto issue_index = [&](const int tile, const int u, const int sb, const int tile_site, const int u_cn, const int slot) {
         if (tile < ntiles && (tid & 31) < 18)
             pipe::cp_async<4>(&wbS[sb][tid >> 5][tid & 31], L.wbase + ((tile * (COLLIDE_TILE / 32) + (tid >> 5)) * 18 + (tid & 31)));
         if (u >= 0) {
 #pragma unroll
             for (int q = 1; q < 19; q++) pipe::cp_async<4>(&nbS[sb][q - 1][tid], cmap + (u + L.off(q)));
         }
+        if (tile_site < ntiles && tile_site * COLLIDE_TILE + tid < L.n_fluid) pipe::cp_async<4>(&uS[slot * COLLIDE_TILE + tid], L.fl_u + (tile_site * COLLIDE_TILE + tid));
+        if (u_cn >= 0) pipe::cp_async<sizeof(T)>(&cS[slot * COLLIDE_TILE + tid], L.c_norm + u_cn);
         pipe::cp_async_commit();
     };
     // slot entries of the 18 neighbour cells: the map entry itself for a non-solid neighbour, the mailbox entry
@@ -221,22 +271,24 @@ __global__ void __launch_bounds__(COLLIDE_TILE, CTAS) k_collide_odd_pipe(const L
     };
 
     int tile = blockIdx.x;
-    // ring of my site ids: uR[j] belongs to tile + j*stride, j = 0 .. D+2
-    int uR[D + 3];
+    // ring of my site ids: uR[j] belongs to tile + j*stride, j = 0 .. D+1 (uR[D+1] arrives through uS at the loop top)
+    int uR[D + 2];
 #pragma unroll
-    for (int j = 0; j < D + 3; j++) uR[j] = site(tile + j * stride);
-    // prologue: index + gathers of my first D tiles (groups B, A per tile, as in the loop), index of tile D
+    for (int j = 0; j < D + 1; j++) uR[j] = site(tile + j * stride);
+    uR[D + 1] = -1;
+    // prologue: index + gathers of my first D tiles (groups B, A per tile, as in the loop), index of tile D together
+    // with what the first iteration picks up from uS / cS
     int nb[18];
 #pragma unroll
     for (int j = 0; j < D; j++) {
-        issue_index(tile + j * stride, uR[j], j % NNB);
+        issue_index(tile + j * stride, uR[j], j % NNB, ntiles, -1, 0);
         pipe::cp_async_wait<0>();
         resolve_index(tile + j * stride, uR[j], j % NNB, nb);
         issue_gather(tile + j * stride, uR[j], nb, j % NST);
     }
-    issue_index(tile + D * stride, uR[D], D % NNB);
+    issue_index(tile + D * stride, uR[D], D % NNB, tile + (D + 1) * stride, uR[0], 0);
     pipe::cp_async_commit();   // keeps the group pattern of the loop: (B, A) per iteration
-    T cnorm = uR[0] >= 0 ? L.c_norm[uR[0]] : T(0);
+    int slot = 0;              // the (cS, uS) half this iteration reads
 
     int st = 0, sb = 0;   // value / index stage of the current tile
     for (; tile < ntiles; tile += stride) {
@@ -244,20 +296,21 @@ __global__ void __launch_bounds__(COLLIDE_TILE, CTAS) k_collide_odd_pipe(const L
         int sbD = sb + D; if (sbD >= NNB) sbD -= NNB;
         int sbD1 = sbD + 1; if (sbD1 >= NNB) sbD1 -= NNB;
         pipe::cp_async_wait<1>();   // index(tile + D) has landed (all but the newest group, the gathers of tile + D - 1)
-        resolve_index(tile + D * stride, uR[D], sbD, nb);
-        issue_index(tile + (D + 1) * stride, uR[D + 1], sbD1);
-        issue_gather(tile + D * stride, uR[D], nb, stD);
         const int t = tile * COLLIDE_TILE + tid;
         const int u = uR[0];
         const bool live = u >= 0;
+        {   // what rode in that group: my site in tile + D + 1 and the c_norm of this tile's site
+            const int tl = tile + (D + 1) * stride;
+            uR[D + 1] = (tl < ntiles && tl * COLLIDE_TILE + tid < L.n_fluid) ? uS[slot * COLLIDE_TILE + tid] : -1;
+        }
+        const T cnorm = live ? cS[slot * COLLIDE_TILE + tid] : T(0);
+        slot ^= 1;
+        resolve_index(tile + D * stride, uR[D], sbD, nb);
+        issue_index(tile + (D + 1) * stride, uR[D + 1], sbD1, tile + (D + 2) * stride, uR[1], slot);
+        issue_gather(tile + D * stride, uR[D], nb, stD);
         T cnx = T(0), cny = T(0), cnz = T(0), tmp = T(0);
         if (live) node_force(L, u, cnorm, bulk_skip != 0, cnx, cny, cnz, tmp);
         pipe::cp_async_wait<2 * D>();   // all but the 2D newest groups: the gathers of this tile have landed
-        // c_norm of tile + 1 and site id of tile + D + 3: ordinary loads that land during this collision.  Issued only
-        // now: a load issued before the uses above would share their scoreboard and expose its full latency there.
-        asm volatile("" ::: "memory");
-        const T cnormN = uR[1] >= 0 ? L.c_norm[uR[1]] : T(0);
-        const int uNew = site(tile + (D + 3) * stride);
         if (live) {
             T g1[19], g2[19];
 #pragma unroll
@@ -275,9 +328,7 @@ __global__ void __launch_bounds__(COLLIDE_TILE, CTAS) k_collide_odd_pipe(const L
             }
         }
 #pragma unroll
-        for (int j = 0; j < D + 2; j++) uR[j] = uR[j + 1];
-        uR[D + 2] = uNew;
-        cnorm = cnormN;
+        for (int j = 0; j < D + 1; j++) uR[j] = uR[j + 1];
         if (++st == NST) st = 0;
         if (++sb == NNB) sb = 0;
     }

@@ -81,6 +81,7 @@ struct Solver {
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
     long long pair_launches = 0;
     int variant = 0;   // kernel schedule variant (MFLBM_VARIANT, tuning only; results are identical)
+    int max_ctas = 0;  // MFLBM_MAX_CTAS: cap on the persistent collide grids (tests only)
     int num_sms = 148;
     // true when c_norm == 0 implies cn_* == 0 at every fluid node: established by k_normals (every gradient_chain), not
     // guaranteed for arrays handed in through upload_state.  Lets the collide kernels skip cn/curvature in the bulk.
@@ -106,6 +107,7 @@ struct Solver {
     void create(const Params* p, const mflbm_slab* sl, int dev, void* strm) {
         device = dev;
         if (const char* v = getenv("MFLBM_VARIANT")) variant = atoi(v);
+        if (const char* v = getenv("MFLBM_MAX_CTAS")) max_ctas = atoi(v);
         MF_CUDA(cudaSetDevice(device));
         MF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
         if (strm) { stream = (cudaStream_t)strm; own_stream = false; }
@@ -501,6 +503,10 @@ struct Solver {
         cn_consistent = true;
     }
 
+    // persistent grid of the collide kernels: CTAS resident CTAs per SM.  MFLBM_MAX_CTAS caps it (tests: a small lattice
+    // then walks many tiles per CTA, so the stage rings wrap as they do at full size)
+    int collide_grid(int ntiles, int ctas) const { return std::max(1, std::min(ntiles, max_ctas > 0 ? std::min(max_ctas, num_sms * ctas) : num_sms * ctas)); }
+
     // pipelined kernels (kernels_collide.cuh): persistent CTAs, TMA / cp.async staged PDF rows
     template <int MRT, int NST, int CTAS>
     void launch_even() {
@@ -509,7 +515,7 @@ struct Solver {
         constexpr size_t smem = collide_even_smem<T, NST>();
         static thread_local int configured = -1;
         if (configured != device) { MF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = device; }
-        kern<<<std::min(ntiles, num_sms * CTAS), COLLIDE_TILE, smem, stream>>>(L, ntiles, cn_consistent ? 1 : 0);
+        kern<<<collide_grid(ntiles, CTAS), COLLIDE_EVEN_THREADS, smem, stream>>>(L, ntiles, cn_consistent ? 1 : 0);
     }
     template <int MRT, int D, int CTAS>
     void launch_odd() {
@@ -518,7 +524,7 @@ struct Solver {
         constexpr size_t smem = collide_odd_smem<T, D>();
         static thread_local int configured = -1;
         if (configured != device) { MF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = device; }
-        kern<<<std::min(ntiles, num_sms * CTAS), COLLIDE_TILE, smem, stream>>>(L, ntiles, cn_consistent ? 1 : 0);
+        kern<<<collide_grid(ntiles, CTAS), COLLIDE_TILE, smem, stream>>>(L, ntiles, cn_consistent ? 1 : 0);
     }
     // Stage counts are sized for the 227 KB of shared memory of an SM.  MFLBM_VARIANT = 100*e + o
     // selects other (even, odd) configurations for tuning runs, for the shipped MRT model only.
