@@ -335,4 +335,146 @@ __global__ void __launch_bounds__(COLLIDE_TILE, CTAS) k_collide_odd_pipe(const L
     pipe::cp_async_wait<0>();
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// ODD step, warp-specialised (the default).  The pipelined kernel above runs one warp per scheduler (255 registers, one
+// CTA per SM) and that warp issues everything - map look-ups, link ranks, 38 gather addresses, the collision, 38 scatter
+// addresses: ncu shows 0.27 eligible warps per scheduler and no dominant stall, i.e. plain issue latency.  Here a CTA is
+// 4 consumer warps + 4 producer warps over the same 128-entry tiles:
+//   producer thread p, tile i :  raw map entries (plain loads, one tile ahead) -> slot entries of the 18 neighbour cells
+//                                (wall links -> mailbox entries) -> stage.nb / stage.u ;  38 PDF gathers + c_norm with
+//                                cp.async into stage.val / stage.cn ;  completion is reported to full[stage] by
+//                                cp.async.mbarrier.arrive (data) and a plain arrive (the st.shared of nb / u)
+//   consumer thread p, tile i :  wait full[stage] -> collide -> scatter through stage.nb -> arrive empty[stage]
+// The consumer's instruction stream shrinks by a third and the producer warp fills its issue slots.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+struct OddStage {
+    T val[38][COLLIDE_TILE];
+    int nb[18][COLLIDE_TILE];
+    T cn[COLLIDE_TILE];
+    int u[COLLIDE_TILE];
+};
+template <typename T, int NST>
+constexpr size_t collide_odd_ws_smem() { return sizeof(OddStage<T>) * NST + 16 * NST; }
+
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(pipe::smem_u32(bar)) : "memory");
+}
+
+template <typename T, int MRT, int NST, int CTAS>
+__global__ void __launch_bounds__(2 * COLLIDE_TILE, CTAS) k_collide_odd_ws(const Lattice<T> L, const int ntiles, const int bulk_skip) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    typedef OddStage<T> Stage;
+    Stage* stg = reinterpret_cast<Stage*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + sizeof(Stage) * NST);
+    uint64_t* empty = full + NST;
+    const int tid = threadIdx.x;
+    const int stride = gridDim.x;
+    const long long NC = L.NC;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NST; s++) { pipe::mbar_init(&full[s], 2 * COLLIDE_TILE); pipe::mbar_init(&empty[s], COLLIDE_TILE / 32); }
+        pipe::fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (tid >= COLLIDE_TILE) {
+        // =========================== producer ===========================
+        // The map entries, link ranks and site ids of the NEXT tile are ordinary loads into registers, issued one tile
+        // ahead (the producer has registers to spare and never calls a subroutine, so nothing waits on their scoreboards
+        // early): an LDG costs the load/store pipe 1.8 cycles against 8 for an LDGSTS, and that pipe is what bounds this
+        // kernel (232 LDGSTS + 152 scattered STG.64 + ~300 LDS per tile).
+        const int p = tid - COLLIDE_TILE, lane = p & 31, w = p >> 5;
+        const T* __restrict__ p0 = L.pdf;
+        const int* __restrict__ cmap = L.cmap;
+        const unsigned lanes_below = (1u << lane) - 1u;
+        auto site_of = [&](const int tl) -> int { return (tl < ntiles && tl * COLLIDE_TILE + p < L.n_fluid) ? __ldg(L.fl_u + (tl * COLLIDE_TILE + p)) : -1; };
+        auto load_raw = [&](const int tl, const int u, int (&c)[18], int& wb) {
+            wb = (tl < ntiles && lane < 18) ? __ldg(L.wbase + ((tl * (COLLIDE_TILE / 32) + w) * 18 + lane)) : 0;
+#pragma unroll
+            for (int q = 1; q < 19; q++) c[q - 1] = u >= 0 ? __ldg(cmap + (u + L.off(q))) : 0;
+        };
+        int tile = blockIdx.x;
+        int uCur = site_of(tile), uNxt = site_of(tile + stride);
+        int cN[18], wbN;
+        load_raw(tile, uCur, cN, wbN);
+        int st = 0;
+        uint32_t ph_empty = 0;
+        for (int i = 0; tile < ntiles; tile += stride, i++) {
+            int c[18];
+#pragma unroll
+            for (int q = 0; q < 18; q++) c[q] = cN[q];
+            const int wb = wbN;
+            const int uNxt2 = site_of(tile + 2 * stride);
+            load_raw(tile + stride, uNxt, cN, wbN);   // consumed in the next iteration
+            if (i >= NST) pipe::mbar_wait(&empty[st], ph_empty);
+            Stage& S = stg[st];
+            // slot entries of the 18 neighbour cells: the map entry itself for a non-solid neighbour, the mailbox entry
+            // mb0 + rank for a wall link (core.cuh)
+            int nb[18];
+#pragma unroll
+            for (int q = 1; q < 19; q++) {
+                const int cc = c[q - 1];
+                const unsigned walls = __ballot_sync(0xffffffffu, cc < 0);
+                const int base = __shfl_sync(0xffffffffu, wb, q - 1);
+                nb[q - 1] = cc >= 0 ? cc : L.mb0 + base + __popc(walls & lanes_below);
+                S.nb[q - 1][p] = nb[q - 1];
+            }
+            S.u[p] = uCur;
+            mbar_arrive(&full[st]);   // release: nb / u are visible to whoever sees the phase complete
+            if (uCur >= 0) {
+                const int t = tile * COLLIDE_TILE + p;
+#pragma unroll
+                for (int q = 0; q < 19; q++) {
+                    const int src = (q == 0) ? t : nb[opc(q) - 1];   // x - e_q = x + e_opc(q), slot q there
+                    pipe::cp_async<sizeof(T)>(&S.val[q][p], p0 + (long long)q * NC + src);
+                    pipe::cp_async<sizeof(T)>(&S.val[q + 19][p], p0 + (long long)(q + 19) * NC + src);
+                }
+                pipe::cp_async<sizeof(T)>(&S.cn[p], L.c_norm + uCur);
+            }
+            cp_async_mbar_arrive_noinc(&full[st]);   // fires when every cp.async above has landed
+            uCur = uNxt; uNxt = uNxt2;
+            if (++st == NST) { st = 0; if (i >= NST) ph_empty ^= 1; }
+        }
+        pipe::cp_async_commit();
+        pipe::cp_async_wait<0>();
+        return;
+    }
+
+    // =========================== consumer ===========================
+    int st = 0;
+    uint32_t ph_full = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += stride) {
+        Stage& S = stg[st];
+        pipe::mbar_wait(&full[st], ph_full);
+        const int t = tile * COLLIDE_TILE + tid;
+        const int u = S.u[tid];
+        const bool live = u >= 0;
+        if (live) {
+            const T cnorm = S.cn[tid];
+            T cnx, cny, cnz, tmp;
+            node_force(L, u, cnorm, bulk_skip != 0, cnx, cny, cnz, tmp);
+            T g1[19], g2[19];
+#pragma unroll
+            for (int q = 0; q < 19; q++) { g1[q] = S.val[q][tid]; g2[q] = S.val[q + 19][tid]; }
+            const T phi_loc = collide_node<T, MRT>(L, g1, g2, cnx, cny, cnz, tmp);
+            L.phi[u] = phi_loc;
+            T* __restrict__ po = L.pdf;
+            po[t] = g1[0];
+            po[19 * NC + t] = g2[0];
+#pragma unroll
+            for (int q = 1; q < 19; q++) {
+                const int dst = S.nb[q - 1][tid];
+                po[(long long)opc(q) * NC + dst] = g1[q];
+                po[(long long)(opc(q) + 19) * NC + dst] = g2[q];
+            }
+        }
+        // every value and every entry of the stage has been consumed by an issued store (see the even kernel)
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&empty[st]);
+        if (++st == NST) { st = 0; ph_full ^= 1; }
+    }
+}
+
 }  // namespace mflbm

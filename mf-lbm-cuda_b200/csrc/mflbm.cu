@@ -526,6 +526,15 @@ struct Solver {
         if (configured != device) { MF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = device; }
         kern<<<collide_grid(ntiles, CTAS), COLLIDE_TILE, smem, stream>>>(L, ntiles, cn_consistent ? 1 : 0);
     }
+    template <int MRT, int NST, int CTAS>
+    void launch_odd_ws() {
+        const int ntiles = ceil_div((int)n_fluid, COLLIDE_TILE);
+        auto kern = k_collide_odd_ws<T, MRT, NST, CTAS>;
+        constexpr size_t smem = collide_odd_ws_smem<T, NST>();
+        static thread_local int configured = -1;
+        if (configured != device) { MF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = device; }
+        kern<<<collide_grid(ntiles, CTAS), 2 * COLLIDE_TILE, smem, stream>>>(L, ntiles, cn_consistent ? 1 : 0);
+    }
     // Stage counts are sized for the 227 KB of shared memory of an SM.  MFLBM_VARIANT = 100*e + o
     // selects other (even, odd) configurations for tuning runs, for the shipped MRT model only.
     template <int MRT>
@@ -539,7 +548,12 @@ struct Solver {
                     if (o == 2) { launch_odd<MRT, 3, 1>(); goto done; }
                     if (o == 3) { launch_odd<MRT, 1, 1>(); goto done; }
                 }
-                launch_odd<MRT, 2, 1>();   // measured best on the 256^3 pack (profiles/README.md)
+                if constexpr (MRT == 2) {
+                    if (o == 4) { launch_odd<MRT, 2, 1>(); goto done; }
+                    if (o == 5) { launch_odd_ws<MRT, 2, 1>(); goto done; }
+                    if (o == 6) { launch_odd_ws<MRT, 4, 1>(); goto done; }
+                }
+                launch_odd_ws<MRT, 3, 1>();   // measured best on the 256^3 pack (profiles/README.md)
             } else {
                 if constexpr (MRT == 2) {
                     if (e == 1) { launch_even<MRT, 4, 1>(); goto done; }
@@ -555,7 +569,14 @@ struct Solver {
                     if (o == 3) { launch_odd<MRT, 2, 1>(); goto done; }
                     if (o == 4) { launch_odd<MRT, 3, 1>(); goto done; }
                 }
-                launch_odd<MRT, 2, 2>();
+                if constexpr (MRT == 2) {
+                    if (o == 5) { launch_odd<MRT, 2, 2>(); goto done; }
+                    if (o == 6) { launch_odd_ws<MRT, 3, 1>(); goto done; }
+                    if (o == 7) { launch_odd_ws<MRT, 6, 1>(); goto done; }
+                    if (o == 8) { launch_odd_ws<MRT, 2, 2>(); goto done; }
+                    if (o == 9) { launch_odd_ws<MRT, 3, 2>(); goto done; }
+                }
+                launch_odd_ws<MRT, 4, 1>();
             } else {
                 if constexpr (MRT == 2) {
                     if (e == 1) { launch_even<MRT, 8, 1>(); goto done; }

@@ -211,7 +211,9 @@ class Run {
         const int g = type == 1 ? 1 : 2;
         std::vector<T> out;
         VtkFile v(vtk_name(opt.dir, type == 1 ? "full_flow_field/full_flow_field_" : "full_flow_field/force_vector_", nt), nx, ny, nz);
-        crop(phi, 4, nx, ny, nz, out); v.scalars("phi", fmt, out);
+        crop(phi, 4, nx, ny, nz, out);
+        if (type == 1) for (size_t n = 0; n < out.size(); n++) if (cs.walls[n]) out[n] = T(0);   // compute_macro_vars zeroes the host phi in solids (src/Misc.cpp:222-274)
+        v.scalars("phi", fmt, out);
         crop(d, g, nx, ny, nz, out); v.scalars("density", fmt, out);
         crop(a, g, nx, ny, nz, out); v.scalars("velocity_X", fmt, out);
         crop(b, g, nx, ny, nz, out); v.scalars("velocity_Y", fmt, out);

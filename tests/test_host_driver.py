@@ -1,0 +1,270 @@
+"""The C++ host driver (mf-lbm-cuda_b200/bin/mflbm_run) as a drop-in for the reference program.
+
+  * CPU (`-m "not gpu"`): `--check-input` parses a reference-format case directory and prints what the host derives before
+    the GPU layer is touched; scalars must be bit-identical to the ones the oracle-checked Python mirror derives
+    (mflbm.derive_params), the velocity-inlet profile bit-identical to the oracle's (itself pinned against the
+    reference's CPU code), and the reference's fatal input errors must be fatal here too.
+  * GPU (`-m gpu`): the driver and the reference's STOCK program (oracle/_ref/MF_LBM_CUDA_*, src/main.cpp compiled
+    unmodified) run the same case directory; monitor files, checkpoint and VTK output are compared.
+"""
+import shutil
+import struct
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import common
+import refcase as rc
+
+REPO = Path(__file__).resolve().parent.parent
+EXE = REPO / "mf-lbm-cuda_b200" / "bin" / "mflbm_run"
+
+
+def run_driver(case: Path, *args, check=True, timeout=900):
+    if not EXE.exists():
+        subprocess.run(["make", "-C", str(REPO / "mf-lbm-cuda_b200" / "host"), "all"], check=True, stdout=subprocess.DEVNULL)
+    r = subprocess.run([str(EXE), "--dir", str(case), *args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
+    if check and r.returncode != 0:
+        raise AssertionError(f"mflbm_run failed ({r.returncode}):\n{r.stdout[-3000:]}")
+    return r
+
+
+def parse_check(out: str) -> dict:
+    d = {}
+    for line in out.splitlines():
+        if line.startswith("CHECK "):
+            k, *v = line.split()[1:]
+            d[k] = v
+    return d
+
+
+def fnv1a(b: bytes) -> int:
+    h = 1469598103934665603
+    for x in np.frombuffer(b, np.uint8).tolist():
+        h = ((h ^ x) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("name", ["tube_pressure", "pack_velocity", "periodic_drop", "rect_quirk"])
+def test_check_input_matches_python_mirror_and_oracle(tmp_path, name, prec):
+    import mflbm
+    ctl, solid = common.CASES[name]()
+    full = rc.write_case(tmp_path, ctl, solid)
+    chk = parse_check(run_driver(tmp_path, "--prec", prec, "--check-input").stdout)
+    o, octl, _ = common.make_oracle(name, prec)
+    assert [int(x) for x in chk["dims"]] == [o.nx, o.ny, o.nz]
+    # interior walls after set_walls (incl. the swapped-stride read quirk for nx != ny): the oracle's array is pinned
+    # against the reference CPU code (tests/test_oracle_vs_reference.py)
+    want_walls = (o.arr("walls_global") != 0).astype(np.int8)
+    assert int(chk["walls_fnv1a"][0]) == fnv1a(want_walls.tobytes())
+    assert int(chk["pore_sum"][0]) == int(o.scalar("pore_sum"))
+    P = mflbm.derive_params(full, prec)
+    R = np.float32 if prec == "f32" else np.float64
+    for k in ("cos_theta", "la_nui1", "la_nui2", "phi_inlet", "force_z", "rho_in", "rho_out", "uin_avg", "A_xy"):
+        got = R(float.fromhex(chk[k][0]))
+        assert got == R(getattr(P, k)), (k, got, getattr(P, k))
+    if full["inlet_BC"] == 1 and full["kper"] == 0:
+        assert int(chk["W_in_fnv1a"][0]) == fnv1a(np.ascontiguousarray(o.arr("W_in")).tobytes()), "W_in must be bit-identical to the reference's"
+
+
+def test_fatal_inputs_are_fatal(tmp_path):
+    ctl, solid = common.CASES["tube_pressure"]()
+    # a trailing newline in job_status.txt (src/IO_multiphase.cpp:25-36 compares the whole file)
+    a = tmp_path / "a"
+    rc.write_case(a, ctl, solid, job_status="new_simulation\n")
+    assert run_driver(a, "--check-input", check=False).returncode == 1
+    # contact angle above 90 degrees (src/IO_multiphase.cpp:200-203)
+    b = tmp_path / "b"
+    rc.write_case(b, dict(ctl, theta=120), solid)
+    r = run_driver(b, "--check-input", check=False)
+    assert r.returncode == 1 and "contact angle" in r.stdout
+    # a missing key (src/utils.cpp:67)
+    c = tmp_path / "c"
+    rc.write_case(c, ctl, solid)
+    f = c / "input" / "simulation_control.txt"
+    f.write_text("\n".join(l for l in f.read_text().splitlines() if not l.startswith("RK_beta")) + "\n")
+    r = run_driver(c, "--check-input", check=False)
+    assert r.returncode == 1 and "RK_beta" in r.stdout
+    # a geometry file name that does not end in a digit (src/Misc.cpp:31-34)
+    d = tmp_path / "d"
+    rc.write_case(d, ctl, solid)
+    (d / "input" / "Geometry_File_Path.txt").write_text("geo_file_path_\tinput/geometry/nodigits\ngeo_boundary_file_path_\tinput/geometry/nodigits\n")
+    assert run_driver(d, "--check-input", check=False).returncode == 1
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GPU: against the reference's stock program
+# ----------------------------------------------------------------------------------------------------------
+def read_checkpoint(path: Path, nx, ny, nz, rt, convective):
+    raw = path.read_bytes()
+    s = np.dtype(rt).itemsize
+    nt = struct.unpack_from("<i", raw, 0)[0]
+    force_z, rho_in = np.frombuffer(raw, rt, 2, 4)
+    off = 4 + 2 * s
+    n1, n4, npl = (nx + 2) * (ny + 2) * (nz + 2), (nx + 8) * (ny + 8) * (nz + 8), (nx + 2) * (ny + 2)
+    pdf = np.frombuffer(raw, rt, 38 * n1, off).reshape(2, 19, nz + 2, ny + 2, nx + 2); off += 38 * n1 * s
+    phi = np.frombuffer(raw, rt, n4, off).reshape(nz + 8, ny + 8, nx + 8); off += n4 * s
+    out = dict(ntime=nt, force_z=force_z, rho_in=rho_in, pdf=pdf, phi=phi)
+    if convective:
+        out["f_convec"] = np.frombuffer(raw, rt, 19 * npl, off); off += 19 * npl * s
+        out["g_convec"] = np.frombuffer(raw, rt, 19 * npl, off); off += 19 * npl * s
+        out["phi_convec"] = np.frombuffer(raw, rt, npl, off); off += npl * s
+    assert off == len(raw), "checkpoint size"
+    return out
+
+
+def read_vtk(path: Path):
+    raw = path.read_bytes()
+    pos, header, fields = 0, [], {}
+    def line():
+        nonlocal pos
+        e = raw.index(b"\n", pos); l = raw[pos:e].decode(); pos = e + 1; return l
+    for _ in range(8):
+        header.append(line())
+    n = int(header[-1].split()[1])
+    while pos < len(raw):
+        _, name, typ = line().split()
+        line()   # LOOKUP_TABLE default
+        fields[name] = (typ, raw[pos:])   # payload cut by the caller (the declared type is not the stored one)
+        # find the next "SCALARS" marker to delimit
+        nxt = raw.find(b"SCALARS ", pos)
+        end = len(raw) if nxt < 0 else nxt
+        fields[name] = (typ, raw[pos:end]); pos = end
+    return header, n, fields
+
+
+def rows(path: Path):
+    return np.array([[float(x) for x in l.split() if x != "sec"] for l in path.read_text().splitlines() if l.strip()])
+
+
+STOCK_CASES = {
+    # name: (control overrides, geometry case)
+    "tube_pressure": dict(max_time_step=39, monitor_timer=10, monitor_profile_timer_ratio=2, computation_time_timer=20, display_steps_timer=20,
+                          ntime_animation=20, ntime_visual=40, benchmark_cmd=0, steady_state_option=3, convergence_criteria=1e-12),
+    "pack_velocity": dict(max_time_step=29, monitor_timer=10, monitor_profile_timer_ratio=1, computation_time_timer=30, display_steps_timer=10,
+                          ntime_animation=1000000, ntime_visual=1000000, benchmark_cmd=1, steady_state_option=0),
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("name", sorted(STOCK_CASES))
+def test_driver_matches_stock_reference_program(gpu_lib, tmp_path, name, prec):
+    stock = rc.REF_BIN_DIR / f"MF_LBM_CUDA_{prec}"
+    if not stock.exists():
+        pytest.skip(f"{stock} not built (oracle/build_ref.sh needs /root/reference)")
+    ctl, solid = common.CASES[name]()
+    ctl = dict(ctl, **STOCK_CASES[name])
+    ours, ref = tmp_path / "ours", tmp_path / "ref"
+    full = rc.write_case(ours, ctl, solid)
+    shutil.copytree(ours, ref)
+    run_driver(ours, "--prec", prec)
+    r = subprocess.run([str(stock)], cwd=str(ref), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:]
+    nz, ny, nx = solid.shape
+    rt = np.float32 if prec == "f32" else np.float64
+    tol = common.TOL[prec]
+    # job status (written to ./job_status.txt by both)
+    assert (ours / "job_status.txt").read_text() == (ref / "job_status.txt").read_text() == "simulation_reached_max_step\n"
+    # monitor files: same rows, same columns (printed with 6 significant digits)
+    out_o, out_r = ours / "results" / "out1.output", ref / "results" / "out1.output"
+    names = sorted(p.name for p in out_r.iterdir() if p.is_file() and p.suffix == ".dat")
+    assert names == sorted(p.name for p in out_o.iterdir() if p.is_file() and p.suffix == ".dat")
+    for n in names:
+        a, b = rows(out_o / n), rows(out_r / n)
+        assert a.shape == b.shape, n
+        if n == "time.dat":
+            assert np.array_equal(a[:, 0], b[:, 0])
+            continue
+        # columns that are sums of signed values (flow rates at rest) are compared on the scale of the file
+        scale = np.maximum(np.abs(b), np.abs(b).max(axis=0, keepdims=True))
+        rtol = 2e-5 if prec == "f64" else 2e-3
+        bad = np.abs(a - b) > rtol * scale + 1e-30
+        if n in ("Ca_number.dat", "flowrate_time.dat", "steady_monitor_saturation_error.dat"):
+            bad &= np.abs(a - b) > (1e-9 if prec == "f64" else 1e-6)   # cancelling sums / differences of nearly equal numbers
+        assert not bad.any(), (n, a[bad][:4], b[bad][:4])
+    assert sorted(p.name for p in (out_o / "profile").iterdir()) == sorted(p.name for p in (out_r / "profile").iterdir())
+    for p in (out_r / "profile").iterdir():
+        a, b = rows(out_o / "profile" / p.name), rows(p)
+        assert a.shape == b.shape
+        assert np.allclose(a[1:], b[1:], rtol=2e-5 if prec == "f64" else 2e-3, atol=1e-9 if prec == "f64" else 1e-5), p.name   # row 0 is out of bounds in the reference
+    info_o, info_r = (out_o / "info.txt").read_text().splitlines(), (out_r / "info.txt").read_text().splitlines()
+    assert info_o == info_r
+    # checkpoint
+    conv = full["outlet_BC"] == 1
+    co = read_checkpoint(ours / "results" / "out2.checkpoint" / "id0000", nx, ny, nz, rt, conv)
+    cr = read_checkpoint(ref / "results" / "out2.checkpoint" / "id0000", nx, ny, nz, rt, conv)
+    assert co["ntime"] == cr["ntime"] and co["force_z"] == cr["force_z"] and co["rho_in"] == cr["rho_in"]
+    assert common.relerr(co["pdf"], cr["pdf"]) <= tol
+    fluid = np.zeros(cr["phi"].shape, bool)
+    fluid[4:-4, 4:-4, 4:-4] = solid == 0
+    fluid[:, :, 4] = False; fluid[:, :, -5] = False; fluid[:, 4, :] = False; fluid[:, -5, :] = False   # domain walls
+    # the reference's host phi was zeroed inside solids by its monitor / VTK writer before the checkpoint was written
+    assert np.abs(co["phi"][fluid].astype(np.float64) - cr["phi"][fluid]).max() <= tol * max(1.0, float(np.abs(cr["phi"]).max()))
+    if conv:
+        # Reference defect: its step function never copies the convective-outlet buffers back to the host
+        # (src/main_iteration_GPU.cu:2059-2076 downloads phi, curv, c_norm, cn_*, pdf only), so its checkpoint carries the
+        # INITIAL buffers whatever the step.  We write the device state; the checker for it is the oracle.
+        o, _, _ = common.make_oracle(name, prec)
+        for k in ("f_convec", "g_convec", "phi_convec"):
+            assert np.array_equal(cr[k], o.arr(k).reshape(-1)), f"reference {k} is expected to be the step-0 buffer"
+        o.run(1, cr["ntime"] - 1)
+        for k in ("f_convec", "g_convec"):
+            assert common.relerr(co[k], o.arr(k).reshape(-1), scale_of=cr["pdf"]) <= tol, k
+        assert common.relerr(co["phi_convec"], o.arr("phi_convec").reshape(-1)) <= tol
+    # VTK files: same set, same headers, same payload sizes, values within tolerance
+    fo, fr = ours / "results" / "out3.field_data", ref / "results" / "out3.field_data"
+    vt_r = sorted(str(p.relative_to(fr)) for p in fr.rglob("*.vtk"))
+    assert vt_r == sorted(str(p.relative_to(fo)) for p in fo.rglob("*.vtk"))
+    for rel in vt_r:
+        ho, no_, fo_ = read_vtk(fo / rel)
+        hr, nr_, fr_ = read_vtk(fr / rel)
+        assert ho == hr and list(fo_) == list(fr_), rel
+        for k in fr_:
+            (to, bo), (tr, br) = fo_[k], fr_[k]
+            assert to == tr and len(bo) == len(br), (rel, k)
+            if k == "walls":
+                assert bo == br
+                continue
+            dt = np.dtype(">f4") if len(br) == 4 * nr_ else np.dtype(">f8")
+            a, b = np.frombuffer(bo, dt).astype(np.float64), np.frombuffer(br, dt).astype(np.float64)
+            if k in ("phi", "density"):   # solid nodes included: both writers store 0 there
+                assert np.abs(a - b).max() <= max(tol, 1e-6 if dt.itemsize == 4 else 0) * max(1.0, np.abs(b).max()), (rel, k)
+            else:   # velocities: O(1e-3 .. 1e-6) numbers built from cancelling sums
+                assert np.abs(a - b).max() <= (1e-9 if prec == "f64" else 1e-5), (rel, k)
+
+
+@pytest.mark.gpu
+def test_driver_restart_continues_like_the_reference(gpu_lib, tmp_path):
+    """continue_simulation from one and the same reference-written checkpoint: both programs re-execute the last step
+    index and must end in the same state."""
+    prec = "f64"
+    stock = rc.REF_BIN_DIR / f"MF_LBM_CUDA_{prec}"
+    if not stock.exists():
+        pytest.skip(f"{stock} not built")
+    ctl, solid = common.CASES["tube_pressure"]()
+    base = dict(ctl, max_time_step=19, monitor_timer=10, computation_time_timer=20, display_steps_timer=1000, benchmark_cmd=1)
+    first = tmp_path / "first"
+    rc.write_case(first, base, solid)
+    r = subprocess.run([str(stock)], cwd=str(first), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:]
+    ours, ref = tmp_path / "ours", tmp_path / "ref"
+    # the second leg must END on a monitor step: the reference checkpoints its last downloaded host copy, which is only
+    # refreshed on timer steps
+    second = dict(base, max_time_step=20)
+    for d in (ours, ref):
+        shutil.copytree(first, d)
+        (d / "input" / "simulation_control.txt").write_text(rc.control_text(dict(second, nxGlobal=solid.shape[2], nyGlobal=solid.shape[1], nzGlobal=solid.shape[0],
+                                                                                  external_geometry_read_cmd=1)))
+        (d / "input" / "job_status.txt").write_text("continue_simulation")
+    run_driver(ours, "--prec", prec)
+    r = subprocess.run([str(stock)], cwd=str(ref), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:]
+    nz, ny, nx = solid.shape
+    co = read_checkpoint(ours / "results" / "out2.checkpoint" / "id0000", nx, ny, nz, np.float64, False)
+    cr = read_checkpoint(ref / "results" / "out2.checkpoint" / "id0000", nx, ny, nz, np.float64, False)
+    assert co["ntime"] == cr["ntime"] == 20 + 20 + 1
+    assert common.relerr(co["pdf"], cr["pdf"]) <= common.TOL[prec]
