@@ -72,8 +72,16 @@ __global__ void k_extrap_phi(const Lattice<T> L, const int* __restrict__ list, c
 // live[t] != 0 says that the four outputs of list entry t may be non-zero in memory.  Away from interfaces the result is
 // zero step after step (the reference rewrites those zeros every step, 4 stores per site); here an entry that was zero
 // and stays zero stores nothing.  Arrays that came from outside (upload_state) start with live = 1 everywhere.
+// near[u'] = 1 is raised at the 18 neighbours of every site that gets a non-zero normal: k_extrap_cn reads that one byte
+// instead of probing the c_norm of 18 scattered neighbours, and clears it.
 template <typename T>
-__global__ void __launch_bounds__(128) k_normals(const Lattice<T> L, const int* __restrict__ list, unsigned char* __restrict__ live, const int count) {
+__device__ __forceinline__ void raise_near(const Lattice<T>& L, unsigned char* __restrict__ near, const int u) {
+#pragma unroll
+    for (int q = 1; q < 19; q++) near[u + L.off(q)] = 1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_normals(const Lattice<T> L, const int* __restrict__ list, unsigned char* __restrict__ live, unsigned char* __restrict__ near, const int count) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
     const int u = list[t];
@@ -88,6 +96,7 @@ __global__ void __launch_bounds__(128) k_normals(const Lattice<T> L, const int* 
     } else {
         gx = gx / nrm; gy = gy / nrm; gz = gz / nrm;
         live[t] = 1;
+        raise_near(L, near, u);
     }
     L.cn_x[u] = gx; L.cn_y[u] = gy; L.cn_z[u] = gz; L.c_norm[u] = nrm;
 }
@@ -150,23 +159,22 @@ __global__ void k_alter(const Lattice<T> L, const int* __restrict__ list, const 
 // cn at solid-boundary nodes <- weighted mean of the fluid neighbours' cn (:880-906); mask as in k_extrap_phi.
 // A neighbour with c_norm == 0 has cn == 0 (k_normals), so where every contributing neighbour is interface-free the mean
 // is exactly +0: 18 c_norm loads decide that, and an entry that was zero and stays zero stores nothing (live, as above).
+// near[c2] (raised by the normals kernel of this chain, cleared here) says whether any of them has c_norm != 0.
 template <typename T>
 __global__ void k_extrap_cn(const Lattice<T> L, const int* __restrict__ list, const int* __restrict__ mask, unsigned char* __restrict__ live,
-                            const int count) {
+                            unsigned char* __restrict__ near, const int count) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
     const int c2 = list[t];
-    const int m = mask[t];
-    bool any = false;
-#pragma unroll
-    for (int q = 1; q < 19; q++)
-        if (m & (1 << (q - 1))) any = any || (L.c_norm[c2 + L.off(q)] != T(0));
+    const bool any = near[c2] != 0;
+    if (any) near[c2] = 0;
     if (!any) {
         if (!live[t]) return;
         live[t] = 0;
         L.cn_x[c2] = T(0); L.cn_y[c2] = T(0); L.cn_z[c2] = T(0);
         return;
     }
+    const int m = mask[t];
     T sx = T(0), sy = T(0), sz = T(0), wsum = T(0);
 #pragma unroll
     for (int q = 1; q < 19; q++) {
