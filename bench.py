@@ -230,6 +230,21 @@ def run_ours(args) -> dict:
     ms = e0.elapsed_time(e1)
     launches = solver.kernel_launches - l0
     nt += args.steps
+    # ---- per-kernel timing of the dominant launches (collide odd / even), CUDA events on the launching stream ----------
+    kpairs = max(2, min(args.steps // 2, 25))
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(2 * kpairs)]
+    for a, b in ev:
+        a.record(stream)
+        solver.step_phase(nt, 0)
+        b.record(stream)
+        solver.step_phase(nt, 1)
+        solver.step_phase(nt, 2)
+        nt += 1
+    torch.cuda.synchronize()
+    first_odd = (nt - 2 * kpairs) % 2 == 1
+    t_all = [a.elapsed_time(b) for a, b in ev]
+    t_odd = float(np.mean(t_all[0::2] if first_odd else t_all[1::2]))
+    t_even = float(np.mean(t_all[1::2] if first_odd else t_all[0::2]))
     mon = solver.monitor()
     assert mon["nan_detected"] == 0, "simulation produced non-finite values"
     ms_step = ms / args.steps
@@ -237,7 +252,12 @@ def run_ours(args) -> dict:
     s_bytes = 8 if prec == "f64" else 4
     bytes_step = 78 * s_bytes * n_fluid + n_site
     peak, peak_src = hbm_peak()
-    achieved = bytes_step / (ms_step * 1e-3) / 1e9
+    achieved_step = bytes_step / (ms_step * 1e-3) / 1e9
+    # dominant kernel = the collide launch (one per step, alternating odd / even): 38 PDF reads + 38 PDF writes + the phi
+    # write per fluid node; the remaining s + 1 B/site of the step model belong to the gradient chain
+    bytes_collide = 77 * s_bytes * n_fluid
+    t_collide = 0.5 * (t_odd + t_even)
+    achieved = bytes_collide / (t_collide * 1e-3) / 1e9
     traffic = None
     tf = REPO / "profiles" / "traffic.json"
     if tf.exists():
@@ -274,8 +294,13 @@ def run_ours(args) -> dict:
                    "fluid_mlups": n_fluid * args.steps / 1e6 / (ms * 1e-3), "geometry_preprocess_s": t_geo,
                    "saturation_full_domain": mon2["saturation_full_domain"]},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": peak_src, "bytes_model": "78*sizeof(real)*N_fluid + N_site per step (whole step, all kernels)",
-                     "bytes_per_step": bytes_step},
+                     "peak_source": peak_src, "kernel": "collide (k_collide_odd_ws / k_collide_even_tma, one launch per step)",
+                     "bytes_model": "77*sizeof(real)*N_fluid per collide launch (38 PDF reads + 38 PDF writes + phi write)",
+                     "bytes_per_launch": bytes_collide, "ms_per_launch": t_collide,
+                     "odd": {"ms": t_odd, "achieved": bytes_collide / (t_odd * 1e-3) / 1e9, "frac": bytes_collide / (t_odd * 1e-3) / 1e9 / peak},
+                     "even": {"ms": t_even, "achieved": bytes_collide / (t_even * 1e-3) / 1e9, "frac": bytes_collide / (t_even * 1e-3) / 1e9 / peak},
+                     "whole_step": {"bytes_model": "78*sizeof(real)*N_fluid + N_site per step, all kernels (SURVEY.md 8d)", "bytes_per_step": bytes_step,
+                                    "achieved": achieved_step, "frac": achieved_step / peak, "collide_share_of_step": t_collide / ms_step}},
         "e2e": {"value": e2e_mlups, "unit": "MLUPS", "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
                 "what": "upload_state from pinned host + K steps + monitor + download_state, through the C ABI"},
         "gpu_launches": int(launches),

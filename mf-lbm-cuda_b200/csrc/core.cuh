@@ -90,7 +90,14 @@ struct Lattice {
     // for the plane kernels and layout conversion only
     __device__ int mail_index(int t, int o) const {
         int r = mb0 + wbase[(t >> 5) * 18 + (o - 1)];
-        for (int tt = t & ~31; tt < t; tt++) r += cmap[fl_u[tt] + off(o)] < -1 ? 1 : 0;
+        const int t0 = t & ~31, n = t & 31, oo = off(o);
+        // all 31 candidates at once: two rounds of independent loads instead of a chain of up to 62 dependent ones (the
+        // plane kernels spent ~20 us in the few threads that sit next to a wall)
+#pragma unroll
+        for (int k = 0; k < 31; k++) {
+            const int uu = fl_u[t0 + (k < n ? k : 0)];
+            r += (k < n && cmap[uu + oo] < -1) ? 1 : 0;
+        }
         return r;
     }
     // PDF of slot (q,g) at the site with U index uu (must lie in the 1-ghost box), wherever it is stored

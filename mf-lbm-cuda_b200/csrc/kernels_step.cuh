@@ -227,18 +227,25 @@ __global__ void k_inlet_velocity(const Lattice<T> L, const int ilo, const int ih
     T tmp2 = L.W_in[L.iplane(i, j)] * L.relaxation;
     const T tmp1 = tmp2 * L.sa_inject;
     tmp2 = tmp2 - tmp1;
+    // three rounds - all addresses, all loads, all stores - instead of ten dependent look-up -> load -> store chains
+    // (the cells are distinct, but behind references the compiler has to assume they alias and serialises them)
+    T* gh[10]; T* in[10]; T v[10];
 #pragma unroll
-    for (int g = 0; g < 2; g++) {
-        const T t = g == 0 ? tmp1 : tmp2;
+    for (int g = 0; g < 2; g++)
 #pragma unroll
         for (int n = 0; n < 5; n++) {
             const int q = qin(n), o = opc(q);
-            const T wgt = n == 0 ? T(1) / T(18) : T(1) / T(36);
-            T& gh = L.f(q, g, L.u(i - ex(q), j - ey(q), 0));   // ghost plane, slot q at x - e_q
-            T& in = L.f(o, g, L.u(i, j, 1));                   // first real plane, slot opc(q)
-            if (!AFTER) gh = in + lit<T>(6.0) * wgt * t;
-            else in = gh + lit<T>(6.0) * wgt * t;
+            gh[5 * g + n] = &L.f(q, g, L.u(i - ex(q), j - ey(q), 0));   // ghost plane, slot q at x - e_q
+            in[5 * g + n] = &L.f(o, g, L.u(i, j, 1));                   // first real plane, slot opc(q)
         }
+#pragma unroll
+    for (int m = 0; m < 10; m++) v[m] = AFTER ? *gh[m] : *in[m];
+#pragma unroll
+    for (int m = 0; m < 10; m++) {
+        const T t = m < 5 ? tmp1 : tmp2;
+        const T wgt = (m % 5) == 0 ? T(1) / T(18) : T(1) / T(36);
+        const T r = v[m] + lit<T>(6.0) * wgt * t;
+        if (!AFTER) *gh[m] = r; else *in[m] = r;
     }
 }
 
@@ -311,20 +318,28 @@ __global__ void k_outlet_convective(const Lattice<T> L, const int ilo, const int
     const T ph = ((L.phi_convec[cb] + u_convec * L.phi[c]) * temp) * (1 - wi) + L.phi[c + sz] * wi;
     L.phi[c + sz] = ph; L.phi_convec[cb] = ph; L.phi[c + 2 * sz] = ph; L.phi[c + 3 * sz] = ph; L.phi[c + 4 * sz] = ph;
     const int plane = L.NX1 * L.NY1;
+    // addresses, loads, stores in three rounds (see k_inlet_velocity)
+    T* dst[10]; const T* inner[10]; T* rec[10]; T a[10], b[10];
 #pragma unroll
     for (int g = 0; g < 2; g++) {
         T* buf = g == 0 ? L.f_convec : L.g_convec;
 #pragma unroll
         for (int n = 0; n < 5; n++) {
             const int o = opc(qin(n));   // unknown incoming direction at the outlet (ez = -1)
-            T* dst; const T* inner;
-            if (!AFTER) { dst = &L.f(o, g, L.u(i - ex(o), j - ey(o), nz + 1)); inner = &L.f(o, g, L.u(i - ex(o), j - ey(o), nz)); }
-            else { dst = &L.f(opc(o), g, L.u(i, j, nz)); inner = &L.f(opc(o), g, L.u(i, j, nz - 1)); }
-            if (wi) { buf[cb + plane * o] = *dst; continue; }   // solid boundary node: the blend keeps *dst and records it
-            const T val = (buf[cb + plane * o] + u_convec * *inner) * temp;
-            *dst = val;
-            buf[cb + plane * o] = val;
+            const int m = 5 * g + n;
+            if (!AFTER) { dst[m] = &L.f(o, g, L.u(i - ex(o), j - ey(o), nz + 1)); inner[m] = &L.f(o, g, L.u(i - ex(o), j - ey(o), nz)); }
+            else { dst[m] = &L.f(opc(o), g, L.u(i, j, nz)); inner[m] = &L.f(opc(o), g, L.u(i, j, nz - 1)); }
+            rec[m] = buf + (cb + plane * o);
         }
+    }
+#pragma unroll
+    for (int m = 0; m < 10; m++) { a[m] = wi ? *dst[m] : *rec[m]; b[m] = wi ? T(0) : *inner[m]; }
+#pragma unroll
+    for (int m = 0; m < 10; m++) {
+        if (wi) { *rec[m] = a[m]; continue; }   // solid boundary node: the blend keeps *dst and records it
+        const T val = (a[m] + u_convec * b[m]) * temp;
+        *dst[m] = val;
+        *rec[m] = val;
     }
 }
 
