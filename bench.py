@@ -360,6 +360,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="N > 1: halo messages through peer memory (default) or NCCL send/recv")
     ap.add_argument("--geometry", default="pack", choices=["pack", "open"], help="open = empty duct, diagnostic only (not the benchmark workload)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -145,6 +145,18 @@ typedef struct mflbm_monitor_out {
     int mflbm_##P##_halo_buffers(mflbm_##P##_solver* s, int kind, int side, REAL** send, REAL** recv, int64_t* count);   \
     int mflbm_##P##_halo_pack(mflbm_##P##_solver* s, int kind);                                                          \
     int mflbm_##P##_halo_unpack(mflbm_##P##_solver* s, int kind);                                                        \
+    /* ---- the same messages through peer memory, no NCCL on the data path.  halo_p2p_local returns my receive      */ \
+    /* buffer and my arrival flag for (kind, side); the neighbour on that side passes them (as peer pointers: same   */ \
+    /* process, or mflbm_ipc_export/import across processes) to ITS halo_p2p_connect for the opposite side.          */ \
+    /* halo_push packs straight into the neighbours' buffers and publishes a sequence number in their flags;         */ \
+    /* halo_unpack_wait spins on my flags until the pushes have landed, then unpacks.  Both are asynchronous on the  */ \
+    /* solver's stream; every rank must call them in the same order.                                                 */ \
+    int mflbm_##P##_halo_p2p_local(mflbm_##P##_solver* s, int kind, int side, REAL** recv, uint32_t** flag);             \
+    /* the single allocation all of these pointers live in (export it once, address the rest by offset) */               \
+    int mflbm_##P##_halo_p2p_region(mflbm_##P##_solver* s, void** base, int64_t* bytes);                                 \
+    int mflbm_##P##_halo_p2p_connect(mflbm_##P##_solver* s, int kind, int side, REAL* peer_recv, uint32_t* peer_flag);   \
+    int mflbm_##P##_halo_push(mflbm_##P##_solver* s, int kind);                                                          \
+    int mflbm_##P##_halo_unpack_wait(mflbm_##P##_solver* s, int kind);                                                   \
     /* split step for overlap: phase 0 = collide (+pack), phase 1 = boundary kernels (after the PDF halo landed),  */ \
     /* phase 2 = gradient chain (after the phi halo landed).  mflbm_step == phases 0,1,2 with no exchange.          */ \
     int mflbm_##P##_step_phase(mflbm_##P##_solver* s, int ntime, int phase);                                             \
@@ -159,6 +171,10 @@ typedef struct mflbm_monitor_out {
 MFLBM_DECLARE_API(f32, float)
 MFLBM_DECLARE_API(f64, double)
 
+/* CUDA IPC for the pointers of halo_p2p_local: export fills a 64-byte handle, import opens it in another process */
+int mflbm_ipc_export(void* device_ptr, void* handle64);
+int mflbm_ipc_import(const void* handle64, void** device_ptr);
+int mflbm_ipc_release(void* device_ptr);
 const char* mflbm_last_error(void);
 int mflbm_version(void);
 

@@ -385,41 +385,89 @@ __global__ void __launch_bounds__(128) k_macro(const Lattice<T> L, T* __restrict
 __host__ __device__ constexpr int slot_exp(int n) { constexpr int t[5] = {1, 7, 9, 11, 13}; return t[n]; }   // ex = +1
 __host__ __device__ constexpr int slot_exm(int n) { constexpr int t[5] = {2, 8, 10, 12, 14}; return t[n]; }  // ex = -1
 
-// copy column `col` of the ten slots (PLUS ? ex=+1 : ex=-1) between the lattice and a buffer
-template <typename T, bool PLUS, bool PACK>
-__global__ void k_halo_pdf(const Lattice<T> L, T* __restrict__ buf, const int col) {
-    const int y = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
-    if (y >= L.NY1) return;
-    const int plane = L.NY1 * L.NZ1;
-    // slot storage proper (f_raw).  Wall links that end in a neighbour-facing ghost column are not mailboxes (Solver::
-    // finish_geometry), so everything a neighbour slab reads or writes lives in slot storage and is exchanged as is; a
-    // solid site of the real boundary column can additionally be the far end of a link of THIS slab's nodes, which keep
-    // that cell in a mailbox the exchange must not touch.
-    const int uu = L.u(col, y, z);
-#pragma unroll
-    for (int g = 0; g < 2; g++) {
-#pragma unroll
-        for (int n = 0; n < 5; n++) {
-            const int q = PLUS ? slot_exp(n) : slot_exm(n);
-            T* cell = &L.f_raw(q, g, uu);
-            T* b = buf + (long long)(g * 5 + n) * plane + (y + L.NY1 * z);
-            if (PACK) *b = *cell; else *cell = *b;
+// ---- halo messages over peer memory (NVLink) --------------------------------------------------------------------
+// A slab's pack kernel can write straight into the neighbour's receive buffer (a peer pointer, cudaIpc*) instead of a
+// local send buffer that NCCL then moves: the message is one kernel, and its arrival is a sequence number in the
+// receiver's memory.  Sender: every block fences its stores system-wide and takes a ticket; the last one publishes
+// `seq` in the receiver's flag.  Receiver: the unpack kernel spins on its own flag, then reads the buffer past L1.
+// Overwriting a buffer is safe without double buffering: the next message of a kind is only packed after data that
+// depends on the receiver having unpacked the previous one has travelled back.
+// The sequence number of a (kind, side) message lives in device memory (`seq`, incremented by the push kernel): both
+// kernels take static arguments and a whole step pair including its halo messages replays from a CUDA graph.  An
+// exchange is symmetric - I push message n of a kind and then wait for the neighbour's message n of that kind - so the
+// number I wait for is the one my own push just wrote.
+struct HaloSync {
+    unsigned* flag;      // push: the peer's flag; unpack: my flag; nullptr = no synchronisation (NCCL path)
+    unsigned* counter;   // push only: block tickets (own memory, returns to 0)
+    unsigned* seq;       // my message counter for this (kind, side)
+};
+__device__ __forceinline__ void halo_publish(const HaloSync& hs) {
+    if (!hs.flag) return;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        const unsigned nblocks = gridDim.x * gridDim.y * gridDim.z;
+        if (atomicAdd(hs.counter, 1u) == nblocks - 1u) {
+            *hs.counter = 0u;
+            const unsigned n = *hs.seq + 1u;
+            *hs.seq = n;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned*>(hs.flag) = n;
         }
     }
+}
+__device__ __forceinline__ void halo_await(const HaloSync& hs) {
+    if (!hs.flag) return;
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        const unsigned want = *reinterpret_cast<volatile unsigned*>(hs.seq);
+        // sequence numbers only grow; the signed difference survives wrap-around
+        while ((int)(*reinterpret_cast<volatile unsigned*>(hs.flag) - want) < 0) __nanosleep(64);
+        __threadfence_system();
+    }
+    __syncthreads();
+}
+
+// copy column `col` of the ten slots (PLUS ? ex=+1 : ex=-1) between the lattice and a buffer
+template <typename T, bool PLUS, bool PACK>
+__global__ void k_halo_pdf(const Lattice<T> L, T* __restrict__ buf, const int col, const HaloSync hs) {
+    if (!PACK) halo_await(hs);
+    const int y = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
+    if (y < L.NY1) {
+        const int plane = L.NY1 * L.NZ1;
+        // slot storage proper (f_raw).  Wall links that end in a neighbour-facing ghost column are not mailboxes (Solver::
+        // finish_geometry), so everything a neighbour slab reads or writes lives in slot storage and is exchanged as is; a
+        // solid site of the real boundary column can additionally be the far end of a link of THIS slab's nodes, which keep
+        // that cell in a mailbox the exchange must not touch.
+        const int uu = L.u(col, y, z);
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+#pragma unroll
+            for (int n = 0; n < 5; n++) {
+                const int q = PLUS ? slot_exp(n) : slot_exm(n);
+                T* cell = &L.f_raw(q, g, uu);
+                T* b = buf + (long long)(g * 5 + n) * plane + (y + L.NY1 * z);
+                if (PACK) *b = *cell; else *cell = __ldcg(b);
+            }
+        }
+    }
+    if (PACK) halo_publish(hs);
 }
 
 // copy 4 phi columns starting at local column `col0` between the lattice and a buffer
 template <typename T, bool PACK>
-__global__ void k_halo_phi(const Lattice<T> L, T* __restrict__ buf, const int col0) {
+__global__ void k_halo_phi(const Lattice<T> L, T* __restrict__ buf, const int col0, const HaloSync hs) {
+    if (!PACK) halo_await(hs);
     const int y = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;   // 0-based over the 4-ghost extents
-    if (y >= L.PY) return;
-    const int plane = L.PY * L.PZ;
+    if (y < L.PY) {
+        const int plane = L.PY * L.PZ;
 #pragma unroll
-    for (int n = 0; n < 4; n++) {
-        T* cell = L.phi + ((col0 + n + 3) + L.PX * (y + L.PY * z));
-        T* b = buf + (long long)n * plane + (y + L.PY * z);
-        if (PACK) *b = *cell; else *cell = *b;
+        for (int n = 0; n < 4; n++) {
+            T* cell = L.phi + ((col0 + n + 3) + L.PX * (y + L.PY * z));
+            T* b = buf + (long long)n * plane + (y + L.PY * z);
+            if (PACK) *b = *cell; else *cell = __ldcg(b);
+        }
     }
+    if (PACK) halo_publish(hs);
 }
 
 }  // namespace mflbm

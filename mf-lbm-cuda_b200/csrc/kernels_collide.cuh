@@ -362,8 +362,16 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(pipe::smem_u32(bar)) : "memory");
 }
 
-template <typename T, int MRT, int NST, int CTAS>
-__global__ void __launch_bounds__(2 * COLLIDE_TILE, CTAS) k_collide_odd_ws(const Lattice<T> L, const int ntiles, const int bulk_skip) {
+// NCONS consumer warpgroups share one producer warpgroup (the producer needs about half a consumer's time per tile):
+// consumer group g takes the CTA's tiles i = g, g + NCONS, ...; stage of tile i = i % NST for everybody.  With two
+// consumer groups each scheduler holds two collision warps.  In double precision a collision warp needs ~216 registers,
+// more than 64 K / 384 threads: REGS_P / REGS_C move registers from the producer to the consumers with setmaxnreg
+// (0 = leave the allocation alone).
+template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
+template <typename T, int MRT, int NST, int CTAS, int NCONS, int REGS_P, int REGS_C>
+__global__ void __launch_bounds__((NCONS + 1) * COLLIDE_TILE, CTAS) k_collide_odd_ws(const Lattice<T> L, const int ntiles, const int bulk_skip) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     typedef OddStage<T> Stage;
     Stage* stg = reinterpret_cast<Stage*>(smem_raw);
@@ -379,13 +387,13 @@ __global__ void __launch_bounds__(2 * COLLIDE_TILE, CTAS) k_collide_odd_ws(const
     }
     __syncthreads();
 
-    if (tid >= COLLIDE_TILE) {
+    if (tid >= NCONS * COLLIDE_TILE) {
         // =========================== producer ===========================
         // The map entries, link ranks and site ids of the NEXT tile are ordinary loads into registers, issued one tile
-        // ahead (the producer has registers to spare and never calls a subroutine, so nothing waits on their scoreboards
-        // early): an LDG costs the load/store pipe 1.8 cycles against 8 for an LDGSTS, and that pipe is what bounds this
-        // kernel (232 LDGSTS + 152 scattered STG.64 + ~300 LDS per tile).
-        const int p = tid - COLLIDE_TILE, lane = p & 31, w = p >> 5;
+        // ahead (the producer never calls a subroutine, so nothing waits on their scoreboards early): an LDG costs the
+        // load/store pipe 1.8 cycles against 8 for an LDGSTS.
+        if (REGS_P > 0) reg_dealloc<REGS_P>();
+        const int p = tid - NCONS * COLLIDE_TILE, lane = p & 31, w = p >> 5;
         const T* __restrict__ p0 = L.pdf;
         const int* __restrict__ cmap = L.cmap;
         const unsigned lanes_below = (1u << lane) - 1u;
@@ -410,29 +418,30 @@ __global__ void __launch_bounds__(2 * COLLIDE_TILE, CTAS) k_collide_odd_ws(const
             load_raw(tile + stride, uNxt, cN, wbN);   // consumed in the next iteration
             if (i >= NST) pipe::mbar_wait(&empty[st], ph_empty);
             Stage& S = stg[st];
+            const int t = tile * COLLIDE_TILE + p;
+            const bool live = uCur >= 0;
+            if (live) {   // the rest populations: slot 0 / 19 at the node itself
+                pipe::cp_async<sizeof(T)>(&S.val[0][p], p0 + t);
+                pipe::cp_async<sizeof(T)>(&S.val[19][p], p0 + 19 * NC + t);
+                pipe::cp_async<sizeof(T)>(&S.cn[p], L.c_norm + uCur);
+            }
             // slot entries of the 18 neighbour cells: the map entry itself for a non-solid neighbour, the mailbox entry
-            // mb0 + rank for a wall link (core.cuh)
-            int nb[18];
+            // mb0 + rank for a wall link (core.cuh).  Neighbour j+1 is where slot opc(j+1) is pulled from: its two
+            // gathers go out as soon as the entry is known, nothing is kept.
 #pragma unroll
             for (int q = 1; q < 19; q++) {
                 const int cc = c[q - 1];
                 const unsigned walls = __ballot_sync(0xffffffffu, cc < 0);
                 const int base = __shfl_sync(0xffffffffu, wb, q - 1);
-                nb[q - 1] = cc >= 0 ? cc : L.mb0 + base + __popc(walls & lanes_below);
-                S.nb[q - 1][p] = nb[q - 1];
+                const int nbq = cc >= 0 ? cc : L.mb0 + base + __popc(walls & lanes_below);
+                S.nb[q - 1][p] = nbq;
+                if (live) {   // x - e_s = x + e_q for s = opc(q): slot s there
+                    pipe::cp_async<sizeof(T)>(&S.val[opc(q)][p], p0 + (long long)opc(q) * NC + nbq);
+                    pipe::cp_async<sizeof(T)>(&S.val[opc(q) + 19][p], p0 + (long long)(opc(q) + 19) * NC + nbq);
+                }
             }
             S.u[p] = uCur;
-            mbar_arrive(&full[st]);   // release: nb / u are visible to whoever sees the phase complete
-            if (uCur >= 0) {
-                const int t = tile * COLLIDE_TILE + p;
-#pragma unroll
-                for (int q = 0; q < 19; q++) {
-                    const int src = (q == 0) ? t : nb[opc(q) - 1];   // x - e_q = x + e_opc(q), slot q there
-                    pipe::cp_async<sizeof(T)>(&S.val[q][p], p0 + (long long)q * NC + src);
-                    pipe::cp_async<sizeof(T)>(&S.val[q + 19][p], p0 + (long long)(q + 19) * NC + src);
-                }
-                pipe::cp_async<sizeof(T)>(&S.cn[p], L.c_norm + uCur);
-            }
+            mbar_arrive(&full[st]);                  // release: nb / u are visible to whoever sees the phase complete
             cp_async_mbar_arrive_noinc(&full[st]);   // fires when every cp.async above has landed
             uCur = uNxt; uNxt = uNxt2;
             if (++st == NST) { st = 0; if (i >= NST) ph_empty ^= 1; }
@@ -442,22 +451,25 @@ __global__ void __launch_bounds__(2 * COLLIDE_TILE, CTAS) k_collide_odd_ws(const
         return;
     }
 
-    // =========================== consumer ===========================
-    int st = 0;
-    uint32_t ph_full = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += stride) {
+    // =========================== consumers ===========================
+    if (REGS_C > 0) reg_alloc<REGS_C>();
+    const int cg = tid / COLLIDE_TILE, ct = tid - cg * COLLIDE_TILE;   // consumer group, entry within the tile
+    for (int i = cg; ; i += NCONS) {
+        const int tile = blockIdx.x + i * stride;
+        if (tile >= ntiles) break;
+        const int st = i % NST;
         Stage& S = stg[st];
-        pipe::mbar_wait(&full[st], ph_full);
-        const int t = tile * COLLIDE_TILE + tid;
-        const int u = S.u[tid];
+        pipe::mbar_wait(&full[st], (uint32_t)((i / NST) & 1));
+        const int t = tile * COLLIDE_TILE + ct;
+        const int u = S.u[ct];
         const bool live = u >= 0;
         if (live) {
-            const T cnorm = S.cn[tid];
+            const T cnorm = S.cn[ct];
             T cnx, cny, cnz, tmp;
             node_force(L, u, cnorm, bulk_skip != 0, cnx, cny, cnz, tmp);
             T g1[19], g2[19];
 #pragma unroll
-            for (int q = 0; q < 19; q++) { g1[q] = S.val[q][tid]; g2[q] = S.val[q + 19][tid]; }
+            for (int q = 0; q < 19; q++) { g1[q] = S.val[q][ct]; g2[q] = S.val[q + 19][ct]; }
             const T phi_loc = collide_node<T, MRT>(L, g1, g2, cnx, cny, cnz, tmp);
             L.phi[u] = phi_loc;
             T* __restrict__ po = L.pdf;
@@ -465,15 +477,14 @@ __global__ void __launch_bounds__(2 * COLLIDE_TILE, CTAS) k_collide_odd_ws(const
             po[19 * NC + t] = g2[0];
 #pragma unroll
             for (int q = 1; q < 19; q++) {
-                const int dst = S.nb[q - 1][tid];
+                const int dst = S.nb[q - 1][ct];
                 po[(long long)opc(q) * NC + dst] = g1[q];
                 po[(long long)(opc(q) + 19) * NC + dst] = g2[q];
             }
         }
         // every value and every entry of the stage has been consumed by an issued store (see the even kernel)
         __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&empty[st]);
-        if (++st == NST) { st = 0; ph_full ^= 1; }
+        if ((ct & 31) == 0) mbar_arrive(&empty[st]);
     }
 }
 

@@ -81,6 +81,13 @@ struct Solver {
     // halo buffers: [kind 0..2][side 0..1]
     T* d_send[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
     T* d_recv[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    // halo messages through peer memory (kernels_aux.cuh): my incoming flags [kind*2+side], block tickets [8 + ...] and
+    // message counters [16 + ...]; the neighbours' receive buffers / flags as peer pointers
+    unsigned char* d_p2p = nullptr;
+    size_t p2p_bytes = 0;
+    unsigned* d_flags = nullptr;
+    T* peer_recv[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    unsigned* peer_flag[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
     // CUDA graph of one (odd, even) or (even, odd) step pair
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
     long long pair_launches = 0;
@@ -146,12 +153,22 @@ struct Solver {
         zalloc((void**)&d_mon, sizeof(double) * MFLBM_MON_N * L.nz);
         MF_CUDA(cudaMallocHost((void**)&h_mon, sizeof(double) * MFLBM_MON_N * L.nz));
         if (is_slab) {
+            // everything a neighbour may write - arrival flags and the six receive buffers - is ONE allocation, so that a
+            // single CUDA IPC handle plus offsets describes it (small cudaMalloc blocks are sub-allocated and cannot be
+            // exported one by one)
             const long long npdf = 10LL * L.NY1 * L.NZ1, nphi = 4LL * L.PY * L.PZ;
+            auto up256 = [](size_t b) { return (b + 255) / 256 * 256; };
+            size_t off = 256, offs[3][2];
+            for (int kind = 0; kind < 3; kind++)
+                for (int side = 0; side < 2; side++) { offs[kind][side] = off; off += up256(sizeof(T) * (size_t)(kind == 2 ? nphi : npdf)); }
+            p2p_bytes = std::max<size_t>(off, 4u << 20);
+            static_assert(16 + 6 <= 64, "flag block");
+            zalloc((void**)&d_p2p, p2p_bytes);
+            d_flags = reinterpret_cast<unsigned*>(d_p2p);
             for (int kind = 0; kind < 3; kind++)
                 for (int side = 0; side < 2; side++) {
-                    const long long n = kind == 2 ? nphi : npdf;
-                    zalloc((void**)&d_send[kind][side], sizeof(T) * n);
-                    zalloc((void**)&d_recv[kind][side], sizeof(T) * n);
+                    d_recv[kind][side] = reinterpret_cast<T*>(d_p2p + offs[kind][side]);
+                    zalloc((void**)&d_send[kind][side], sizeof(T) * (kind == 2 ? nphi : npdf));
                 }
         }
         L.pdf = d_pdf; L.phi = d_phi; L.cn_x = d_cnx; L.cn_y = d_cny; L.cn_z = d_cnz; L.c_norm = d_cnorm;
@@ -171,9 +188,9 @@ struct Solver {
         dfree(d_list_phi); dfree(d_mask_phi); dfree(d_list_cn); dfree(d_mask_cn); dfree(d_list_alter); dfree(d_list_n);
         for (auto& q : d_sn) dfree(q);
         dfree(d_live_n); dfree(d_live_cn); dfree(d_live_u); dfree(d_near);
-        dfree(d_mon); dfree(d_phi_old);
+        dfree(d_mon); dfree(d_phi_old); dfree(d_p2p); d_flags = nullptr;
         if (d_stage) { cudaFree(d_stage); d_stage = nullptr; }
-        for (int kind = 0; kind < 3; kind++) for (int side = 0; side < 2; side++) { dfree(d_send[kind][side]); dfree(d_recv[kind][side]); }
+        for (int kind = 0; kind < 3; kind++) for (int side = 0; side < 2; side++) { dfree(d_send[kind][side]); d_recv[kind][side] = nullptr; }
         if (h_mon) { cudaFreeHost(h_mon); h_mon = nullptr; }
         if (own_stream && stream) cudaStreamDestroy(stream);
         stream = nullptr;
@@ -552,14 +569,14 @@ struct Solver {
         if (configured != device) { MF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = device; }
         kern<<<collide_grid(ntiles, CTAS), COLLIDE_TILE, smem, stream>>>(L, ntiles, cn_consistent ? 1 : 0);
     }
-    template <int MRT, int NST, int CTAS>
+    template <int MRT, int NST, int CTAS, int NCONS = 1, int REGS_P = 0, int REGS_C = 0>
     void launch_odd_ws() {
         const int ntiles = ceil_div((int)n_fluid, COLLIDE_TILE);
-        auto kern = k_collide_odd_ws<T, MRT, NST, CTAS>;
+        auto kern = k_collide_odd_ws<T, MRT, NST, CTAS, NCONS, REGS_P, REGS_C>;
         constexpr size_t smem = collide_odd_ws_smem<T, NST>();
         static thread_local int configured = -1;
         if (configured != device) { MF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = device; }
-        kern<<<collide_grid(ntiles, CTAS), 2 * COLLIDE_TILE, smem, stream>>>(L, ntiles, cn_consistent ? 1 : 0);
+        kern<<<collide_grid(ntiles, CTAS), (NCONS + 1) * COLLIDE_TILE, smem, stream>>>(L, ntiles, cn_consistent ? 1 : 0);
     }
     // Stage counts are sized for the 227 KB of shared memory of an SM.  MFLBM_VARIANT = 100*e + o
     // selects other (even, odd) configurations for tuning runs, for the shipped MRT model only.
@@ -578,6 +595,10 @@ struct Solver {
                     if (o == 4) { launch_odd<MRT, 2, 1>(); goto done; }
                     if (o == 5) { launch_odd_ws<MRT, 2, 1>(); goto done; }
                     if (o == 6) { launch_odd_ws<MRT, 4, 1>(); goto done; }
+                    if (o == 7) { launch_odd_ws<MRT, 4, 1, 2, 72, 216>(); goto done; }
+                    if (o == 8) { launch_odd_ws<MRT, 4, 1, 2, 56, 224>(); goto done; }
+                    if (o == 9) { launch_odd_ws<MRT, 4, 1, 2, 40, 232>(); goto done; }
+                    if (o == 10) { launch_odd_ws<MRT, 4, 1, 2>(); goto done; }
                 }
                 launch_odd_ws<MRT, 3, 1>();   // measured best on the 256^3 pack (profiles/README.md)
             } else {
@@ -601,6 +622,9 @@ struct Solver {
                     if (o == 7) { launch_odd_ws<MRT, 6, 1>(); goto done; }
                     if (o == 8) { launch_odd_ws<MRT, 2, 2>(); goto done; }
                     if (o == 9) { launch_odd_ws<MRT, 3, 2>(); goto done; }
+                    if (o == 10) { launch_odd_ws<MRT, 4, 1, 2>(); goto done; }
+                    if (o == 11) { launch_odd_ws<MRT, 6, 1, 2>(); goto done; }
+                    if (o == 12) { launch_odd_ws<MRT, 6, 1, 3>(); goto done; }
                 }
                 launch_odd_ws<MRT, 4, 1>();
             } else {
@@ -671,14 +695,21 @@ struct Solver {
         else MF_FAIL("bad phase");
     }
 
-    void step(int ntime) { step_phase(ntime, 0); step_phase(ntime, 1); step_phase(ntime, 2); }
+    void step(int ntime) {
+        if (is_slab && (slab.has_left || slab.has_right)) {
+            if (!p2p_ready()) MF_FAIL("a slab with neighbours steps through step_phase + halo exchange, or through step/run once halo_p2p_connect has been called for every neighbour");
+            step_p2p(ntime);
+            return;
+        }
+        step_phase(ntime, 0); step_phase(ntime, 1); step_phase(ntime, 2);
+    }
 
     // nsteps consecutive steps; pairs of steps are replayed from a captured CUDA graph (launch-bound small lattices)
     void run(int ntime_first, int nsteps) {
         if (nsteps <= 0) return;
         if (!have_geometry) MF_FAIL("step before geometry");
         int nt = ntime_first, left = nsteps;
-        if (left >= 4 && !is_slab) {
+        if (left >= 4) {
             const int par = nt & 1;
             if (!graph_exec[par]) {
                 const long long l0 = launches;
@@ -774,40 +805,82 @@ struct Solver {
     // halo exchange (x slabs)
     long long halo_count(int kind) const { return kind == 2 ? 4LL * L.PY * L.PZ : 10LL * L.NY1 * L.NZ1; }
 
-    void halo_pack(int kind) {
+    // pack the outgoing columns of message `kind`.  push = false: into my send buffers (the caller moves them, e.g. NCCL);
+    // push = true: straight into the neighbours' receive buffers over NVLink, arrival published in their flags
+    void halo_pack(int kind, bool push = false) {
         if (!is_slab) MF_FAIL("halo_pack on a non-slab solver");
         if (!have_geometry) MF_FAIL("halo_pack before geometry");
+        if (kind < 0 || kind > 2) MF_FAIL("bad halo kind");
         const int bt = 128;
         const dim3 g1(ceil_div(L.NY1, bt), L.NZ1), g4(ceil_div(L.PY, bt), L.PZ);
+        auto dst = [&](int side) -> T* {
+            if (!push) return d_send[kind][side];
+            if (!peer_recv[kind][side] || !peer_flag[kind][side]) MF_FAIL("halo_push: neighbour %d of message kind %d is not connected", side, kind);
+            return peer_recv[kind][side];
+        };
+        auto sync = [&](int side) -> HaloSync {
+            if (!push) return HaloSync{nullptr, nullptr, nullptr};
+            return HaloSync{peer_flag[kind][side], d_flags + 8 + kind * 2 + side, d_flags + 16 + kind * 2 + side};
+        };
         if (kind == 0) {   // after an even step: real boundary columns -> neighbour ghost columns
-            if (slab.has_left) { k_halo_pdf<T, false, true><<<g1, bt, 0, stream>>>(L, d_send[0][0], 1); count(); }          // ex=-1 slots of column 1
-            if (slab.has_right) { k_halo_pdf<T, true, true><<<g1, bt, 0, stream>>>(L, d_send[0][1], L.nx); count(); }       // ex=+1 slots of column nx
+            if (slab.has_left) { k_halo_pdf<T, false, true><<<g1, bt, 0, stream>>>(L, dst(0), 1, sync(0)); count(); }          // ex=-1 slots of column 1
+            if (slab.has_right) { k_halo_pdf<T, true, true><<<g1, bt, 0, stream>>>(L, dst(1), L.nx, sync(1)); count(); }       // ex=+1 slots of column nx
         } else if (kind == 1) {   // after an odd step: what was pushed into my ghost columns -> neighbour real columns
-            if (slab.has_left) { k_halo_pdf<T, true, true><<<g1, bt, 0, stream>>>(L, d_send[1][0], 0); count(); }           // ex=+1 slots of ghost column 0
-            if (slab.has_right) { k_halo_pdf<T, false, true><<<g1, bt, 0, stream>>>(L, d_send[1][1], L.nx + 1); count(); }  // ex=-1 slots of ghost column nx+1
-        } else if (kind == 2) {
-            if (slab.has_left) { k_halo_phi<T, true><<<g4, bt, 0, stream>>>(L, d_send[2][0], 1); count(); }
-            if (slab.has_right) { k_halo_phi<T, true><<<g4, bt, 0, stream>>>(L, d_send[2][1], L.nx - 3); count(); }
-        } else MF_FAIL("bad halo kind");
+            if (slab.has_left) { k_halo_pdf<T, true, true><<<g1, bt, 0, stream>>>(L, dst(0), 0, sync(0)); count(); }           // ex=+1 slots of ghost column 0
+            if (slab.has_right) { k_halo_pdf<T, false, true><<<g1, bt, 0, stream>>>(L, dst(1), L.nx + 1, sync(1)); count(); }  // ex=-1 slots of ghost column nx+1
+        } else {
+            if (slab.has_left) { k_halo_phi<T, true><<<g4, bt, 0, stream>>>(L, dst(0), 1, sync(0)); count(); }
+            if (slab.has_right) { k_halo_phi<T, true><<<g4, bt, 0, stream>>>(L, dst(1), L.nx - 3, sync(1)); count(); }
+        }
         check_launch();
     }
 
-    void halo_unpack(int kind) {
+    // unpack message `kind` from my receive buffers; wait = true: spin on my flags until the neighbours' pushes have landed
+    void halo_unpack(int kind, bool wait = false) {
         if (!is_slab) MF_FAIL("halo_unpack on a non-slab solver");
         if (!have_geometry) MF_FAIL("halo_unpack before geometry");
+        if (kind < 0 || kind > 2) MF_FAIL("bad halo kind");
         const int bt = 128;
         const dim3 g1(ceil_div(L.NY1, bt), L.NZ1), g4(ceil_div(L.PY, bt), L.PZ);
+        auto sync = [&](int side) -> HaloSync {
+            if (!wait) return HaloSync{nullptr, nullptr, nullptr};
+            return HaloSync{d_flags + kind * 2 + side, nullptr, d_flags + 16 + kind * 2 + side};
+        };
         if (kind == 0) {   // neighbour's real boundary column -> my ghost column
-            if (slab.has_left) { k_halo_pdf<T, true, false><<<g1, bt, 0, stream>>>(L, d_recv[0][0], 0); count(); }          // left's column nx (ex=+1) -> ghost 0
-            if (slab.has_right) { k_halo_pdf<T, false, false><<<g1, bt, 0, stream>>>(L, d_recv[0][1], L.nx + 1); count(); } // right's column 1 (ex=-1) -> ghost nx+1
+            if (slab.has_left) { k_halo_pdf<T, true, false><<<g1, bt, 0, stream>>>(L, d_recv[0][0], 0, sync(0)); count(); }          // left's column nx (ex=+1) -> ghost 0
+            if (slab.has_right) { k_halo_pdf<T, false, false><<<g1, bt, 0, stream>>>(L, d_recv[0][1], L.nx + 1, sync(1)); count(); } // right's column 1 (ex=-1) -> ghost nx+1
         } else if (kind == 1) {   // neighbour's ghost column -> my real boundary column
-            if (slab.has_left) { k_halo_pdf<T, false, false><<<g1, bt, 0, stream>>>(L, d_recv[1][0], 1); count(); }         // left's ghost nx+1 (ex=-1) -> column 1
-            if (slab.has_right) { k_halo_pdf<T, true, false><<<g1, bt, 0, stream>>>(L, d_recv[1][1], L.nx); count(); }      // right's ghost 0 (ex=+1) -> column nx
-        } else if (kind == 2) {
-            if (slab.has_left) { k_halo_phi<T, false><<<g4, bt, 0, stream>>>(L, d_recv[2][0], -3); count(); }
-            if (slab.has_right) { k_halo_phi<T, false><<<g4, bt, 0, stream>>>(L, d_recv[2][1], L.nx + 1); count(); }
-        } else MF_FAIL("bad halo kind");
+            if (slab.has_left) { k_halo_pdf<T, false, false><<<g1, bt, 0, stream>>>(L, d_recv[1][0], 1, sync(0)); count(); }         // left's ghost nx+1 (ex=-1) -> column 1
+            if (slab.has_right) { k_halo_pdf<T, true, false><<<g1, bt, 0, stream>>>(L, d_recv[1][1], L.nx, sync(1)); count(); }      // right's ghost 0 (ex=+1) -> column nx
+        } else {
+            if (slab.has_left) { k_halo_phi<T, false><<<g4, bt, 0, stream>>>(L, d_recv[2][0], -3, sync(0)); count(); }
+            if (slab.has_right) { k_halo_phi<T, false><<<g4, bt, 0, stream>>>(L, d_recv[2][1], L.nx + 1, sync(1)); count(); }
+        }
         check_launch();
+    }
+
+    void halo_connect(int kind, int side, T* recv_of_peer, unsigned* flag_of_peer) {
+        if (!is_slab) MF_FAIL("halo_connect on a non-slab solver");
+        if (kind < 0 || kind > 2 || side < 0 || side > 1) MF_FAIL("halo_connect: bad kind/side");
+        peer_recv[kind][side] = recv_of_peer;
+        peer_flag[kind][side] = flag_of_peer;
+        drop_graphs();
+    }
+    bool p2p_ready() const {
+        for (int kind = 0; kind < 3; kind++) {
+            if (slab.has_left && !(peer_recv[kind][0] && peer_flag[kind][0])) return false;
+            if (slab.has_right && !(peer_recv[kind][1] && peer_flag[kind][1])) return false;
+        }
+        return true;
+    }
+    // one step of a slab with its two halo messages through peer memory (the sequence of mflbm/slab.py SlabStepper.step)
+    void step_p2p(int ntime) {
+        step_phase(ntime, 0);
+        const int kind = (ntime % 2) ? 1 : 0;
+        halo_pack(kind, true); halo_unpack(kind, true);
+        step_phase(ntime, 1);
+        halo_pack(2, true); halo_unpack(2, true);
+        step_phase(ntime, 2);
     }
 
     void* device_ptr(const char* name) {
@@ -900,6 +973,28 @@ using namespace mflbm;
     }                                                                                                                                     \
     extern "C" int mflbm_##P##_halo_pack(mflbm_##P##_solver* s, int kind) { MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->halo_pack(kind); }) } \
     extern "C" int mflbm_##P##_halo_unpack(mflbm_##P##_solver* s, int kind) { MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->halo_unpack(kind); }) } \
+    extern "C" int mflbm_##P##_halo_p2p_local(mflbm_##P##_solver* s, int kind, int side, REAL** recv, uint32_t** flag) {                  \
+        MF_GUARD({                                                                                                                        \
+            MF_NEED(s);                                                                                                                   \
+            if (kind < 0 || kind > 2 || side < 0 || side > 1) throw Error{"halo_p2p_local: bad kind/side"};                               \
+            if (!MF_SOLVER(P, REAL)->is_slab) throw Error{"halo_p2p_local on a non-slab solver"};                                         \
+            if (recv) *recv = MF_SOLVER(P, REAL)->d_recv[kind][side];                                                                     \
+            if (flag) *flag = MF_SOLVER(P, REAL)->d_flags + kind * 2 + side;                                                              \
+        })                                                                                                                                \
+    }                                                                                                                                     \
+    extern "C" int mflbm_##P##_halo_p2p_region(mflbm_##P##_solver* s, void** base, int64_t* bytes) {                                      \
+        MF_GUARD({                                                                                                                        \
+            MF_NEED(s);                                                                                                                   \
+            if (!MF_SOLVER(P, REAL)->is_slab) throw Error{"halo_p2p_region on a non-slab solver"};                                        \
+            if (base) *base = MF_SOLVER(P, REAL)->d_p2p;                                                                                  \
+            if (bytes) *bytes = (int64_t)MF_SOLVER(P, REAL)->p2p_bytes;                                                                   \
+        })                                                                                                                                \
+    }                                                                                                                                     \
+    extern "C" int mflbm_##P##_halo_p2p_connect(mflbm_##P##_solver* s, int kind, int side, REAL* peer_recv, uint32_t* peer_flag) {        \
+        MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->halo_connect(kind, side, peer_recv, peer_flag); })                                     \
+    }                                                                                                                                     \
+    extern "C" int mflbm_##P##_halo_push(mflbm_##P##_solver* s, int kind) { MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->halo_pack(kind, true); }) } \
+    extern "C" int mflbm_##P##_halo_unpack_wait(mflbm_##P##_solver* s, int kind) { MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->halo_unpack(kind, true); }) } \
     extern "C" int mflbm_##P##_step_phase(mflbm_##P##_solver* s, int ntime, int phase) {                                                  \
         MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->step_phase(ntime, phase); })                                                           \
     }                                                                                                                                     \
@@ -912,6 +1007,26 @@ using namespace mflbm;
 
 MFLBM_DEFINE_API(f32, float)
 MFLBM_DEFINE_API(f64, double)
+
+// CUDA IPC helpers so that a caller in another process can reach the buffers returned by halo_p2p_local
+extern "C" int mflbm_ipc_export(void* device_ptr, void* handle64) {
+    MF_GUARD({
+        if (!device_ptr || !handle64) throw Error{"ipc_export: null argument"};
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+        cudaIpcMemHandle_t h;
+        MF_CUDA(cudaIpcGetMemHandle(&h, device_ptr));
+        memcpy(handle64, &h, 64);
+    })
+}
+extern "C" int mflbm_ipc_import(const void* handle64, void** device_ptr) {
+    MF_GUARD({
+        if (!device_ptr || !handle64) throw Error{"ipc_import: null argument"};
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle64, 64);
+        MF_CUDA(cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    })
+}
+extern "C" int mflbm_ipc_release(void* device_ptr) { MF_GUARD({ if (device_ptr) MF_CUDA(cudaIpcCloseMemHandle(device_ptr)); }) }
 
 extern "C" const char* mflbm_last_error(void) { return g_last_error.c_str(); }
 extern "C" int mflbm_version(void) { return MFLBM_VERSION; }

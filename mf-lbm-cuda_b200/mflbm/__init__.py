@@ -107,6 +107,11 @@ def load_library() -> C.CDLL:
             "halo_buffers": [vp, i32, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)],
             "halo_pack": [vp, i32],
             "halo_unpack": [vp, i32],
+            "halo_p2p_local": [vp, i32, i32, C.POINTER(vp), C.POINTER(vp)],
+            "halo_p2p_region": [vp, C.POINTER(vp), C.POINTER(i64)],
+            "halo_p2p_connect": [vp, i32, i32, vp, vp],
+            "halo_push": [vp, i32],
+            "halo_unpack_wait": [vp, i32],
             "step_phase": [vp, i32, i32],
         }
         for name, argtypes in sig.items():
@@ -121,13 +126,17 @@ def load_library() -> C.CDLL:
         getattr(lib, f"mflbm_{p}_stream").restype = vp
         getattr(lib, f"mflbm_{p}_device_ptr").argtypes = [vp, C.c_char_p]
         getattr(lib, f"mflbm_{p}_device_ptr").restype = vp
+    for name, argtypes in (("mflbm_ipc_export", [vp, vp]), ("mflbm_ipc_import", [vp, C.POINTER(vp)]), ("mflbm_ipc_release", [vp])):
+        getattr(lib, name).argtypes = argtypes
+        getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib
 
 
 EXPORTED = ["create", "destroy", "set_params", "upload_geometry", "preprocess_geometry", "download_geometry", "upload_state",
             "init_state", "download_state", "step", "run", "color_gradient", "monitor", "sync", "phi_change", "download_macro", "halo_buffers", "halo_pack",
-            "halo_unpack", "step_phase", "num_fluid_nodes", "kernel_launches", "stream", "device_ptr"]
+            "halo_unpack", "halo_p2p_local", "halo_p2p_region", "halo_p2p_connect", "halo_push", "halo_unpack_wait", "step_phase",
+            "num_fluid_nodes", "kernel_launches", "stream", "device_ptr"]
 
 
 class MflbmError(RuntimeError):
@@ -349,6 +358,28 @@ class Solver:
     def halo_unpack(self, kind: int):
         self._check(self._fn("halo_unpack")(self.h, kind))
 
+    # -- halo messages through peer memory -------------------------------------------------------------
+    def halo_p2p_local(self, kind: int, side: int):
+        """-> (device address of my receive buffer, device address of my arrival flag) for message `kind` from `side`"""
+        recv, flag = C.c_void_p(), C.c_void_p()
+        self._check(self._fn("halo_p2p_local")(self.h, kind, side, C.byref(recv), C.byref(flag)))
+        return recv.value, flag.value
+
+    def halo_p2p_region(self):
+        """-> (base address, bytes) of the single allocation that holds every pointer of halo_p2p_local"""
+        base, n = C.c_void_p(), C.c_int64()
+        self._check(self._fn("halo_p2p_region")(self.h, C.byref(base), C.byref(n)))
+        return base.value, n.value
+
+    def halo_p2p_connect(self, kind: int, side: int, peer_recv: int, peer_flag: int):
+        self._check(self._fn("halo_p2p_connect")(self.h, kind, side, C.c_void_p(peer_recv), C.c_void_p(peer_flag)))
+
+    def halo_push(self, kind: int):
+        self._check(self._fn("halo_push")(self.h, kind))
+
+    def halo_unpack_wait(self, kind: int):
+        self._check(self._fn("halo_unpack_wait")(self.h, kind))
+
     # -- bookkeeping ---------------------------------------------------------------------------------
     @property
     def num_fluid_nodes(self) -> int:
@@ -364,3 +395,20 @@ class Solver:
 
     def device_ptr(self, name: str) -> int:
         return int(self._fn("device_ptr")(self.h, name.encode()) or 0)
+
+
+def ipc_export(device_ptr: int) -> bytes:
+    """64-byte CUDA IPC handle of the allocation that starts at device_ptr"""
+    lib = load_library()
+    buf = C.create_string_buffer(64)
+    if lib.mflbm_ipc_export(C.c_void_p(device_ptr), buf) != 0:
+        raise MflbmError(lib.mflbm_last_error().decode())
+    return buf.raw
+
+
+def ipc_import(handle: bytes) -> int:
+    lib = load_library()
+    out = C.c_void_p()
+    if lib.mflbm_ipc_import(C.create_string_buffer(handle, 64), C.byref(out)) != 0:
+        raise MflbmError(lib.mflbm_last_error().decode())
+    return out.value

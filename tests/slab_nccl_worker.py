@@ -25,7 +25,8 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    for name, prec, nsteps in (("pack_velocity", "f64", 20), ("tube_pressure", "f32", 21), ("periodic_drop", "f64", 10)):
+    for name, prec, nsteps, halo in (("pack_velocity", "f64", 20, "nccl"), ("tube_pressure", "f32", 21, "nccl"), ("periodic_drop", "f64", 10, "nccl"),
+                                     ("pack_velocity", "f64", 20, "p2p"), ("tube_pressure", "f32", 21, "p2p"), ("periodic_drop", "f32", 10, "p2p")):
         o, ctl, solid = common.make_oracle(name, prec)
         P = mflbm.derive_params(ctl, prec)
         interior = (o.arr("walls_global") != 0).astype(np.int8)
@@ -36,6 +37,8 @@ def main():
             cs = slab.CudaSlab(P, prec, rng, local, stream=stream)
             cs.solver.preprocess_geometry(interior)
             cs.solver.init_state(opt, z0, W_in=np.ascontiguousarray(W[:, rng.x0 - 1:rng.x1 + 2]))
+            if halo == "p2p":   # CUDA IPC handles of the receive buffers / arrival flags, halo messages over NVLink stores
+                cs.connect_p2p(dist)
             st = slab.SlabStepper(cs, rng)
             st.run(1, nsteps)
             st.settle()
@@ -54,7 +57,7 @@ def main():
                 got = np.concatenate([p[k] for p in parts], axis=-1)
                 if got.shape != want[k].shape or not np.array_equal(got, want[k]):
                     ok = False
-                    print(f"MISMATCH {name} {prec} {k}", flush=True)
+                    print(f"MISMATCH {name} {prec} {halo} {k}", flush=True)
             if mon is not None:
                 m = ref.monitor()
                 for k in ("saturation", "saturation_full_domain", "ca"):

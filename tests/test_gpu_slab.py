@@ -21,11 +21,25 @@ REPO = Path(__file__).resolve().parent.parent
 class LocalChain:
     """all slabs in one process: exchange = pack everywhere, copy send -> neighbour's recv, unpack everywhere"""
 
-    def __init__(self, slabs):
-        self.slabs = slabs
+    def __init__(self, slabs, p2p=False):
+        from mflbm.slab import LEFT, RIGHT
+        self.slabs, self.p2p = slabs, p2p
+        if p2p:   # same process, same device: the neighbours' buffers and flags are ordinary device pointers
+            for r, s in enumerate(slabs):
+                for kind in (0, 1, 2):
+                    if s.rng.has_left:
+                        s.solver.halo_p2p_connect(kind, LEFT, *slabs[r - 1].solver.halo_p2p_local(kind, RIGHT))
+                    if s.rng.has_right:
+                        s.solver.halo_p2p_connect(kind, RIGHT, *slabs[r + 1].solver.halo_p2p_local(kind, LEFT))
 
     def exchange(self, kind):
         from mflbm.slab import LEFT, RIGHT
+        if self.p2p:   # every push is enqueued before the first unpack spins on its flag (one stream here)
+            for s in self.slabs:
+                s.solver.halo_push(kind)
+            for s in self.slabs:
+                s.solver.halo_unpack_wait(kind)
+            return
         for s in self.slabs:
             s.halo_pack(kind)
         for r, s in enumerate(self.slabs):
@@ -59,14 +73,17 @@ def owned(st, rng, nx_global):
     return out
 
 
-@pytest.mark.parametrize("name,prec,world,nsteps", [
-    ("tube_pressure", "f64", 2, 12),
-    ("pack_velocity", "f64", 3, 12),
-    ("periodic_drop", "f64", 2, 11),
-    ("imbibition_plate2", "f32", 2, 12),
-    ("rect_quirk", "f32", 4, 7),
+@pytest.mark.parametrize("name,prec,world,nsteps,p2p", [
+    ("tube_pressure", "f64", 2, 12, False),
+    ("pack_velocity", "f64", 3, 12, False),
+    ("periodic_drop", "f64", 2, 11, False),
+    ("imbibition_plate2", "f32", 2, 12, False),
+    ("rect_quirk", "f32", 4, 7, False),
+    ("pack_velocity", "f64", 3, 12, True),     # halo messages pushed into the neighbour's buffers, arrival flags
+    ("periodic_drop", "f32", 2, 11, True),
+    ("rect_quirk", "f64", 4, 8, True),
 ])
-def test_cuda_slabs_on_one_gpu_equal_single_domain(gpu_lib, name, prec, world, nsteps):
+def test_cuda_slabs_on_one_gpu_equal_single_domain(gpu_lib, name, prec, world, nsteps, p2p):
     import torch
     import mflbm
     from mflbm import slab
@@ -91,7 +108,7 @@ def test_cuda_slabs_on_one_gpu_equal_single_domain(gpu_lib, name, prec, world, n
             cs.solver.init_state(opt, z0, W_in=np.ascontiguousarray(W[:, rng.x0 - 1:rng.x1 + 2]))
             slabs.append(cs)
         assert sum(s.solver.num_fluid_nodes for s in slabs) == ref.num_fluid_nodes
-        chain = LocalChain(slabs)
+        chain = LocalChain(slabs, p2p=p2p)
         for n in range(nsteps):
             chain.step(1 + n)
         if nsteps % 2 == 0:
