@@ -353,8 +353,8 @@ def run_reference(args) -> dict:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=2000, help="timed steps (BASELINE configs 2/3: 2 k timed steps after 100 warm-up)")
+    ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--prec", default="f64", choices=["f64", "f32"])
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

@@ -117,6 +117,10 @@ typedef struct mflbm_monitor_out {
     /* src/Phase_gradient.cpp:15).  W_in (inlet_BC == 1) still comes from the host, it needs libm.                  */ \
     int mflbm_##P##_init_state(mflbm_##P##_solver* s, int initial_fluid_distribution_option, REAL interface_z0,          \
                                const REAL* W_in);                                                                        \
+    /* the same from a caller-supplied phase field (4-ghost layout): equilibrium PDFs at rest from phi                */ \
+    /* (initialization_new_multi_pdf, src/Init_multiphase.cpp:393-496) + colour gradient.  For option 6, whose phi is  */ \
+    /* drawn with rand() on the host (:345-351).                                                                       */ \
+    int mflbm_##P##_init_state_from_phi(mflbm_##P##_solver* s, const REAL* phi, const REAL* W_in);                       \
     /* the implicit post-condition of main_iteration_kernel_GPU on timer steps (:2059-2076); NULL skips an array.  */ \
     int mflbm_##P##_download_state(mflbm_##P##_solver* s, REAL* pdf, REAL* phi, REAL* cn_x, REAL* cn_y, REAL* cn_z,      \
                                    REAL* c_norm, REAL* curv, REAL* f_convec, REAL* g_convec, REAL* phi_convec);          \

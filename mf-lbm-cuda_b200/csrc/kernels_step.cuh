@@ -81,7 +81,7 @@ __device__ __forceinline__ void raise_near(const Lattice<T>& L, unsigned char* _
 }
 
 template <typename T>
-__global__ void __launch_bounds__(128) k_normals(const Lattice<T> L, const int* __restrict__ list, unsigned char* __restrict__ live, unsigned char* __restrict__ near, const int count) {
+__global__ void __launch_bounds__(128, 16) k_normals(const Lattice<T> L, const int* __restrict__ list, unsigned char* __restrict__ live, unsigned char* __restrict__ near, const int count) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
     const int u = list[t];

@@ -493,15 +493,18 @@ struct Solver {
 
     bool open_z() const { return P.kper == 0 && P.wall_z_min == 0 && P.wall_z_max == 0; }
 
-    void init_state(int option, T interface_z0, const T* Win) {
+    // phi_s4 != nullptr: the caller's phase field (4-ghost layout, e.g. the rand()-drawn distribution of option 6 with the
+    // inlet ghost planes already filled, src/Init_multiphase.cpp:345-372) instead of one of the device patterns
+    void init_state(int option, T interface_z0, const T* Win, const T* phi_s4 = nullptr) {
         if (!have_geometry) MF_FAIL("init_state before geometry");
-        if (option < 1 || option > 5) MF_FAIL("initial_fluid_distribution_option %d not supported on the device (1..5)", option);
+        if (!phi_s4 && (option < 1 || option > 5)) MF_FAIL("initial_fluid_distribution_option %d not supported on the device (1..5)", option);
         const int bx = 128;
         MF_CUDA(cudaMemsetAsync(d_phi, 0, sizeof(T) * PN, stream));
-        k_init_phi<T><<<grid_box(4, bx), bx, 0, stream>>>(L, option, interface_z0, (int)P.ny, (int)P.nz, open_z() ? 1 : 0);
+        if (phi_s4) { to_u<T>(phi_s4, d_phi, 4, N4); drop_stage(); }
+        else { k_init_phi<T><<<grid_box(4, bx), bx, 0, stream>>>(L, option, interface_z0, (int)P.ny, (int)P.nz, open_z() ? 1 : 0); count(); }
         check_launch();
         k_init_pdf<T><<<grid_box(1, bx), bx, 0, stream>>>(L, P.outlet_BC == 1 ? 1 : 0); check_launch();
-        count(2);
+        count();
         if (Win) MF_CUDA(cudaMemcpyAsync(d_Win, Win, sizeof(T) * NP, cudaMemcpyHostToDevice, stream));
         MF_CUDA(cudaMemsetAsync(d_cnx, 0, sizeof(T) * PN, stream)); MF_CUDA(cudaMemsetAsync(d_cny, 0, sizeof(T) * PN, stream));
         MF_CUDA(cudaMemsetAsync(d_cnz, 0, sizeof(T) * PN, stream)); MF_CUDA(cudaMemsetAsync(d_cnorm, 0, sizeof(T) * PN, stream));
@@ -941,6 +944,9 @@ using namespace mflbm;
     }                                                                                                                                     \
     extern "C" int mflbm_##P##_init_state(mflbm_##P##_solver* s, int option, REAL interface_z0, const REAL* W_in) {                       \
         MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->init_state(option, interface_z0, W_in); })                                             \
+    }                                                                                                                                     \
+    extern "C" int mflbm_##P##_init_state_from_phi(mflbm_##P##_solver* s, const REAL* phi, const REAL* W_in) {                            \
+        MF_GUARD({ MF_NEED(s); if (!phi) throw Error{"init_state_from_phi: null phi"}; MF_SOLVER(P, REAL)->init_state(0, REAL(0), W_in, phi); }) \
     }                                                                                                                                     \
     extern "C" int mflbm_##P##_download_state(mflbm_##P##_solver* s, REAL* pdf, REAL* phi, REAL* cn_x, REAL* cn_y, REAL* cn_z,             \
                                               REAL* c_norm, REAL* curv, REAL* f_convec, REAL* g_convec, REAL* phi_convec) {               \

@@ -24,6 +24,10 @@ template <typename T> struct Api;
         static void preprocess_geometry(Handle* h, const int8_t* w) { api_check(mflbm_##P##_preprocess_geometry(h, w), "preprocess_geometry"); } \
         static void geometry_counts(Handle* h, int64_t* c) { api_check(mflbm_##P##_download_geometry(h, nullptr, nullptr, nullptr, nullptr, nullptr, c), "download_geometry"); } \
         static void init_state(Handle* h, int opt, REAL z0, const REAL* W) { api_check(mflbm_##P##_init_state(h, opt, z0, W), "init_state"); } \
+        static void init_state_from_phi(Handle* h, const REAL* phi, const REAL* W) { api_check(mflbm_##P##_init_state_from_phi(h, phi, W), "init_state_from_phi"); } \
+        static void upload_pdf(Handle* h, const REAL* pdf) {                                                                        \
+            api_check(mflbm_##P##_upload_state(h, pdf, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr), "upload_state"); \
+        }                                                                                                                           \
         static void upload_restart(Handle* h, const REAL* pdf, const REAL* phi, const REAL* W, const REAL* fc, const REAL* gc, const REAL* pc) { \
             api_check(mflbm_##P##_upload_state(h, pdf, phi, nullptr, nullptr, nullptr, nullptr, nullptr, W, fc, gc, pc), "upload_state"); \
         }                                                                                                                           \

@@ -10,11 +10,12 @@
 //   * the time loop hands the GPU whole batches of steps up to the next output event (monitor / VTK / timer /
 //     checkpoint step) instead of synchronising eight times per step (src/main_iteration_GPU.cu:1903-2055), and the state
 //     only crosses PCIe when a checkpoint or a VTK file is written: the monitor reductions run on the device;
-//   * geometry_preprocess_cmd 1 (unimplemented in the reference too, src/Geometry_preprocessing.cpp:426),
-//     change_inlet_fluid_phase_cmd and the random initial distribution (option 6) are rejected.
+//   * geometry_preprocess_cmd 1 (unimplemented in the reference too, src/Geometry_preprocessing.cpp:426) is rejected.
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <iostream>
 #include <memory>
 
@@ -56,7 +57,6 @@ class Run {
         if (c.geometry_preprocess_cmd == 1) throw Fatal("geometry_preprocess_cmd 1: loading precomputed boundary info is not implemented (nor in the reference)");
         if (c.geometry_preprocess_cmd != 0) throw Fatal("Wrong value of geometry_preprocess_cmd! Stop program!");
         if (c.extreme_large_sim_cmd != 0) throw Fatal("Extreme large simulation domain (extreme_large_sim_cmd = 1) is not supported yet!");
-        if (c.change_inlet_fluid_phase_cmd != 0) throw Fatal("change_inlet_fluid_phase_cmd is not supported by this driver");
         if (!opt.check_input) make_result_dirs(opt.dir);
         cs.set_walls();
         cs.derive();
@@ -75,13 +75,19 @@ class Run {
         write_info(counts);
 
         if (c.job_status == "new_simulation") {
-            if (c.initial_fluid_distribution_option < 1 || c.initial_fluid_distribution_option > 5)
-                throw Fatal("initial_fluid_distribution_option must be 1..5 (6, the rand()-seeded distribution, is not supported)");
+            if (c.initial_fluid_distribution_option < 1 || c.initial_fluid_distribution_option > 6)
+                throw Fatal("Input parameter initial_fluid_distribution_option error! Stop program!!!");
             cs.ntime0 = 1;
-            Api<T>::init_state(h, c.initial_fluid_distribution_option, c.interface_z0, cs.W_in.empty() ? nullptr : cs.W_in.data());
+            const T* W = cs.W_in.empty() ? nullptr : cs.W_in.data();
+            if (c.initial_fluid_distribution_option == 6) { const std::vector<T> phi = random_phi(); Api<T>::init_state_from_phi(h, phi.data(), W); }
+            else Api<T>::init_state(h, c.initial_fluid_distribution_option, c.interface_z0, W);
             if (c.steady_state_option == 2) Api<T>::phi_change(h, 1, nullptr);   // phi_old = phi, src/Init_multiphase.cpp:381-391
         } else {
             load_checkpoint(P);
+        }
+        if (c.change_inlet_fluid_phase_cmd != 0) {
+            change_inlet_fluid_phase();
+            std::cout << "Inlet fluid phase was changed (1 to fluid1; 2 to fluid2): " << c.change_inlet_fluid_phase_cmd << std::endl;
         }
         std::cout << "************************** Initialization ends ********************************" << std::endl;
 
@@ -133,6 +139,48 @@ class Run {
             for (size_t n = 0; n < cs.W_in.size() * sizeof(T); n++) { hw ^= b[n]; hw *= 1099511628211ULL; }
             std::cout << "CHECK W_in_fnv1a " << hw << std::endl;
         }
+    }
+
+    // initial distribution 6 (src/Init_multiphase.cpp:303-372): fluid 1 with probability sa_target per site of [0..n+1]^3,
+    // drawn with rand() seeded by the wall clock like the reference (so not reproducible there either), then the inlet
+    // ghost planes
+    std::vector<T> random_phi() const {
+        const long long NX4 = cs.nx() + 8, NY4 = cs.ny() + 8;
+        std::vector<T> phi((size_t)N(4), T(0));
+        auto at = [&](long long i, long long j, long long k) -> T& { return phi[(size_t)((i + 3) + NX4 * ((j + 3) + NY4 * (k + 3)))]; };
+        srand((unsigned)time(NULL));
+        for (long long k = 0; k <= cs.nz() + 1; k++)
+            for (long long j = 0; j <= cs.ny() + 1; j++)
+                for (long long i = 0; i <= cs.nx() + 1; i++) {
+                    const T r = (T)rand() / RAND_MAX;
+                    at(i, j, k) = r > cs.ctl.sa_target ? T(-1.) : T(1.);
+                }
+        if (cs.ctl.open_z())
+            for (long long k = -3; k <= 0; k++)
+                for (long long j = -3; j <= cs.ny() + 4; j++)
+                    for (long long i = -3; i <= cs.nx() + 4; i++) at(i, j, k) = cs.phi_inlet;
+        return phi;
+    }
+
+    // change_inlet_fluid_phase (src/Misc.cpp:277-384): for k <= interface_z0 and i in [0 .. nx-1] (the reference's loop bound)
+    // the populations of one component are added to the other's and zeroed.  Host-side, once, on the downloaded PDFs.
+    void change_inlet_fluid_phase() {
+        const long long NX1 = cs.nx() + 2, NY1 = cs.ny() + 2, n1 = N(1);
+        std::vector<T> pdf((size_t)(38 * n1));
+        Api<T>::download(h, pdf.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        const int to = cs.ctl.change_inlet_fluid_phase_cmd == 1 ? 0 : 1, from = 1 - to;
+        if (cs.ctl.change_inlet_fluid_phase_cmd == 1 || cs.ctl.change_inlet_fluid_phase_cmd == 2)
+            for (long long k = 0; k <= cs.nz() + 1; k++) {
+                if (!((T)k <= cs.ctl.interface_z0)) continue;
+                for (long long j = 0; j <= cs.ny() + 1; j++)
+                    for (long long i = 0; i <= cs.nx() - 1; i++)
+                        for (int q = 0; q < 19; q++) {
+                            const size_t cell = (size_t)(i + NX1 * (j + NY1 * k));
+                            pdf[(size_t)(q + 19 * to) * n1 + cell] += pdf[(size_t)(q + 19 * from) * n1 + cell];
+                            pdf[(size_t)(q + 19 * from) * n1 + cell] = T(0.);
+                        }
+            }
+        Api<T>::upload_pdf(h, pdf.data());
     }
 
     // results/out1.output/info.txt, src/Init_multiphase.cpp:128-165

@@ -96,6 +96,7 @@ def load_library() -> C.CDLL:
             "download_geometry": [vp, vp, vp, vp, vp, vp, vp],
             "upload_state": [vp] + [vp] * 11,
             "init_state": [vp, i32, r, vp],
+            "init_state_from_phi": [vp, vp, vp],
             "download_state": [vp] + [vp] * 10,
             "step": [vp, i32],
             "run": [vp, i32, i32],
@@ -134,7 +135,7 @@ def load_library() -> C.CDLL:
 
 
 EXPORTED = ["create", "destroy", "set_params", "upload_geometry", "preprocess_geometry", "download_geometry", "upload_state",
-            "init_state", "download_state", "step", "run", "color_gradient", "monitor", "sync", "phi_change", "download_macro", "halo_buffers", "halo_pack",
+            "init_state", "init_state_from_phi", "download_state", "step", "run", "color_gradient", "monitor", "sync", "phi_change", "download_macro", "halo_buffers", "halo_pack",
             "halo_unpack", "halo_p2p_local", "halo_p2p_region", "halo_p2p_connect", "halo_push", "halo_unpack_wait", "step_phase",
             "num_fluid_nodes", "kernel_launches", "stream", "device_ptr"]
 
@@ -275,6 +276,12 @@ class Solver:
         self._keep = []
         rc = self._fn("init_state")(self.h, int(option), CREAL[self.prec](float(self.rt(interface_z0))),
                                     self._in(W_in, self.rt, (self.ny + 2, self.nx + 2)))
+        self._check(rc)
+
+    def init_state_from_phi(self, phi, W_in=None):
+        """equilibrium PDFs at rest + colour gradient from a caller-supplied phase field [nz+8, ny+8, nx+8]"""
+        self._keep = []
+        rc = self._fn("init_state_from_phi")(self.h, self._in(phi, self.rt, self._shape(4)), self._in(W_in, self.rt, (self.ny + 2, self.nx + 2)))
         self._check(rc)
 
     def download_state(self, convective: bool | None = None, fields=None) -> dict:

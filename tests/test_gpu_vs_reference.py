@@ -105,3 +105,37 @@ def common_fluid_mask(geom, g):
     m = np.zeros((nz + 2 * g, ny + 2 * g, nx + 2 * g), dtype=bool)
     m[g:g + nz, g:g + ny, g:g + nx] = w[2:2 + nz, 2:2 + ny, 2:2 + nx] == 0
     return m
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("name", ["tube_pressure", "pack_velocity"])
+def test_saturation_after_10k_steps_matches_reference(gpu_lib, name, prec):
+    """north_star: the monitored saturation must agree within 1e-6 after 10 000 steps.  Both codes start from the same
+    step-0 state (the reference's own) and are monitored at steps 2 000, 6 000 and 10 000."""
+    if not rc.ref_binary("gpu", prec).exists():
+        pytest.skip("oracle/_ref/ref_gpu_* not present")
+    import mflbm
+    marks = (2000, 6000, 10000)
+    meta, geom, states, mon = refgpu.run_reference_gpu(name, prec, steps=(), monitor=marks)
+    ctl, solid = common.full_control(name)
+    s = mflbm.Solver(mflbm.derive_params(ctl, prec), prec)
+    s.upload_geometry(geom["walls"], geom["walls_type"], geom["s_nx"], geom["s_ny"], geom["s_nz"])
+    st0 = states[0]
+    s.upload_state(pdf=st0["pdf"], phi=st0["phi"], cn_x=st0["cn_x"], cn_y=st0["cn_y"], cn_z=st0["cn_z"], c_norm=st0["c_norm"],
+                   curv=st0["curv"], W_in=geom["W_in"], f_convec=st0.get("f_convec_bc"), g_convec=st0.get("g_convec_bc"),
+                   phi_convec=st0.get("phi_convec_bc"))
+    rows = [l.split() for l in mon.splitlines() if l.strip()]
+    assert len(rows) == len(marks)
+    done = 0
+    for step, row in zip(marks, rows):
+        s.run(1 + done, step - done)
+        done = step
+        m = s.monitor()
+        assert m["nan_detected"] == 0
+        sat_ref, sat_full_ref = float(row[2]), float(row[3])
+        # FP32: the reference itself prints 6-7 significant digits of a float; 1e-6 is the north_star figure for both
+        tol = 1e-6 if prec == "f64" else 2e-5
+        assert abs(m["saturation"] - sat_ref) <= tol, (step, m["saturation"], sat_ref)
+        assert abs(m["saturation_full_domain"] - sat_full_ref) <= tol, (step, m["saturation_full_domain"], sat_full_ref)
+    s.close()

@@ -141,11 +141,17 @@ def rows(path: Path):
 
 
 STOCK_CASES = {
-    # name: (control overrides, geometry case)
-    "tube_pressure": dict(max_time_step=39, monitor_timer=10, monitor_profile_timer_ratio=2, computation_time_timer=20, display_steps_timer=20,
-                          ntime_animation=20, ntime_visual=40, benchmark_cmd=0, steady_state_option=3, convergence_criteria=1e-12),
-    "pack_velocity": dict(max_time_step=29, monitor_timer=10, monitor_profile_timer_ratio=1, computation_time_timer=30, display_steps_timer=10,
-                          ntime_animation=1000000, ntime_visual=1000000, benchmark_cmd=1, steady_state_option=0),
+    # label: (case of tests/common.py, control overrides)
+    "tube_pressure": ("tube_pressure", dict(max_time_step=39, monitor_timer=10, monitor_profile_timer_ratio=2, computation_time_timer=20, display_steps_timer=20,
+                                            ntime_animation=20, ntime_visual=40, benchmark_cmd=0, steady_state_option=3, convergence_criteria=1e-12)),
+    "pack_velocity": ("pack_velocity", dict(max_time_step=29, monitor_timer=10, monitor_profile_timer_ratio=1, computation_time_timer=30, display_steps_timer=10,
+                                            ntime_animation=1000000, ntime_visual=1000000, benchmark_cmd=1, steady_state_option=0)),
+    # change_inlet_fluid_phase (src/Misc.cpp:277-384) and the capillary-pressure steady-state monitor (src/Monitor.cpp:357-441)
+    "tube_change_inlet": ("tube_pressure", dict(max_time_step=19, monitor_timer=10, computation_time_timer=20, display_steps_timer=1000, benchmark_cmd=1,
+                                                change_inlet_fluid_phase_cmd=2, steady_state_option=1, convergence_criteria=1e-12)),
+    # y/z periodic body-force case with the phase-field steady-state monitor (src/Monitor.cpp:279-352)
+    "periodic_phasefield": ("periodic_drop", dict(max_time_step=19, monitor_timer=10, computation_time_timer=20, display_steps_timer=1000, benchmark_cmd=1,
+                                                  steady_state_option=2, convergence_criteria=1e-12)),
 }
 
 
@@ -156,8 +162,9 @@ def test_driver_matches_stock_reference_program(gpu_lib, tmp_path, name, prec):
     stock = rc.REF_BIN_DIR / f"MF_LBM_CUDA_{prec}"
     if not stock.exists():
         pytest.skip(f"{stock} not built (oracle/build_ref.sh needs /root/reference)")
+    label, (name, over) = name, STOCK_CASES[name]
     ctl, solid = common.CASES[name]()
-    ctl = dict(ctl, **STOCK_CASES[name])
+    ctl = dict(ctl, **over)
     ours, ref = tmp_path / "ours", tmp_path / "ref"
     full = rc.write_case(ours, ctl, solid)
     shutil.copytree(ours, ref)
@@ -199,9 +206,12 @@ def test_driver_matches_stock_reference_program(gpu_lib, tmp_path, name, prec):
     cr = read_checkpoint(ref / "results" / "out2.checkpoint" / "id0000", nx, ny, nz, rt, conv)
     assert co["ntime"] == cr["ntime"] and co["force_z"] == cr["force_z"] and co["rho_in"] == cr["rho_in"]
     assert common.relerr(co["pdf"], cr["pdf"]) <= tol
+    # fluid nodes as the programs see them: domain walls added, geometry read with the reference's swapped strides when
+    # nx != ny - the oracle's wall array, pinned against the reference CPU code
+    o_walls = common.make_oracle(name, prec)[0]
+    walls_seen = o_walls.arr("walls_global").copy()   # (arr() is a view into the oracle's memory)
     fluid = np.zeros(cr["phi"].shape, bool)
-    fluid[4:-4, 4:-4, 4:-4] = solid == 0
-    fluid[:, :, 4] = False; fluid[:, :, -5] = False; fluid[:, 4, :] = False; fluid[:, -5, :] = False   # domain walls
+    fluid[4:-4, 4:-4, 4:-4] = walls_seen == 0
     # the reference's host phi was zeroed inside solids by its monitor / VTK writer before the checkpoint was written
     assert np.abs(co["phi"][fluid].astype(np.float64) - cr["phi"][fluid]).max() <= tol * max(1.0, float(np.abs(cr["phi"]).max()))
     if conv:
@@ -268,3 +278,19 @@ def test_driver_restart_continues_like_the_reference(gpu_lib, tmp_path):
     cr = read_checkpoint(ref / "results" / "out2.checkpoint" / "id0000", nx, ny, nz, np.float64, False)
     assert co["ntime"] == cr["ntime"] == 20 + 20 + 1
     assert common.relerr(co["pdf"], cr["pdf"]) <= common.TOL[prec]
+
+
+@pytest.mark.gpu
+def test_driver_random_initial_distribution(gpu_lib, tmp_path):
+    """initial_fluid_distribution_option 6: fluid 1 with probability target_fluid1_saturation per node, drawn with rand()
+    seeded by the wall clock in the reference too, so only statistics can be checked"""
+    ctl, solid = common.CASES["imbibition_plate2"]()
+    ctl = dict(ctl, initial_fluid_distribution_option=6, target_fluid1_saturation=0.4, max_time_step=9, monitor_timer=10, computation_time_timer=10,
+               display_steps_timer=1000, benchmark_cmd=1)
+    rc.write_case(tmp_path, ctl, solid)
+    r = run_driver(tmp_path, "--prec", "f64")
+    sat0 = float([l for l in r.stdout.splitlines() if l.startswith("Initial saturation:")][0].split(":")[1])
+    assert abs(sat0 - 0.4) < 0.03, sat0
+    sat = rows(tmp_path / "results" / "out1.output" / "saturation_full_domain.dat")
+    assert sat.shape[0] == 1 and np.isfinite(sat).all() and 0.3 < sat[0, 1] < 0.5
+    assert (tmp_path / "job_status.txt").read_text() == "simulation_reached_max_step\n"
