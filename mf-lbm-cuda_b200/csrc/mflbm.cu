@@ -444,7 +444,7 @@ struct Solver {
         if (cny) to_u<T>(cny, d_cny, 2, N2);
         if (cnz) to_u<T>(cnz, d_cnz, 2, N2);
         if (cnorm) to_u<T>(cnorm, d_cnorm, 2, N2);
-        if (cnx || cny || cnz || cnorm) { cn_consistent = false; mark_all_live(); }
+        if (cnx || cny || cnz || cnorm) { cn_consistent = false; mark_all_live(); drop_graphs(); }   // bulk_skip is baked into captured launches
         if (cnx || cny || cnz || cnorm) {   // the caller's arrays are not trusted to hold zeros in solids
             k_zero_solid_normals<T><<<grid_box(2, 128), 128, 0, stream>>>(L); check_launch(); count();
         }
@@ -712,6 +712,9 @@ struct Solver {
         if (nsteps <= 0) return;
         if (!have_geometry) MF_FAIL("step before geometry");
         int nt = ntime_first, left = nsteps;
+        // the collide launch carries bulk_skip = cn_consistent as an argument: step once outside the graph after arrays came
+        // from outside, so that the captured pair has the fast setting in both of its collide launches
+        if (!cn_consistent && left > 0) { step(nt); nt++; left--; }
         if (left >= 4) {
             const int par = nt & 1;
             if (!graph_exec[par]) {

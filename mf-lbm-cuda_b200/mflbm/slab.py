@@ -28,6 +28,7 @@ from __future__ import annotations
 import ctypes as C
 import json
 import os
+import sys
 import time
 from dataclasses import dataclass
 
@@ -298,10 +299,15 @@ def bench_slabs(args, rank: int, world: int, local: int) -> dict | None:
         t0 = time.perf_counter()
         slab.solver.upload_state(**{k: host[k] for k in ("pdf", "phi", "cn_x", "cn_y", "cn_z", "c_norm", "curv")},
                                  f_convec=host.get("f_convec"), g_convec=host.get("g_convec"), phi_convec=host.get("phi_convec"))
+        t1 = time.perf_counter()
         stepper.run(nt, args.steps)
+        t2 = time.perf_counter()
         reduce_monitor(slab.solver.monitor(), rng, params, dist, device=f"cuda:{local}")
+        t3 = time.perf_counter()
         slab.solver.download_state_into(host)
         torch.cuda.synchronize()
+        if os.environ.get("MFLBM_BENCH_DEBUG"):
+            print(f"[rank {rank}] e2e: upload {t1 - t0:.3f} s, run (enqueue) {t2 - t1:.3f} s, monitor {t3 - t2:.3f} s, download {time.perf_counter() - t3:.3f} s", file=sys.stderr, flush=True)
         te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         t_e2e = float(te[0])

@@ -10,8 +10,8 @@ if [ "$2" != "notest" ]; then
   tail -5 $O/${TAG}_pytest.log
 fi
 for p in f64 f32; do
-  timeout 600 python bench.py --prec $p --steps 200 --warmup 10 > $O/${TAG}_bench_$p.json 2> $O/${TAG}_bench_$p.err
-  timeout 600 python bench.py --impl reference --prec $p --steps 50 --warmup 5 > $O/${TAG}_bench_reference_$p.json 2>> $O/${TAG}_bench_$p.err
+  timeout 600 python bench.py --prec $p > $O/${TAG}_bench_$p.json 2> $O/${TAG}_bench_$p.err
+  timeout 600 python bench.py --impl reference --prec $p --steps 400 --warmup 20 > $O/${TAG}_bench_reference_$p.json 2>> $O/${TAG}_bench_$p.err
 done
 cat $O/${TAG}_bench_f64.json $O/${TAG}_bench_f32.json
 for p in f64 f32; do
