@@ -83,6 +83,8 @@ struct Solver {
     T* d_recv[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
     // halo messages through peer memory (kernels_aux.cuh): my incoming flags [kind*2+side], block tickets [8 + ...] and
     // message counters [16 + ...]; the neighbours' receive buffers / flags as peer pointers
+    cudaStream_t aux_stream = nullptr;          // second lane for the right-hand neighbour's messages (fork/join with events)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     unsigned char* d_p2p = nullptr;
     size_t p2p_bytes = 0;
     unsigned* d_flags = nullptr;
@@ -153,6 +155,9 @@ struct Solver {
         zalloc((void**)&d_mon, sizeof(double) * MFLBM_MON_N * L.nz);
         MF_CUDA(cudaMallocHost((void**)&h_mon, sizeof(double) * MFLBM_MON_N * L.nz));
         if (is_slab) {
+            MF_CUDA(cudaStreamCreateWithFlags(&aux_stream, cudaStreamNonBlocking));
+            MF_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+            MF_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
             // everything a neighbour may write - arrival flags and the six receive buffers - is ONE allocation, so that a
             // single CUDA IPC handle plus offsets describes it (small cudaMalloc blocks are sub-allocated and cannot be
             // exported one by one)
@@ -192,6 +197,9 @@ struct Solver {
         if (d_stage) { cudaFree(d_stage); d_stage = nullptr; }
         for (int kind = 0; kind < 3; kind++) for (int side = 0; side < 2; side++) { dfree(d_send[kind][side]); d_recv[kind][side] = nullptr; }
         if (h_mon) { cudaFreeHost(h_mon); h_mon = nullptr; }
+        if (aux_stream) { cudaStreamDestroy(aux_stream); aux_stream = nullptr; }
+        if (ev_fork) { cudaEventDestroy(ev_fork); ev_fork = nullptr; }
+        if (ev_join) { cudaEventDestroy(ev_join); ev_join = nullptr; }
         if (own_stream && stream) cudaStreamDestroy(stream);
         stream = nullptr;
     }
@@ -813,7 +821,9 @@ struct Solver {
 
     // pack the outgoing columns of message `kind`.  push = false: into my send buffers (the caller moves them, e.g. NCCL);
     // push = true: straight into the neighbours' receive buffers over NVLink, arrival published in their flags
-    void halo_pack(int kind, bool push = false) {
+    void halo_pack(int kind, bool push = false, int sides = 3, cudaStream_t on = nullptr) {
+        cudaStream_t stream = on ? on : this->stream;
+        const bool do_left = slab.has_left && (sides & 1), do_right = slab.has_right && (sides & 2);
         if (!is_slab) MF_FAIL("halo_pack on a non-slab solver");
         if (!have_geometry) MF_FAIL("halo_pack before geometry");
         if (kind < 0 || kind > 2) MF_FAIL("bad halo kind");
@@ -829,20 +839,22 @@ struct Solver {
             return HaloSync{peer_flag[kind][side], d_flags + 8 + kind * 2 + side, d_flags + 16 + kind * 2 + side};
         };
         if (kind == 0) {   // after an even step: real boundary columns -> neighbour ghost columns
-            if (slab.has_left) { k_halo_pdf<T, false, true><<<g1, bt, 0, stream>>>(L, dst(0), 1, sync(0)); count(); }          // ex=-1 slots of column 1
-            if (slab.has_right) { k_halo_pdf<T, true, true><<<g1, bt, 0, stream>>>(L, dst(1), L.nx, sync(1)); count(); }       // ex=+1 slots of column nx
+            if (do_left) { k_halo_pdf<T, false, true><<<g1, bt, 0, stream>>>(L, dst(0), 1, sync(0)); count(); }          // ex=-1 slots of column 1
+            if (do_right) { k_halo_pdf<T, true, true><<<g1, bt, 0, stream>>>(L, dst(1), L.nx, sync(1)); count(); }       // ex=+1 slots of column nx
         } else if (kind == 1) {   // after an odd step: what was pushed into my ghost columns -> neighbour real columns
-            if (slab.has_left) { k_halo_pdf<T, true, true><<<g1, bt, 0, stream>>>(L, dst(0), 0, sync(0)); count(); }           // ex=+1 slots of ghost column 0
-            if (slab.has_right) { k_halo_pdf<T, false, true><<<g1, bt, 0, stream>>>(L, dst(1), L.nx + 1, sync(1)); count(); }  // ex=-1 slots of ghost column nx+1
+            if (do_left) { k_halo_pdf<T, true, true><<<g1, bt, 0, stream>>>(L, dst(0), 0, sync(0)); count(); }           // ex=+1 slots of ghost column 0
+            if (do_right) { k_halo_pdf<T, false, true><<<g1, bt, 0, stream>>>(L, dst(1), L.nx + 1, sync(1)); count(); }  // ex=-1 slots of ghost column nx+1
         } else {
-            if (slab.has_left) { k_halo_phi<T, true><<<g4, bt, 0, stream>>>(L, dst(0), 1, sync(0)); count(); }
-            if (slab.has_right) { k_halo_phi<T, true><<<g4, bt, 0, stream>>>(L, dst(1), L.nx - 3, sync(1)); count(); }
+            if (do_left) { k_halo_phi<T, true><<<g4, bt, 0, stream>>>(L, dst(0), 1, sync(0)); count(); }
+            if (do_right) { k_halo_phi<T, true><<<g4, bt, 0, stream>>>(L, dst(1), L.nx - 3, sync(1)); count(); }
         }
         check_launch();
     }
 
     // unpack message `kind` from my receive buffers; wait = true: spin on my flags until the neighbours' pushes have landed
-    void halo_unpack(int kind, bool wait = false) {
+    void halo_unpack(int kind, bool wait = false, int sides = 3, cudaStream_t on = nullptr) {
+        cudaStream_t stream = on ? on : this->stream;
+        const bool do_left = slab.has_left && (sides & 1), do_right = slab.has_right && (sides & 2);
         if (!is_slab) MF_FAIL("halo_unpack on a non-slab solver");
         if (!have_geometry) MF_FAIL("halo_unpack before geometry");
         if (kind < 0 || kind > 2) MF_FAIL("bad halo kind");
@@ -853,14 +865,14 @@ struct Solver {
             return HaloSync{d_flags + kind * 2 + side, nullptr, d_flags + 16 + kind * 2 + side};
         };
         if (kind == 0) {   // neighbour's real boundary column -> my ghost column
-            if (slab.has_left) { k_halo_pdf<T, true, false><<<g1, bt, 0, stream>>>(L, d_recv[0][0], 0, sync(0)); count(); }          // left's column nx (ex=+1) -> ghost 0
-            if (slab.has_right) { k_halo_pdf<T, false, false><<<g1, bt, 0, stream>>>(L, d_recv[0][1], L.nx + 1, sync(1)); count(); } // right's column 1 (ex=-1) -> ghost nx+1
+            if (do_left) { k_halo_pdf<T, true, false><<<g1, bt, 0, stream>>>(L, d_recv[0][0], 0, sync(0)); count(); }          // left's column nx (ex=+1) -> ghost 0
+            if (do_right) { k_halo_pdf<T, false, false><<<g1, bt, 0, stream>>>(L, d_recv[0][1], L.nx + 1, sync(1)); count(); } // right's column 1 (ex=-1) -> ghost nx+1
         } else if (kind == 1) {   // neighbour's ghost column -> my real boundary column
-            if (slab.has_left) { k_halo_pdf<T, false, false><<<g1, bt, 0, stream>>>(L, d_recv[1][0], 1, sync(0)); count(); }         // left's ghost nx+1 (ex=-1) -> column 1
-            if (slab.has_right) { k_halo_pdf<T, true, false><<<g1, bt, 0, stream>>>(L, d_recv[1][1], L.nx, sync(1)); count(); }      // right's ghost 0 (ex=+1) -> column nx
+            if (do_left) { k_halo_pdf<T, false, false><<<g1, bt, 0, stream>>>(L, d_recv[1][0], 1, sync(0)); count(); }         // left's ghost nx+1 (ex=-1) -> column 1
+            if (do_right) { k_halo_pdf<T, true, false><<<g1, bt, 0, stream>>>(L, d_recv[1][1], L.nx, sync(1)); count(); }      // right's ghost 0 (ex=+1) -> column nx
         } else {
-            if (slab.has_left) { k_halo_phi<T, false><<<g4, bt, 0, stream>>>(L, d_recv[2][0], -3, sync(0)); count(); }
-            if (slab.has_right) { k_halo_phi<T, false><<<g4, bt, 0, stream>>>(L, d_recv[2][1], L.nx + 1, sync(1)); count(); }
+            if (do_left) { k_halo_phi<T, false><<<g4, bt, 0, stream>>>(L, d_recv[2][0], -3, sync(0)); count(); }
+            if (do_right) { k_halo_phi<T, false><<<g4, bt, 0, stream>>>(L, d_recv[2][1], L.nx + 1, sync(1)); count(); }
         }
         check_launch();
     }
@@ -880,12 +892,25 @@ struct Solver {
         return true;
     }
     // one step of a slab with its two halo messages through peer memory (the sequence of mflbm/slab.py SlabStepper.step)
+    // one message of `kind` to and from every neighbour.  With two neighbours the right-hand side runs on a second stream
+    // (event fork / join, capturable): the four small latency-bound kernels of an interior slab overlap pairwise.
+    void exchange_p2p(int kind) {
+        if (slab.has_left && slab.has_right) {
+            MF_CUDA(cudaEventRecord(ev_fork, stream));
+            MF_CUDA(cudaStreamWaitEvent(aux_stream, ev_fork, 0));
+            halo_pack(kind, true, 2, aux_stream); halo_unpack(kind, true, 2, aux_stream);
+            halo_pack(kind, true, 1); halo_unpack(kind, true, 1);
+            MF_CUDA(cudaEventRecord(ev_join, aux_stream));
+            MF_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
+        } else {
+            halo_pack(kind, true); halo_unpack(kind, true);
+        }
+    }
     void step_p2p(int ntime) {
         step_phase(ntime, 0);
-        const int kind = (ntime % 2) ? 1 : 0;
-        halo_pack(kind, true); halo_unpack(kind, true);
+        exchange_p2p((ntime % 2) ? 1 : 0);
         step_phase(ntime, 1);
-        halo_pack(2, true); halo_unpack(2, true);
+        exchange_p2p(2);
         step_phase(ntime, 2);
     }
 
