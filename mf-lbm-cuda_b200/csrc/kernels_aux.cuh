@@ -400,7 +400,9 @@ struct HaloSync {
     unsigned* flag;      // push: the peer's flag; unpack: my flag; nullptr = no synchronisation (NCCL path)
     unsigned* counter;   // push only: block tickets (own memory, returns to 0)
     unsigned* seq;       // my message counter for this (kind, side)
+    unsigned* error;     // unpack only: set to 1 + kind*2 + side when a message did not arrive within HALO_TIMEOUT_CYCLES
 };
+constexpr long long HALO_TIMEOUT_CYCLES = 20000000000LL;   // ~10 s at 2 GHz: a dead neighbour must not hang this GPU for ever
 __device__ __forceinline__ void halo_publish(const HaloSync& hs) {
     if (!hs.flag) return;
     __threadfence_system();
@@ -420,8 +422,12 @@ __device__ __forceinline__ void halo_await(const HaloSync& hs) {
     if (!hs.flag) return;
     if (threadIdx.x == 0 && threadIdx.y == 0) {
         const unsigned want = *reinterpret_cast<volatile unsigned*>(hs.seq);
+        const long long t0 = clock64();
         // sequence numbers only grow; the signed difference survives wrap-around
-        while ((int)(*reinterpret_cast<volatile unsigned*>(hs.flag) - want) < 0) __nanosleep(64);
+        while ((int)(*reinterpret_cast<volatile unsigned*>(hs.flag) - want) < 0) {
+            __nanosleep(64);
+            if (clock64() - t0 > HALO_TIMEOUT_CYCLES) { if (hs.error) *hs.error = 1u + (unsigned)(hs.flag - (hs.error - 31)); break; }
+        }
         __threadfence_system();
     }
     __syncthreads();
@@ -439,16 +445,13 @@ __global__ void k_halo_pdf(const Lattice<T> L, T* __restrict__ buf, const int co
         // solid site of the real boundary column can additionally be the far end of a link of THIS slab's nodes, which keep
         // that cell in a mailbox the exchange must not touch.
         const int uu = L.u(col, y, z);
-#pragma unroll
-        for (int g = 0; g < 2; g++) {
-#pragma unroll
-            for (int n = 0; n < 5; n++) {
-                const int q = PLUS ? slot_exp(n) : slot_exm(n);
-                T* cell = &L.f_raw(q, g, uu);
-                T* b = buf + (long long)(g * 5 + n) * plane + (y + L.NY1 * z);
-                if (PACK) *b = *cell; else *cell = __ldcg(b);
-            }
-        }
+        // one thread per (slot, y, z): blockIdx.z = 5 * component + n.  (With one thread per site walking its ten slots
+        // the kernel was a chain of dependent look-up -> access pairs, 17-23 us for a 258 x 258 face.)
+        const int g = blockIdx.z / 5, n = blockIdx.z % 5;
+        const int q = PLUS ? slot_exp(n) : slot_exm(n);
+        T* cell = &L.f_raw(q, g, uu);
+        T* b = buf + (long long)(g * 5 + n) * plane + (y + L.NY1 * z);
+        if (PACK) *b = *cell; else *cell = __ldcg(b);
     }
     if (PACK) halo_publish(hs);
 }

@@ -594,60 +594,33 @@ struct Solver {
     template <int MRT>
     void launch_collide_default(bool odd) {
         if (!n_fluid) return;
-        const int e = (variant % 10000) / 100, o = variant % 100;
-        if (sizeof(T) == 8) {
-            if (odd) {
-                if constexpr (MRT == 2) {
-                    if (o == 1) { launch_odd<MRT, 1, 2>(); goto done; }
-                    if (o == 2) { launch_odd<MRT, 3, 1>(); goto done; }
-                    if (o == 3) { launch_odd<MRT, 1, 1>(); goto done; }
-                }
-                if constexpr (MRT == 2) {
-                    if (o == 4) { launch_odd<MRT, 2, 1>(); goto done; }
-                    if (o == 5) { launch_odd_ws<MRT, 2, 1>(); goto done; }
-                    if (o == 6) { launch_odd_ws<MRT, 4, 1>(); goto done; }
-                    if (o == 7) { launch_odd_ws<MRT, 4, 1, 2, 72, 216>(); goto done; }
-                    if (o == 8) { launch_odd_ws<MRT, 4, 1, 2, 56, 224>(); goto done; }
-                    if (o == 9) { launch_odd_ws<MRT, 4, 1, 2, 40, 232>(); goto done; }
-                    if (o == 10) { launch_odd_ws<MRT, 4, 1, 2>(); goto done; }
-                }
-                launch_odd_ws<MRT, 3, 1>();   // measured best on the 256^3 pack (profiles/README.md)
+        // MFLBM_VARIANT = 100 * even + odd selects the other configurations that were measured (profiles/README.md); they
+        // are only instantiated for the shipped MRT model.  0 = the defaults.  Results are identical whatever the variant.
+        bool done = false;
+        if constexpr (MRT == 2) {
+            const int e = (variant % 10000) / 100, o = variant % 100;
+            done = true;
+            if constexpr (sizeof(T) == 8) {
+                if (odd && o == 1) launch_odd_ws<MRT, 2, 1>();
+                else if (odd && o == 2) launch_odd_ws<MRT, 4, 1>();
+                else if (odd && o == 3) launch_odd_ws<MRT, 4, 1, 2, 72, 216>();   // two consumer warpgroups, registers moved with setmaxnreg
+                else if (odd && o == 4) launch_odd<MRT, 2, 1>();                  // the pipelined kernel before warp specialisation
+                else if (!odd && e == 1) launch_even<MRT, 3, 1>();
+                else done = false;
             } else {
-                if constexpr (MRT == 2) {
-                    if (e == 1) { launch_even<MRT, 4, 1>(); goto done; }
-                    if (e == 2) { launch_even<MRT, 3, 1>(); goto done; }
-                }
-                launch_even<MRT, 2, 2>();
-            }
-        } else {
-            if (odd) {
-                if constexpr (MRT == 2) {
-                    if (o == 1) { launch_odd<MRT, 1, 3>(); goto done; }
-                    if (o == 2) { launch_odd<MRT, 4, 1>(); goto done; }
-                    if (o == 3) { launch_odd<MRT, 2, 1>(); goto done; }
-                    if (o == 4) { launch_odd<MRT, 3, 1>(); goto done; }
-                }
-                if constexpr (MRT == 2) {
-                    if (o == 5) { launch_odd<MRT, 2, 2>(); goto done; }
-                    if (o == 6) { launch_odd_ws<MRT, 3, 1>(); goto done; }
-                    if (o == 7) { launch_odd_ws<MRT, 6, 1>(); goto done; }
-                    if (o == 8) { launch_odd_ws<MRT, 2, 2>(); goto done; }
-                    if (o == 9) { launch_odd_ws<MRT, 3, 2>(); goto done; }
-                    if (o == 10) { launch_odd_ws<MRT, 4, 1, 2>(); goto done; }
-                    if (o == 11) { launch_odd_ws<MRT, 6, 1, 2>(); goto done; }
-                    if (o == 12) { launch_odd_ws<MRT, 6, 1, 3>(); goto done; }
-                }
-                launch_odd_ws<MRT, 4, 1>();
-            } else {
-                if constexpr (MRT == 2) {
-                    if (e == 1) { launch_even<MRT, 8, 1>(); goto done; }
-                    if (e == 2) { launch_even<MRT, 2, 4>(); goto done; }
-                    if (e == 3) { launch_even<MRT, 3, 3>(); goto done; }
-                }
-                launch_even<MRT, 4, 2>();
+                if (odd && o == 1) launch_odd_ws<MRT, 3, 1>();
+                else if (odd && o == 2) launch_odd_ws<MRT, 2, 2>();
+                else if (odd && o == 3) launch_odd_ws<MRT, 4, 1, 2>();
+                else if (odd && o == 4) launch_odd<MRT, 2, 2>();
+                else if (!odd && e == 1) launch_even<MRT, 8, 1>();
+                else if (!odd && e == 2) launch_even<MRT, 2, 4>();
+                else done = false;
             }
         }
-    done:
+        if (!done) {
+            if constexpr (sizeof(T) == 8) { if (odd) launch_odd_ws<MRT, 3, 1>(); else launch_even<MRT, 2, 2>(); }
+            else { if (odd) launch_odd_ws<MRT, 4, 1>(); else launch_even<MRT, 4, 2>(); }
+        }
         check_launch(); count();
     }
 
@@ -743,9 +716,19 @@ struct Solver {
     }
 
     // ------------------------------------------------------------------------------------------------
+    // a halo message that never arrived (kernels_aux.cuh, HALO_TIMEOUT_CYCLES): surface it at the next host synchronisation
+    void check_halo_error() {
+        if (!d_flags) return;
+        unsigned e = 0;
+        MF_CUDA(cudaMemcpyAsync(&e, d_flags + 31, sizeof e, cudaMemcpyDeviceToHost, stream));
+        MF_CUDA(cudaStreamSynchronize(stream));
+        if (e) MF_FAIL("halo message %u (1 + 2*kind + side) from a neighbour slab did not arrive within the time-out", e);
+    }
+
     void monitor(mflbm_monitor_out* out) {
         if (!have_geometry) MF_FAIL("monitor before geometry");
         if (!out) MF_FAIL("monitor: null output");
+        check_halo_error();
         k_monitor<T><<<L.nz, 256, 0, stream>>>(L, d_zstart, d_mon); check_launch(); count();
         MF_CUDA(cudaMemcpyAsync(h_mon, d_mon, sizeof(double) * MFLBM_MON_N * L.nz, cudaMemcpyDeviceToHost, stream));
         MF_CUDA(cudaStreamSynchronize(stream));
@@ -828,15 +811,15 @@ struct Solver {
         if (!have_geometry) MF_FAIL("halo_pack before geometry");
         if (kind < 0 || kind > 2) MF_FAIL("bad halo kind");
         const int bt = 128;
-        const dim3 g1(ceil_div(L.NY1, bt), L.NZ1), g4(ceil_div(L.PY, bt), L.PZ);
+        const dim3 g1(ceil_div(L.NY1, bt), L.NZ1, 10), g4(ceil_div(L.PY, bt), L.PZ);
         auto dst = [&](int side) -> T* {
             if (!push) return d_send[kind][side];
             if (!peer_recv[kind][side] || !peer_flag[kind][side]) MF_FAIL("halo_push: neighbour %d of message kind %d is not connected", side, kind);
             return peer_recv[kind][side];
         };
         auto sync = [&](int side) -> HaloSync {
-            if (!push) return HaloSync{nullptr, nullptr, nullptr};
-            return HaloSync{peer_flag[kind][side], d_flags + 8 + kind * 2 + side, d_flags + 16 + kind * 2 + side};
+            if (!push) return HaloSync{nullptr, nullptr, nullptr, nullptr};
+            return HaloSync{peer_flag[kind][side], d_flags + 8 + kind * 2 + side, d_flags + 16 + kind * 2 + side, nullptr};
         };
         if (kind == 0) {   // after an even step: real boundary columns -> neighbour ghost columns
             if (do_left) { k_halo_pdf<T, false, true><<<g1, bt, 0, stream>>>(L, dst(0), 1, sync(0)); count(); }          // ex=-1 slots of column 1
@@ -859,10 +842,10 @@ struct Solver {
         if (!have_geometry) MF_FAIL("halo_unpack before geometry");
         if (kind < 0 || kind > 2) MF_FAIL("bad halo kind");
         const int bt = 128;
-        const dim3 g1(ceil_div(L.NY1, bt), L.NZ1), g4(ceil_div(L.PY, bt), L.PZ);
+        const dim3 g1(ceil_div(L.NY1, bt), L.NZ1, 10), g4(ceil_div(L.PY, bt), L.PZ);
         auto sync = [&](int side) -> HaloSync {
-            if (!wait) return HaloSync{nullptr, nullptr, nullptr};
-            return HaloSync{d_flags + kind * 2 + side, nullptr, d_flags + 16 + kind * 2 + side};
+            if (!wait) return HaloSync{nullptr, nullptr, nullptr, nullptr};
+            return HaloSync{d_flags + kind * 2 + side, nullptr, d_flags + 16 + kind * 2 + side, d_flags + 31};
         };
         if (kind == 0) {   // neighbour's real boundary column -> my ghost column
             if (do_left) { k_halo_pdf<T, true, false><<<g1, bt, 0, stream>>>(L, d_recv[0][0], 0, sync(0)); count(); }          // left's column nx (ex=+1) -> ghost 0
@@ -993,7 +976,7 @@ using namespace mflbm;
         MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->download_macro(rho, u, v, w); })                                                       \
     }                                                                                                                                     \
     extern "C" int mflbm_##P##_sync(mflbm_##P##_solver* s) {                                                                              \
-        MF_GUARD({ MF_NEED(s); MF_CUDA(cudaStreamSynchronize(MF_SOLVER(P, REAL)->stream)); })                                             \
+        MF_GUARD({ MF_NEED(s); MF_CUDA(cudaStreamSynchronize(MF_SOLVER(P, REAL)->stream)); MF_SOLVER(P, REAL)->check_halo_error(); })      \
     }                                                                                                                                     \
     extern "C" int mflbm_##P##_halo_buffers(mflbm_##P##_solver* s, int kind, int side, REAL** send, REAL** recv, int64_t* count) {        \
         MF_GUARD({                                                                                                                        \

@@ -179,32 +179,47 @@ class CudaSlab:
     def connect_p2p(self, dist, group=None) -> None:
         """Exchange CUDA IPC handles with the neighbour ranks (once) so that halo messages go through peer memory.
         Every rank exports the one allocation that holds its receive buffers and arrival flags; the offsets inside it are
-        the same on every rank that has the same y/z extents, but they are sent along anyway."""
+        the same on every rank that has the same y/z extents, but they are sent along anyway.  Collective: every rank
+        takes part in every step, and all of them fall back to NCCL send/recv together if any import fails."""
         import mflbm
+        import torch
         r = self.rng
         self.p2p = False
         if r.world == 1:
             return
-        base, nbytes = self.solver.halo_p2p_region()
-        mine = {"handle": mflbm.ipc_export(base), "offsets": {}}
-        for kind in (0, 1, 2):
-            for side in (LEFT, RIGHT):
-                recv, flag = self.solver.halo_p2p_local(kind, side)
-                mine["offsets"][(kind, side)] = (recv - base, flag - base)
+        mine, why = None, ""
+        try:
+            base, nbytes = self.solver.halo_p2p_region()
+            mine = {"handle": mflbm.ipc_export(base), "offsets": {}}
+            for kind in (0, 1, 2):
+                for side in (LEFT, RIGHT):
+                    recv, flag = self.solver.halo_p2p_local(kind, side)
+                    mine["offsets"][(kind, side)] = (recv - base, flag - base)
+        except Exception as e:
+            mine, why = None, str(e)
         everyone = [None] * r.world
         dist.all_gather_object(everyone, mine, group=group)
+        ok = 1 if mine is not None else 0
         self._peer_bases = {}
         for side, nb in ((LEFT, r.rank - 1), (RIGHT, r.rank + 1)):
-            if nb < 0 or nb >= r.world:
+            if not ok or nb < 0 or nb >= r.world:
                 continue
-            pbase = mflbm.ipc_import(everyone[nb]["handle"])
-            self._peer_bases[side] = pbase
-            opposite = RIGHT if side == LEFT else LEFT     # my left neighbour receives my message in ITS right-side buffer
-            for kind in (0, 1, 2):
-                orecv, oflag = everyone[nb]["offsets"][(kind, opposite)]
-                self.solver.halo_p2p_connect(kind, side, pbase + orecv, pbase + oflag)
-        dist.barrier(group=group)
-        self.p2p = True
+            try:
+                if everyone[nb] is None:
+                    raise RuntimeError(f"rank {nb} exported nothing")
+                pbase = mflbm.ipc_import(everyone[nb]["handle"])
+                self._peer_bases[side] = pbase
+                opposite = RIGHT if side == LEFT else LEFT     # my left neighbour receives my message in ITS right-side buffer
+                for kind in (0, 1, 2):
+                    orecv, oflag = everyone[nb]["offsets"][(kind, opposite)]
+                    self.solver.halo_p2p_connect(kind, side, pbase + orecv, pbase + oflag)
+            except Exception as e:
+                ok, why = 0, str(e)
+        flag = torch.tensor([ok], dtype=torch.int32, device=f"cuda:{torch.cuda.current_device()}")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        self.p2p = bool(int(flag[0]))
+        if not self.p2p and why:
+            print(f"[rank {r.rank}] peer-memory halo transport unavailable ({why}); using NCCL send/recv", flush=True)
 
     def halo_push(self, kind):
         self.solver.halo_push(kind)
