@@ -35,9 +35,12 @@ template <typename T> __host__ __device__ constexpr T w_equ(int q) { return q ==
 //        u(x,y,z) = (x+3) + PX*((y+3) + PY*(z+3)),   neighbour in direction q = u + ex + PX*(ey + PY*ez).
 //    The reference keeps four different ghost widths (0/1/2/4) and hence four index spaces; one space means a kernel
 //    decodes a site once and every stencil offset is the same constant for every field.
-//  * PDFs: struct-of-arrays over the 38 slots like the reference (slot = e + 19*g), but the SITE order inside a slot
-//    is permuted: the n_fluid real fluid nodes first (in z,y,x order), then every other site of the 1-ghost box.
-//        pdf[(q + 19*g)*NC + cmap[u]]
+//  * PDFs: struct-of-arrays over the 19 directions; the two components of a direction sit side by side,
+//        pdf[2*(q*NC + cmap[u]) + g]          (g = 0, 1: the reference's slots q and q + 19)
+//    because every kernel that touches a population touches both components of it: one 8/16-byte request moves the
+//    pair, which halves the number of gather (LDGSTS) and scatter (STG) requests of the odd step - the load/store pipe
+//    is what bounds that kernel.  The SITE order inside a direction row is permuted: the n_fluid
+//    real fluid nodes first (in z,y,x order), then every other site of the 1-ghost box.
 //    The collide kernels run one thread per entry of the fluid range: warps are full, the even (local) step reads and
 //    writes perfectly contiguous, aligned rows, and no DRAM sector is shared between fluid and solid sites.  Solid
 //    and ghost sites keep their storage (the reference realises bounce-back through it).
@@ -54,6 +57,10 @@ template <typename T> __host__ __device__ constexpr T w_equ(int q) { return q ==
 //    at the reference's addresses.
 //  * curv is not stored: the collide kernel (and the monitor) evaluate it from cn_* where it is consumed; the
 //    reference's dense curv array is produced on demand by download_state.
+// the two components of one population
+template <typename T>
+struct alignas(2 * sizeof(T)) Pair { T a, b; };
+
 template <typename T>
 struct Lattice {
     int nx, ny, nz;          // real nodes of this lattice (slab-local nx)
@@ -84,7 +91,8 @@ struct Lattice {
     __device__ __forceinline__ int off(int q) const { return ex(q) + sy * ey(q) + sz * ez(q); }
     __device__ __forceinline__ int iplane(int x, int y) const { return x + NX1 * y; }          // W_in, *_convec
     __device__ __forceinline__ bool solid(int uu) const { return types[uu] > 0; }
-    __device__ __forceinline__ T* slot(int q, int g) const { return pdf + (long long)(q + 19 * g) * NC; }
+    __device__ __forceinline__ T& at(int q, int g, long long entry) const { return pdf[(((long long)q * NC + entry) << 1) + g]; }
+    __device__ __forceinline__ Pair<T>* pairs(int q) const { return reinterpret_cast<Pair<T>*>(pdf) + (long long)q * NC; }
     __device__ __forceinline__ static int entry_of(int c) { return c >= 0 ? c : -c - 2; }
     // entry of the mailbox of link (fluid entry t, direction o) in slot opc(o); slow path (walks the 32-entry group),
     // for the plane kernels and layout conversion only
@@ -103,15 +111,15 @@ struct Lattice {
     // PDF of slot (q,g) at the site with U index uu (must lie in the 1-ghost box), wherever it is stored
     __device__ __forceinline__ T& f(int q, int g, int uu) const {
         const int c = cmap[uu];
-        if (c >= 0) return pdf[(long long)(q + 19 * g) * NC + c];
+        if (c >= 0) return at(q, g, c);
         if (q != 0) {   // solid-type site: the cell may be the private mailbox of the fluid node at uu + e_q
             const int co = cmap[uu + off(q)];
-            if (co >= 0 && co < n_fluid) return pdf[(long long)(q + 19 * g) * NC + mail_index(co, opc(q))];
+            if (co >= 0 && co < n_fluid) return at(q, g, mail_index(co, opc(q)));
         }
-        return pdf[(long long)(q + 19 * g) * NC + (-c - 2)];
+        return at(q, g, -c - 2);
     }
     // the cell in slot storage proper, never a mailbox (x-slab halo columns, see k_halo_pdf)
-    __device__ __forceinline__ T& f_raw(int q, int g, int uu) const { return pdf[(long long)(q + 19 * g) * NC + entry_of(cmap[uu])]; }
+    __device__ __forceinline__ T& f_raw(int q, int g, int uu) const { return at(q, g, entry_of(cmap[uu])); }
 };
 
 // MRT relaxation rates, src/main_iteration_GPU.cu:157-186.  MRT is a template parameter so that the compiler folds

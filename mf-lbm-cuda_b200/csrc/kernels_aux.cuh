@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(256) k_monitor(const Lattice<T> L, const int* 
         const int u = L.fl_u[t];
         T ft[19];
 #pragma unroll
-        for (int q = 0; q < 19; q++) ft[q] = L.slot(q, 0)[t] + L.slot(q, 1)[t];
+        for (int q = 0; q < 19; q++) { const Pair<T> v = L.pairs(q)[t]; ft[q] = v.a + v.b; }
         T rho = ft[0];
 #pragma unroll
         for (int q = 1; q < 19; q++) rho = rho + ft[q];
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(128) k_macro(const Lattice<T> L, T* __restrict
     const int u = L.fl_u[t];
     T ft[19];
 #pragma unroll
-    for (int q = 0; q < 19; q++) ft[q] = L.slot(q, 0)[t] + L.slot(q, 1)[t];
+    for (int q = 0; q < 19; q++) { const Pair<T> v = L.pairs(q)[t]; ft[q] = v.a + v.b; }
     T rho = ft[0];
 #pragma unroll
     for (int q = 1; q < 19; q++) rho = rho + ft[q];

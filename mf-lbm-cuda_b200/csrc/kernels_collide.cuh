@@ -71,9 +71,6 @@ __device__ __forceinline__ void node_force(const Lattice<T>& L, const int u, con
     tmp = lit<T>(0.5) * L.lbm_gamma * curvature_at(L, u) * cnorm;   // :147
 }
 
-// odd kernel: D + 1 value stages, D + 2 index stages (18 map entries + link ranks), one site id and one c_norm per thread
-template <typename T, int D>
-constexpr size_t collide_odd_smem() { return (sizeof(T) * 38 * (D + 1) + sizeof(int) * 19 * (D + 2) + 2 * (sizeof(int) + sizeof(T))) * COLLIDE_TILE; }
 
 // ---------------------------------------------------------------------------------------------------------
 // EVEN step: f_q = local slot opc(q); collide; local slot q = f_q*     (:395-726)
@@ -94,7 +91,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 template <typename T, int MRT, int NST, int CTAS>
 __global__ void __launch_bounds__(COLLIDE_EVEN_THREADS, CTAS) k_collide_even_tma(const Lattice<T> L, const int ntiles, const int bulk_skip) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    typedef T Stage[38][COLLIDE_TILE];
+    typedef Pair<T> Stage[19][COLLIDE_TILE];
     Stage* buf = reinterpret_cast<Stage*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + sizeof(Stage) * NST);
     uint64_t* empty = full + NST;
@@ -111,7 +108,7 @@ __global__ void __launch_bounds__(COLLIDE_EVEN_THREADS, CTAS) k_collide_even_tma
     __syncthreads();
 
     if (tid >= COLLIDE_TILE) {
-        // ---- producer warp: lane l copies slot rows l and l + 32 of every tile of this CTA ----
+        // ---- producer warp: lane l < 19 copies the row of direction l (both components, 128 pairs) of every tile of this CTA ----
         const int lane = tid - COLLIDE_TILE;
         int s = 0;
         uint32_t phase = 0;   // parity of the empty-phase a refill of stage s has to see completed
@@ -119,9 +116,7 @@ __global__ void __launch_bounds__(COLLIDE_EVEN_THREADS, CTAS) k_collide_even_tma
         for (int tile = blockIdx.x; tile < ntiles; tile += stride, it++) {
             if (it >= NST) pipe::mbar_wait(&empty[s], phase);
             if (lane == 0) pipe::mbar_expect_tx(&full[s], (uint32_t)sizeof(Stage));
-            const T* src = L.pdf + (long long)tile * COLLIDE_TILE;
-            pipe::bulk_g2s(&buf[s][lane][0], src + (long long)lane * NC, (uint32_t)(sizeof(T) * COLLIDE_TILE), &full[s]);
-            if (lane < 6) pipe::bulk_g2s(&buf[s][lane + 32][0], src + (long long)(lane + 32) * NC, (uint32_t)(sizeof(T) * COLLIDE_TILE), &full[s]);
+            if (lane < 19) pipe::bulk_g2s(&buf[s][lane][0], L.pairs(lane) + (long long)tile * COLLIDE_TILE, (uint32_t)(sizeof(Pair<T>) * COLLIDE_TILE), &full[s]);
             if (++s == NST) { s = 0; if (it >= NST) phase ^= 1; }
         }
         return;
@@ -158,7 +153,7 @@ __global__ void __launch_bounds__(COLLIDE_EVEN_THREADS, CTAS) k_collide_even_tma
         pipe::mbar_wait(&full[s], phase);
         T g1[19], g2[19];
 #pragma unroll
-        for (int q = 0; q < 19; q++) { g1[q] = buf[s][opc(q)][tid]; g2[q] = buf[s][opc(q) + 19][tid]; }
+        for (int q = 0; q < 19; q++) { const Pair<T> v = buf[s][opc(q)][tid]; g1[q] = v.a; g2[q] = v.b; }
         // The columns must BE in registers before the stage is released: an LDS that is merely issued can still be queued
         // in the shared-memory pipe when the arrive below becomes visible, and the refill then overwrites what it was
         // about to read (seen once per ~10^5 warp-tiles at 256^3).  An empty asm that consumes the values makes the
@@ -177,9 +172,9 @@ __global__ void __launch_bounds__(COLLIDE_EVEN_THREADS, CTAS) k_collide_even_tma
                 __syncwarp(live_mask);
                 if ((tid & 31) == leader) mbar_arrive(bar);
             });
-            T* __restrict__ po = L.pdf + t;
+            Pair<T>* __restrict__ po = L.pairs(0) + t;
 #pragma unroll
-            for (int q = 0; q < 19; q++) { po[(long long)q * NC] = g1[q]; po[(long long)(q + 19) * NC] = g2[q]; }
+            for (int q = 0; q < 19; q++) po[(long long)q * NC] = Pair<T>{g1[q], g2[q]};
         } else if (live_mask == 0u && (tid & 31) == 0) {
             mbar_arrive(&empty[s]);   // a warp past the last fluid entry
         }
@@ -189,158 +184,11 @@ __global__ void __launch_bounds__(COLLIDE_EVEN_THREADS, CTAS) k_collide_even_tma
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// ODD step: f_q pulled from x - e_q (slot q); collide; f_q* pushed to x + e_q (slot opc(q))     (:56-388)
-// D = how many tiles ahead the PDF gathers are issued (D + 1 value stages, D + 2 index stages).
-//
-// Per iteration k of a CTA (tiles k, k+1, ... are the CTA's own tiles, `stride` apart):
-//   wait     index(k+D) has landed                                   (cp.async group B of iteration k-1)
-//   resolve  map entries of tile k+D -> slot entries (wall links -> mailbox entries), parked for the scatter
-//   issue    index(k+D+1): 18 map entries per thread, cp.async 4 B   (group B_k)
-//   issue    gathers(k+D): 38 PDFs per thread, cp.async 4/8 B        (group A_k)
-//   wait     gathers(k) have landed;  collide tile k;  scatter through the parked entries of tile k
-// Nothing a later tile needs is held in registers across the collision (the plain-load version kept 18 map entries
-// live and ptxas tied constant-bank reloads to the scoreboard of the outstanding loads: 28 % of all stall samples).
-// ---------------------------------------------------------------------------------------------------------
-template <typename T, int MRT, int D, int CTAS>
-__global__ void __launch_bounds__(COLLIDE_TILE, CTAS) k_collide_odd_pipe(const Lattice<T> L, const int ntiles, const int bulk_skip) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int NST = D + 1, NNB = D + 2;
-    typedef T Stage[38][COLLIDE_TILE];
-    typedef int NbStage[18][COLLIDE_TILE];
-    Stage* vals = reinterpret_cast<Stage*>(smem_raw);
-    NbStage* nbS = reinterpret_cast<NbStage*>(smem_raw + sizeof(Stage) * NST);
-    typedef int WbStage[COLLIDE_TILE / 32][32];
-    WbStage* wbS = reinterpret_cast<WbStage*>(smem_raw + sizeof(Stage) * NST + sizeof(NbStage) * NNB);
-    // [2][tile] each, one half read while the other is being filled: c_norm of my entry in the next tile, site id D + 2 tiles ahead
-    T* cS = reinterpret_cast<T*>(smem_raw + sizeof(Stage) * NST + (sizeof(NbStage) + sizeof(WbStage)) * NNB);
-    int* uS = reinterpret_cast<int*>(cS + 2 * COLLIDE_TILE);
-    const int tid = threadIdx.x;
-    const long long NC = L.NC;
-    const int stride = gridDim.x;
-    const T* __restrict__ p0 = L.pdf;
-    const int* __restrict__ cmap = L.cmap;
-    const unsigned lanes_below = (1u << (tid & 31)) - 1u;
-
-    // site id of my entry in a tile (-1: no such entry)
-    auto site = [&](const int tile) -> int {
-        const int t = tile * COLLIDE_TILE + tid;
-        return (tile < ntiles && t < L.n_fluid) ? L.fl_u[t] : -1;
-    };
-    // raw map entries of my 18 neighbours -> my column of index stage sb, link ranks of my warp's 32-entry group ->
-    // lanes 0..17.  Rides in the same group: the site id of my entry in tile `tile_site` and the c_norm at site u_cn (the
-    // next tile's).  As cp.async none of these occupies a scoreboard: the collision's division subroutine is a real CALL
-    // and a call waits for every outstanding load (23 % of all stall samples sat there, profiles/r01d_*_stalls.txt).
-    // Always commits one group.
-    auto issue_index = [&](const int tile, const int u, const int sb, const int tile_site, const int u_cn, const int slot) {
-        if (tile < ntiles && (tid & 31) < 18)
-            pipe::cp_async<4>(&wbS[sb][tid >> 5][tid & 31], L.wbase + ((tile * (COLLIDE_TILE / 32) + (tid >> 5)) * 18 + (tid & 31)));
-        if (u >= 0) {
-#pragma unroll
-            for (int q = 1; q < 19; q++) pipe::cp_async<4>(&nbS[sb][q - 1][tid], cmap + (u + L.off(q)));
-        }
-        if (tile_site < ntiles && tile_site * COLLIDE_TILE + tid < L.n_fluid) pipe::cp_async<4>(&uS[slot * COLLIDE_TILE + tid], L.fl_u + (tile_site * COLLIDE_TILE + tid));
-        if (u_cn >= 0) pipe::cp_async<sizeof(T)>(&cS[slot * COLLIDE_TILE + tid], L.c_norm + u_cn);
-        pipe::cp_async_commit();
-    };
-    // slot entries of the 18 neighbour cells: the map entry itself for a non-solid neighbour, the mailbox entry
-    // mb0 + rank for a wall link (core.cuh).  Whole warps (`tile` is warp-uniform); parked in place for the scatter.
-    auto resolve_index = [&](const int tile, const int u, const int sb, int (&nb)[18]) {
-        if (tile >= ntiles) return;
-        const int wb = (tid & 31) < 18 ? wbS[sb][tid >> 5][tid & 31] : 0;
-#pragma unroll
-        for (int q = 1; q < 19; q++) {
-            const int c = u >= 0 ? nbS[sb][q - 1][tid] : 0;
-            const unsigned walls = __ballot_sync(0xffffffffu, c < 0);
-            const int base = __shfl_sync(0xffffffffu, wb, q - 1);
-            nb[q - 1] = c >= 0 ? c : L.mb0 + base + __popc(walls & lanes_below);
-            if (c < 0) nbS[sb][q - 1][tid] = nb[q - 1];
-        }
-    };
-    // the 38 gathers of a tile; always commits one group
-    auto issue_gather = [&](const int tile, const int u, const int (&nb)[18], const int st) {
-        if (u >= 0) {
-            const int t = tile * COLLIDE_TILE + tid;
-#pragma unroll
-            for (int q = 0; q < 19; q++) {
-                const int src = (q == 0) ? t : nb[opc(q) - 1];   // x - e_q = x + e_opc(q), slot q there
-                pipe::cp_async<sizeof(T)>(&vals[st][q][tid], p0 + (long long)q * NC + src);
-                pipe::cp_async<sizeof(T)>(&vals[st][q + 19][tid], p0 + (long long)(q + 19) * NC + src);
-            }
-        }
-        pipe::cp_async_commit();
-    };
-
-    int tile = blockIdx.x;
-    // ring of my site ids: uR[j] belongs to tile + j*stride, j = 0 .. D+1 (uR[D+1] arrives through uS at the loop top)
-    int uR[D + 2];
-#pragma unroll
-    for (int j = 0; j < D + 1; j++) uR[j] = site(tile + j * stride);
-    uR[D + 1] = -1;
-    // prologue: index + gathers of my first D tiles (groups B, A per tile, as in the loop), index of tile D together
-    // with what the first iteration picks up from uS / cS
-    int nb[18];
-#pragma unroll
-    for (int j = 0; j < D; j++) {
-        issue_index(tile + j * stride, uR[j], j % NNB, ntiles, -1, 0);
-        pipe::cp_async_wait<0>();
-        resolve_index(tile + j * stride, uR[j], j % NNB, nb);
-        issue_gather(tile + j * stride, uR[j], nb, j % NST);
-    }
-    issue_index(tile + D * stride, uR[D], D % NNB, tile + (D + 1) * stride, uR[0], 0);
-    pipe::cp_async_commit();   // keeps the group pattern of the loop: (B, A) per iteration
-    int slot = 0;              // the (cS, uS) half this iteration reads
-
-    int st = 0, sb = 0;   // value / index stage of the current tile
-    for (; tile < ntiles; tile += stride) {
-        int stD = st + D; if (stD >= NST) stD -= NST;
-        int sbD = sb + D; if (sbD >= NNB) sbD -= NNB;
-        int sbD1 = sbD + 1; if (sbD1 >= NNB) sbD1 -= NNB;
-        pipe::cp_async_wait<1>();   // index(tile + D) has landed (all but the newest group, the gathers of tile + D - 1)
-        const int t = tile * COLLIDE_TILE + tid;
-        const int u = uR[0];
-        const bool live = u >= 0;
-        {   // what rode in that group: my site in tile + D + 1 and the c_norm of this tile's site
-            const int tl = tile + (D + 1) * stride;
-            uR[D + 1] = (tl < ntiles && tl * COLLIDE_TILE + tid < L.n_fluid) ? uS[slot * COLLIDE_TILE + tid] : -1;
-        }
-        const T cnorm = live ? cS[slot * COLLIDE_TILE + tid] : T(0);
-        slot ^= 1;
-        resolve_index(tile + D * stride, uR[D], sbD, nb);
-        issue_index(tile + (D + 1) * stride, uR[D + 1], sbD1, tile + (D + 2) * stride, uR[1], slot);
-        issue_gather(tile + D * stride, uR[D], nb, stD);
-        T cnx = T(0), cny = T(0), cnz = T(0), tmp = T(0);
-        if (live) node_force(L, u, cnorm, bulk_skip != 0, cnx, cny, cnz, tmp);
-        pipe::cp_async_wait<2 * D>();   // all but the 2D newest groups: the gathers of this tile have landed
-        if (live) {
-            T g1[19], g2[19];
-#pragma unroll
-            for (int q = 0; q < 19; q++) { g1[q] = vals[st][q][tid]; g2[q] = vals[st][q + 19][tid]; }
-            const T phi_loc = collide_node<T, MRT>(L, g1, g2, cnx, cny, cnz, tmp);
-            L.phi[u] = phi_loc;
-            T* __restrict__ po = L.pdf;
-            po[t] = g1[0];
-            po[19 * NC + t] = g2[0];
-#pragma unroll
-            for (int q = 1; q < 19; q++) {
-                const int dst = nbS[sb][q - 1][tid];
-                po[(long long)opc(q) * NC + dst] = g1[q];
-                po[(long long)(opc(q) + 19) * NC + dst] = g2[q];
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < D + 1; j++) uR[j] = uR[j + 1];
-        if (++st == NST) st = 0;
-        if (++sb == NNB) sb = 0;
-    }
-    pipe::cp_async_wait<0>();
-}
-
-
-// ---------------------------------------------------------------------------------------------------------
-// ODD step, warp-specialised (the default).  The pipelined kernel above runs one warp per scheduler (255 registers, one
-// CTA per SM) and that warp issues everything - map look-ups, link ranks, 38 gather addresses, the collision, 38 scatter
-// addresses: ncu shows 0.27 eligible warps per scheduler and no dominant stall, i.e. plain issue latency.  Here a CTA is
-// 4 consumer warps + 4 producer warps over the same 128-entry tiles:
+// ODD step: f_q pulled from x - e_q (direction row q); collide; f_q* pushed to x + e_q (row opc(q))     (:56-388)
+// Neighbours are found through the site map, so rows are gathered per thread (no bulk copies).  Warp-specialised: a first
+// version had one warp per scheduler (255 registers, one CTA per SM) issue everything - map look-ups, link ranks, gather
+// addresses, the collision, scatter addresses - and ncu showed 0.27 eligible warps per scheduler with no dominant stall.
+// Here a CTA is 4 consumer warps + 4 producer warps over the same 128-entry tiles:
 //   producer thread p, tile i :  raw map entries (plain loads, one tile ahead) -> slot entries of the 18 neighbour cells
 //                                (wall links -> mailbox entries) -> stage.nb / stage.u ;  38 PDF gathers + c_norm with
 //                                cp.async into stage.val / stage.cn ;  completion is reported to full[stage] by
@@ -350,7 +198,7 @@ __global__ void __launch_bounds__(COLLIDE_TILE, CTAS) k_collide_odd_pipe(const L
 // ---------------------------------------------------------------------------------------------------------
 template <typename T>
 struct OddStage {
-    T val[38][COLLIDE_TILE];
+    Pair<T> val[19][COLLIDE_TILE];
     int nb[18][COLLIDE_TILE];
     T cn[COLLIDE_TILE];
     int u[COLLIDE_TILE];
@@ -394,7 +242,6 @@ __global__ void __launch_bounds__((NCONS + 1) * COLLIDE_TILE, CTAS) k_collide_od
         // load/store pipe 1.8 cycles against 8 for an LDGSTS.
         if (REGS_P > 0) reg_dealloc<REGS_P>();
         const int p = tid - NCONS * COLLIDE_TILE, lane = p & 31, w = p >> 5;
-        const T* __restrict__ p0 = L.pdf;
         const int* __restrict__ cmap = L.cmap;
         const unsigned lanes_below = (1u << lane) - 1u;
         auto site_of = [&](const int tl) -> int { return (tl < ntiles && tl * COLLIDE_TILE + p < L.n_fluid) ? __ldg(L.fl_u + (tl * COLLIDE_TILE + p)) : -1; };
@@ -420,9 +267,8 @@ __global__ void __launch_bounds__((NCONS + 1) * COLLIDE_TILE, CTAS) k_collide_od
             Stage& S = stg[st];
             const int t = tile * COLLIDE_TILE + p;
             const bool live = uCur >= 0;
-            if (live) {   // the rest populations: slot 0 / 19 at the node itself
-                pipe::cp_async<sizeof(T)>(&S.val[0][p], p0 + t);
-                pipe::cp_async<sizeof(T)>(&S.val[19][p], p0 + 19 * NC + t);
+            if (live) {   // the rest populations: direction 0 at the node itself
+                pipe::cp_async<sizeof(Pair<T>)>(&S.val[0][p], L.pairs(0) + t);
                 pipe::cp_async<sizeof(T)>(&S.cn[p], L.c_norm + uCur);
             }
             // slot entries of the 18 neighbour cells: the map entry itself for a non-solid neighbour, the mailbox entry
@@ -435,10 +281,7 @@ __global__ void __launch_bounds__((NCONS + 1) * COLLIDE_TILE, CTAS) k_collide_od
                 const int base = __shfl_sync(0xffffffffu, wb, q - 1);
                 const int nbq = cc >= 0 ? cc : L.mb0 + base + __popc(walls & lanes_below);
                 S.nb[q - 1][p] = nbq;
-                if (live) {   // x - e_s = x + e_q for s = opc(q): slot s there
-                    pipe::cp_async<sizeof(T)>(&S.val[opc(q)][p], p0 + (long long)opc(q) * NC + nbq);
-                    pipe::cp_async<sizeof(T)>(&S.val[opc(q) + 19][p], p0 + (long long)(opc(q) + 19) * NC + nbq);
-                }
+                if (live) pipe::cp_async<sizeof(Pair<T>)>(&S.val[opc(q)][p], L.pairs(opc(q)) + nbq);   // x - e_s = x + e_q for s = opc(q): row s there
             }
             S.u[p] = uCur;
             mbar_arrive(&full[st]);                  // release: nb / u are visible to whoever sees the phase complete
@@ -469,17 +312,14 @@ __global__ void __launch_bounds__((NCONS + 1) * COLLIDE_TILE, CTAS) k_collide_od
             node_force(L, u, cnorm, bulk_skip != 0, cnx, cny, cnz, tmp);
             T g1[19], g2[19];
 #pragma unroll
-            for (int q = 0; q < 19; q++) { g1[q] = S.val[q][ct]; g2[q] = S.val[q + 19][ct]; }
+            for (int q = 0; q < 19; q++) { const Pair<T> v = S.val[q][ct]; g1[q] = v.a; g2[q] = v.b; }
             const T phi_loc = collide_node<T, MRT>(L, g1, g2, cnx, cny, cnz, tmp);
             L.phi[u] = phi_loc;
-            T* __restrict__ po = L.pdf;
-            po[t] = g1[0];
-            po[19 * NC + t] = g2[0];
+            L.pairs(0)[t] = Pair<T>{g1[0], g2[0]};
 #pragma unroll
             for (int q = 1; q < 19; q++) {
                 const int dst = S.nb[q - 1][ct];
-                po[(long long)opc(q) * NC + dst] = g1[q];
-                po[(long long)(opc(q) + 19) * NC + dst] = g2[q];
+                L.pairs(opc(q))[dst] = Pair<T>{g1[q], g2[q]};
             }
         }
         // every value and every entry of the stage has been consumed by an issued store (see the even kernel)

@@ -571,15 +571,6 @@ struct Solver {
         if (configured != device) { MF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = device; }
         kern<<<collide_grid(ntiles, CTAS), COLLIDE_EVEN_THREADS, smem, stream>>>(L, ntiles, cn_consistent ? 1 : 0);
     }
-    template <int MRT, int D, int CTAS>
-    void launch_odd() {
-        const int ntiles = ceil_div((int)n_fluid, COLLIDE_TILE);
-        auto kern = k_collide_odd_pipe<T, MRT, D, CTAS>;
-        constexpr size_t smem = collide_odd_smem<T, D>();
-        static thread_local int configured = -1;
-        if (configured != device) { MF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = device; }
-        kern<<<collide_grid(ntiles, CTAS), COLLIDE_TILE, smem, stream>>>(L, ntiles, cn_consistent ? 1 : 0);
-    }
     template <int MRT, int NST, int CTAS, int NCONS = 1, int REGS_P = 0, int REGS_C = 0>
     void launch_odd_ws() {
         const int ntiles = ceil_div((int)n_fluid, COLLIDE_TILE);
@@ -604,14 +595,12 @@ struct Solver {
                 if (odd && o == 1) launch_odd_ws<MRT, 2, 1>();
                 else if (odd && o == 2) launch_odd_ws<MRT, 4, 1>();
                 else if (odd && o == 3) launch_odd_ws<MRT, 4, 1, 2, 72, 216>();   // two consumer warpgroups, registers moved with setmaxnreg
-                else if (odd && o == 4) launch_odd<MRT, 2, 1>();                  // the pipelined kernel before warp specialisation
                 else if (!odd && e == 1) launch_even<MRT, 3, 1>();
                 else done = false;
             } else {
                 if (odd && o == 1) launch_odd_ws<MRT, 3, 1>();
                 else if (odd && o == 2) launch_odd_ws<MRT, 2, 2>();
                 else if (odd && o == 3) launch_odd_ws<MRT, 4, 1, 2>();
-                else if (odd && o == 4) launch_odd<MRT, 2, 2>();
                 else if (!odd && e == 1) launch_even<MRT, 8, 1>();
                 else if (!odd && e == 2) launch_even<MRT, 2, 4>();
                 else done = false;
