@@ -598,8 +598,8 @@ struct Solver {
                 else if (!odd && e == 1) launch_even<MRT, 3, 1>();
                 else done = false;
             } else {
-                if (odd && o == 1) launch_odd_ws<MRT, 3, 1>();
-                else if (odd && o == 2) launch_odd_ws<MRT, 2, 2>();
+                if (odd && o == 1) launch_odd_ws<MRT, 4, 1>();
+                else if (odd && o == 2) launch_odd_ws<MRT, 3, 2>();
                 else if (odd && o == 3) launch_odd_ws<MRT, 4, 1, 2>();
                 else if (!odd && e == 1) launch_even<MRT, 8, 1>();
                 else if (!odd && e == 2) launch_even<MRT, 2, 4>();
@@ -608,7 +608,7 @@ struct Solver {
         }
         if (!done) {
             if constexpr (sizeof(T) == 8) { if (odd) launch_odd_ws<MRT, 3, 1>(); else launch_even<MRT, 2, 2>(); }
-            else { if (odd) launch_odd_ws<MRT, 4, 1>(); else launch_even<MRT, 4, 2>(); }
+            else { if (odd) launch_odd_ws<MRT, 2, 2>(); else launch_even<MRT, 4, 2>(); }
         }
         check_launch(); count();
     }
