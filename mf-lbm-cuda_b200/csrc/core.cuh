@@ -49,8 +49,8 @@ template <typename T> __host__ __device__ constexpr T w_equ(int q) { return q ==
 //    cell (its only reader and writer is the node at s + e_slot = x).  At porosity 0.44 there are 1.2 such links per
 //    fluid node, and as isolated 4/8-byte accesses into solid storage they cost a third of the odd step's DRAM traffic
 //    (32 B sector fetched for the read, fetched again to merge the partial write).  They live in a compact region at
-//    the END of the slot instead: entry mb0 + rank_o(x) of slot opc(o) (the slot the cell has in the reference; a slot
-//    only ever hosts links of one direction), rank_o = number of fluid entries before x that have a link in direction
+//    the END of the direction row instead: entry mb0 + rank_o(x) of row opc(o) (the slot the cell has in the reference; a
+//    row only ever hosts links of one direction), rank_o = number of fluid entries before x that have a link in direction
 //    o, = wbase[(t>>5)*18 + o-1] + popc(ballot & lanes below) inside the odd kernel.  Consecutive threads hit
 //    consecutive elements, and a wall link is addressed exactly like a fluid neighbour (slot base + entry).  Every
 //    other kernel reaches the same cells through Lattice::f(); the arrays handed back by download_state place them

@@ -402,7 +402,7 @@ struct HaloSync {
     unsigned* seq;       // my message counter for this (kind, side)
     unsigned* error;     // unpack only: set to 1 + kind*2 + side when a message did not arrive within HALO_TIMEOUT_CYCLES
 };
-constexpr long long HALO_TIMEOUT_CYCLES = 20000000000LL;   // ~10 s at 2 GHz: a dead neighbour must not hang this GPU for ever
+constexpr long long HALO_TIMEOUT_CYCLES = 120000000000LL;   // ~60 s at 2 GHz: a dead neighbour must not hang this GPU for ever
 __device__ __forceinline__ void halo_publish(const HaloSync& hs) {
     if (!hs.flag) return;
     __threadfence_system();
