@@ -5,7 +5,9 @@
 
 Workload (BASELINE.json configs[1]): synthetic SxSxS random sphere pack (S=256, porosity ~0.4, radius 12), drainage,
 velocity inlet + convective outlet, contact angle 45 deg, FP64.  For N > 1 the lattice is (S*N) x S x S cut into N
-x-slabs (weak scaling), PDF/phi halos exchanged with NCCL send/recv between neighbours.
+x-slabs (weak scaling; BASELINE configs[4] is --size 512), PDF/phi halos pushed into the neighbour's memory over NVLink
+(--halo nccl: NCCL send/recv).  --global-nx NX fixes the lattice at NX x S x S for every N (strong scaling; BASELINE
+configs[3] is --global-nx 1024 --size 512).
 
 One JSON line on stdout (rank 0).  `value` = MLUPS with the reference's definition nx*ny*nz*steps/1e6/s
 (/root/reference/src/main.cpp:270), state resident in HBM; `e2e` = the same through the C ABI starting from pinned
@@ -203,10 +205,10 @@ def run_ours(args) -> dict:
         from mflbm import slab as slabmod
         return slabmod.bench_slabs(args, rank, world, local)
     S = args.size
+    NX = args.global_nx or S
     prec = args.prec
-    rt = np.float64 if prec == "f64" else np.float32
-    ctl = workload_control(S, S, S)
-    solid = workload_geometry(S, S, S, kind=args.geometry)
+    ctl = workload_control(NX, S, S)
+    solid = workload_geometry(NX, S, S, kind=args.geometry)
     stream = torch.cuda.Stream()
     solver = mflbm.Solver(mflbm.derive_params(ctl, prec), prec, device=local, stream=stream.cuda_stream)
     t0 = time.perf_counter()
@@ -214,7 +216,8 @@ def run_ours(args) -> dict:
     t_geo = time.perf_counter() - t0
     W = inlet_profile(ctl, prec)
     solver.init_state(1, ctl["initial_interface_position"], W_in=W)
-    n_fluid, n_site = solver.num_fluid_nodes, S ** 3
+    n_fluid, n_site = solver.num_fluid_nodes, NX * S * S
+    dims = f"{S}^3" if NX == S else f"{NX}x{S}x{S}"
     # ---- device-resident timing -------------------------------------------------------------------
     solver.run(1, args.warmup)
     solver.sync()
@@ -262,7 +265,7 @@ def run_ours(args) -> dict:
     tf = REPO / "profiles" / "traffic.json"
     if tf.exists():
         try:
-            traffic = json.loads(tf.read_text()).get(f"{prec}_{S}", None)
+            traffic = json.loads(tf.read_text()).get(f"{prec}_{S}", None) if NX == S else None
         except Exception:
             traffic = None
     # ---- end to end through the C ABI with host buffers ---------------------------------------------
@@ -285,11 +288,12 @@ def run_ours(args) -> dict:
         d2h = h2d + 11 * 8 * S
     out = {
         "metric": "multiphase MLUPS (all lattice sites, reference definition src/main.cpp:270)", "value": mlups, "unit": "MLUPS",
-        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong" if args.global_nx else "weak",
         "vs_baseline": None, "dtype": prec, "data": "synthetic",
-        "config": {"workload": (f"{S}^3 random sphere pack (radius 12, porosity ~0.4)" if args.geometry == "pack" else f"DIAGNOSTIC {S}^3 empty duct") +
+        "config": {"workload": (f"{dims} random sphere pack (radius 12, porosity ~0.4)" if args.geometry == "pack" else f"DIAGNOSTIC {dims} empty duct") +
                                f", drainage, velocity inlet + convective outlet, theta 45, {prec}",
-                   "lattice": [S, S, S], "fluid_nodes": n_fluid, "porosity": n_fluid / n_site, "parallelism": "1 GPU",
+                   "lattice": [NX, S, S], "fluid_nodes": n_fluid, "porosity": n_fluid / n_site, "parallelism": "1 GPU",
                    "l2": f"state {(38 * s_bytes * n_fluid) / 1e9:.2f}+ GB >> 126 MB L2 (inputs larger than L2, no flush needed)",
                    "fluid_mlups": n_fluid * args.steps / 1e6 / (ms * 1e-3), "geometry_preprocess_s": t_geo,
                    "saturation_full_domain": mon2["saturation_full_domain"]},
@@ -321,15 +325,17 @@ def run_reference(args) -> dict:
     if rank != 0:
         sys.exit(0)
     S, prec = args.size, args.prec
+    NX = args.global_nx or S
+    dims = f"{S}^3" if NX == S else f"{NX}x{S}x{S}"
     exe = rc.ref_binary("gpu", prec)
     base = {"impl": "reference", "metric": "multiphase MLUPS (all lattice sites, reference definition src/main.cpp:270)", "unit": "MLUPS",
-            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": prec, "data": "synthetic"}
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "strong" if args.global_nx else "weak",
+            "vs_baseline": None, "dtype": prec, "data": "synthetic"}
     if not exe.exists():
         base["unavailable"] = f"{exe} missing (oracle/build_ref.sh needs /root/reference)"
         return base
-    ctl = workload_control(S, S, S)
-    solid = workload_geometry(S, S, S)
+    ctl = workload_control(NX, S, S)
+    solid = workload_geometry(NX, S, S)
     solid_file = solid.copy()   # the reference applies the x/y walls itself (src/Misc.cpp:67-78); harmless to pre-apply
     with tempfile.TemporaryDirectory() as td:
         td = Path(td)
@@ -341,7 +347,7 @@ def run_reference(args) -> dict:
         host = dict(l.split() for l in (out / "host_timing.txt").read_text().splitlines())
     mlups = float(tim["mlups"])
     base.update({"value": mlups, "ms_per_step": float(tim["ms_per_step"]),
-                 "config": {"workload": f"{S}^3 random sphere pack (radius 12, porosity ~0.4), drainage, velocity inlet + convective outlet, theta 45, {prec}",
+                 "config": {"workload": f"{dims} random sphere pack (radius 12, porosity ~0.4), drainage, velocity inlet + convective outlet, theta 45, {prec}",
                             "what": "reference CUDA kernels (unmodified sources, nvcc sm_100 -O3, block 128x1x1) via main_iteration_kernel_GPU()",
                             "host_setup_s": float(host["initialization_basic_multi_s"]), "wall_s": wall},
                  "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": 1, "kind": "reference",
@@ -356,7 +362,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2000, help="timed steps (BASELINE configs 2/3: 2 k timed steps after 100 warm-up)")
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--prec", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--size", type=int, default=256, help="S: the lattice is S^3 per GPU (weak scaling)")
+    ap.add_argument("--global-nx", type=int, default=0, help="strong scaling: the lattice is NX x S x S whatever the number of GPUs")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")

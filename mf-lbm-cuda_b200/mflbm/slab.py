@@ -265,7 +265,8 @@ def bench_slabs(args, rank: int, world: int, local: int) -> dict | None:
     import bench as B
     import mflbm
     S, prec = args.size, args.prec
-    nxg = S * world
+    strong = int(getattr(args, "global_nx", 0) or 0)
+    nxg = strong if strong else S * world      # strong scaling: fixed NX x S x S lattice; weak: S^3 per GPU
     ctl = B.workload_control(nxg, S, S)
     rng = partition(nxg, world, rank)
     params = mflbm.derive_params(ctl, prec)
@@ -305,27 +306,29 @@ def bench_slabs(args, rank: int, world: int, local: int) -> dict | None:
         n_fluid = int(nf[0])
         mon = reduce_monitor(slab.solver.monitor(), rng, params, dist, device=f"cuda:{local}")
         # ---- end to end through the C ABI: pinned host state -> device, K steps, monitor + state back ----------
-        st = slab.solver.download_state()
-        pinned = {k: torch.from_numpy(v).pin_memory() for k, v in st.items()}
-        host = {k: v.numpy() for k, v in pinned.items()}
-        h2d = sum(v.nbytes for v in host.values())
-        torch.cuda.synchronize()
-        dist.barrier()
-        t0 = time.perf_counter()
-        slab.solver.upload_state(**{k: host[k] for k in ("pdf", "phi", "cn_x", "cn_y", "cn_z", "c_norm", "curv")},
-                                 f_convec=host.get("f_convec"), g_convec=host.get("g_convec"), phi_convec=host.get("phi_convec"))
-        t1 = time.perf_counter()
-        stepper.run(nt, args.steps)
-        t2 = time.perf_counter()
-        reduce_monitor(slab.solver.monitor(), rng, params, dist, device=f"cuda:{local}")
-        t3 = time.perf_counter()
-        slab.solver.download_state_into(host)
-        torch.cuda.synchronize()
-        if os.environ.get("MFLBM_BENCH_DEBUG"):
-            print(f"[rank {rank}] e2e: upload {t1 - t0:.3f} s, run (enqueue) {t2 - t1:.3f} s, monitor {t3 - t2:.3f} s, download {time.perf_counter() - t3:.3f} s", file=sys.stderr, flush=True)
-        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        t_e2e = float(te[0])
+        h2d, t_e2e = 0, None
+        if not getattr(args, "no_e2e", False):
+            st = slab.solver.download_state()
+            pinned = {k: torch.from_numpy(v).pin_memory() for k, v in st.items()}
+            host = {k: v.numpy() for k, v in pinned.items()}
+            h2d = sum(v.nbytes for v in host.values())
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            slab.solver.upload_state(**{k: host[k] for k in ("pdf", "phi", "cn_x", "cn_y", "cn_z", "c_norm", "curv")},
+                                     f_convec=host.get("f_convec"), g_convec=host.get("g_convec"), phi_convec=host.get("phi_convec"))
+            t1 = time.perf_counter()
+            stepper.run(nt, args.steps)
+            t2 = time.perf_counter()
+            reduce_monitor(slab.solver.monitor(), rng, params, dist, device=f"cuda:{local}")
+            t3 = time.perf_counter()
+            slab.solver.download_state_into(host)
+            torch.cuda.synchronize()
+            if os.environ.get("MFLBM_BENCH_DEBUG"):
+                print(f"[rank {rank}] e2e: upload {t1 - t0:.3f} s, run (enqueue) {t2 - t1:.3f} s, monitor {t3 - t2:.3f} s, download {time.perf_counter() - t3:.3f} s", file=sys.stderr, flush=True)
+            te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            t_e2e = float(te[0])
     n_site = nxg * S * S
     s_bytes = 8 if prec == "f64" else 4
     bytes_step = 78 * s_bytes * n_fluid + n_site
@@ -338,15 +341,15 @@ def bench_slabs(args, rank: int, world: int, local: int) -> dict | None:
         out = {
             "metric": "multiphase MLUPS (all lattice sites, reference definition src/main.cpp:270)", "value": n_site * args.steps / 1e6 / (ms * 1e-3),
             "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": prec, "data": "synthetic",
-            "config": {"workload": f"{nxg}x{S}x{S} random sphere pack (radius 12, porosity ~0.4) = {S}^3 per GPU, drainage, velocity inlet + convective outlet, theta 45, {prec}",
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": prec, "data": "synthetic",
+            "config": {"workload": f"{nxg}x{S}x{S} random sphere pack (radius 12, porosity ~0.4)" + ("" if strong else f" = {S}^3 per GPU") + f", drainage, velocity inlet + convective outlet, theta 45, {prec}",
                        "lattice": [nxg, S, S], "fluid_nodes": n_fluid, "porosity": n_fluid / n_site, "parallelism": f"{world} x-slabs, halos " + ("pushed into peer memory over NVLink (CUDA IPC), arrival flags, no collective" if getattr(slab, "p2p", False) else "NCCL send/recv"),
                        "l2": "state per GPU >> 126 MB L2 (inputs larger than L2, no flush needed)",
                        "fluid_mlups": n_fluid * args.steps / 1e6 / (ms * 1e-3), "geometry_preprocess_s": t_geo,
                        "saturation_full_domain": mon["saturation_full_domain"], "halo_exchanges_per_step": 2},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src, "bytes_model": "78*sizeof(real)*N_fluid + N_site per step, per GPU", "bytes_per_step": bytes_step / world},
-            "e2e": {"value": n_site * args.steps / 1e6 / t_e2e, "unit": "MLUPS", "h2d_bytes_per_step": h2d * world / args.steps,
+            "e2e": {"value": n_site * args.steps / 1e6 / t_e2e if t_e2e else None, "unit": "MLUPS", "h2d_bytes_per_step": h2d * world / args.steps,
                     "d2h_bytes_per_step": h2d * world / args.steps,
                     "what": "per rank: upload_state from pinned host + K steps + monitor (all_reduce) + download_state, through the C ABI"},
             "gpu_launches": int(launches) * world,
