@@ -296,7 +296,7 @@ def run_ours(args) -> dict:
                    "lattice": [NX, S, S], "fluid_nodes": n_fluid, "porosity": n_fluid / n_site, "parallelism": "1 GPU",
                    "l2": f"state {(38 * s_bytes * n_fluid) / 1e9:.2f}+ GB >> 126 MB L2 (inputs larger than L2, no flush needed)",
                    "fluid_mlups": n_fluid * args.steps / 1e6 / (ms * 1e-3), "geometry_preprocess_s": t_geo,
-                   "saturation_full_domain": mon2["saturation_full_domain"]},
+                   "saturation_full_domain": mon2["saturation_full_domain"], "activity_map": solver.activity},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "kernel": "collide (k_collide_odd_ws / k_collide_even_tma, one launch per step)",
                      "bytes_model": "77*sizeof(real)*N_fluid per collide launch (38 PDF reads + 38 PDF writes + phi write)",
@@ -368,9 +368,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="N > 1: halo messages through peer memory (default) or NCCL send/recv")
+    ap.add_argument("--activity", type=int, default=None, choices=[0, 1],
+                    help="gradient chain with the interface-activity map (kernels_activity.cuh); default: the library's (MFLBM_ACTIVITY)")
     ap.add_argument("--geometry", default="pack", choices=["pack", "open"], help="open = empty duct, diagnostic only (not the benchmark workload)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.activity is not None:
+        os.environ["MFLBM_ACTIVITY"] = str(args.activity)   # read by the library when a solver is created
     if args.impl == "reference":
         out = run_reference(args)
     else:

@@ -15,6 +15,7 @@
 #include "kernels_step.cuh"
 #include "kernels_collide.cuh"
 #include "kernels_gradient.cuh"
+#include "kernels_activity.cuh"
 #include "kernels_aux.cuh"
 
 namespace mflbm {
@@ -66,6 +67,11 @@ struct Solver {
     unsigned char* d_live_u = nullptr;                         // the same per U site, for the tiled normals kernel
     unsigned char* d_near = nullptr;                           // per U site: a neighbour got a non-zero normal in this chain (kernels_step.cuh)
     int grad_tx = 0;                                           // x extent of its tiles
+    // interface-activity map (kernels_activity.cuh), opt-in with MFLBM_ACTIVITY=1
+    bool activity = false;
+    ActGrid act{};
+    unsigned char *d_act_raw = nullptr, *d_act_quiet = nullptr;   // [2][bricks] P | M flags of one chain; [bricks] verdict
+    int *d_brick_n = nullptr, *d_brick_cn = nullptr;              // brick of every entry of d_list_n / d_list_cn
     int n_list_phi = 0, n_list_cn = 0, n_list_alter = 0, n_list_alter_all = 0, n_list_n = 0;
     long long counts[4] = {0, 0, 0, 0};
     long long n_fluid = 0;
@@ -121,6 +127,7 @@ struct Solver {
         device = dev;
         if (const char* v = getenv("MFLBM_VARIANT")) variant = atoi(v);
         if (const char* v = getenv("MFLBM_MAX_CTAS")) max_ctas = atoi(v);
+        if (const char* v = getenv("MFLBM_ACTIVITY")) activity = atoi(v) != 0;
         MF_CUDA(cudaSetDevice(device));
         MF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
         if (strm) { stream = (cudaStream_t)strm; own_stream = false; }
@@ -193,6 +200,7 @@ struct Solver {
         dfree(d_list_phi); dfree(d_mask_phi); dfree(d_list_cn); dfree(d_mask_cn); dfree(d_list_alter); dfree(d_list_n);
         for (auto& q : d_sn) dfree(q);
         dfree(d_live_n); dfree(d_live_cn); dfree(d_live_u); dfree(d_near);
+        dfree(d_act_raw); dfree(d_act_quiet); dfree(d_brick_n); dfree(d_brick_cn);
         dfree(d_mon); dfree(d_phi_old); dfree(d_p2p); d_flags = nullptr;
         if (d_stage) { cudaFree(d_stage); d_stage = nullptr; }
         for (int kind = 0; kind < 3; kind++) for (int side = 0; side < 2; side++) { dfree(d_send[kind][side]); d_recv[kind][side] = nullptr; }
@@ -258,6 +266,8 @@ struct Solver {
         int offq[19];
         for (int q = 0; q < 19; q++) offq[q] = ex(q) + PX * (ey(q) + PY * ez(q));
         std::vector<int> cmap((size_t)PN, -1), flu, passive, lphi, mphi, lcn, mcn, lalt_in, lalt_out, ln, zstart((size_t)nz + 2, 0);
+        std::vector<int> bcn, bn;   // activity map: brick of every list entry
+        act.nbx = ceil_div(L.PX, ACT_BX); act.nby = ceil_div(L.PY, ACT_BY); act.nbz = ceil_div(L.PZ, ACT_BZ);
         flu.reserve((size_t)nx * ny * nz / 2);
         counts[0] = counts[1] = counts[2] = counts[3] = 0;
         for (int z = -3; z <= nz + 4; z++) {
@@ -270,7 +280,8 @@ struct Solver {
                 const bool in1 = x >= 0 && x <= nx + 1 && y >= 0 && y <= ny + 1 && z >= 0 && z <= nz + 1;
                 const bool in0 = x >= 1 && x <= nx && y >= 1 && y <= ny && z >= 1 && z <= nz;
                 if (in1) { if (t <= 0 && in0) flu.push_back(u); else passive.push_back(u); }
-                if (t <= 0 && in2) ln.push_back(u);                      // k_normals: non-solid sites of [-1..n+2]^3 (:760-764)
+                const int brick = activity ? act.brick(x + 3, y + 3, z + 3) : 0;
+                if (t <= 0 && in2) { ln.push_back(u); if (activity) bn.push_back(brick); }   // k_normals: non-solid sites of [-1..n+2]^3 (:760-764)
                 if (t == 2) {
                     counts[0]++;
                     if (in3) {                                           // :737 [-2..n+3]; :885 [0..n+1]
@@ -278,7 +289,7 @@ struct Solver {
                         int m = 0;
                         for (int q = 1; q < 19; q++) if (ty[(size_t)(u + offq[q])] <= 0) m |= 1 << (q - 1);
                         lphi.push_back(u); mphi.push_back(m);
-                        if (in1) { lcn.push_back(u); mcn.push_back(m); }
+                        if (in1) { lcn.push_back(u); mcn.push_back(m); if (activity) bcn.push_back(brick); }
                     }
                 } else if (t == -1) {
                     counts[1]++; if (in3) counts[3]++;
@@ -331,6 +342,11 @@ struct Solver {
         n_list_n = (int)ln.size();
         dfree(d_live_n); dfree(d_live_cn);
         MF_CUDA(cudaMalloc((void**)&d_live_n, std::max(n_list_n, 1))); MF_CUDA(cudaMalloc((void**)&d_live_cn, std::max(n_list_cn, 1)));
+        dfree(d_act_raw); dfree(d_act_quiet);
+        if (activity) {
+            up(d_brick_n, bn); up(d_brick_cn, bcn);
+            MF_CUDA(cudaMalloc((void**)&d_act_raw, 2 * (size_t)act.count())); MF_CUDA(cudaMalloc((void**)&d_act_quiet, (size_t)act.count()));
+        }
         mark_all_live();
         MF_CUDA(cudaMemcpyAsync(d_cmap, cmap.data(), sizeof(int) * (size_t)PN, cudaMemcpyHostToDevice, stream));
         MF_CUDA(cudaMemcpyAsync(d_zstart, zstart.data(), sizeof(int) * zstart.size(), cudaMemcpyHostToDevice, stream));
@@ -531,6 +547,7 @@ struct Solver {
     void gradient_chain() {
         if (!have_geometry) MF_FAIL("gradient chain before geometry");
         const int bl = 128;
+        if (activity && gradient_chain_act()) return;
         if (n_list_phi) { k_extrap_phi<T><<<ceil_div(n_list_phi, bl), bl, 0, stream>>>(L, d_list_phi, d_mask_phi, n_list_phi); check_launch(); count(); }
         // Two normals kernels with bit-identical results.  The list-driven one only touches non-solid sites but gathers from
         // global memory; the TMA-tiled one walks the dense grid with phi staged in shared memory, so its cost does not
@@ -555,6 +572,26 @@ struct Solver {
         if (n_list_alter) { k_alter<T><<<ceil_div(n_list_alter, bl), bl, 0, stream>>>(L, d_list_alter, d_sn[0], d_sn[1], d_sn[2], n_list_alter); check_launch(); count(); }
         if (n_list_cn) { k_extrap_cn<T><<<ceil_div(n_list_cn, bl), bl, 0, stream>>>(L, d_list_cn, d_mask_cn, d_live_cn, d_near, n_list_cn); check_launch(); count(); }
         cn_consistent = true;
+    }
+
+    // the same chain with the interface-activity map (kernels_activity.cuh): one pass over phi decides, brick by brick, where
+    // the order parameter is +1 or -1 to within 1e-7; the normals and cn-extrapolation kernels skip their stencils there.
+    // Stores are identical to the plain chain's.  Only with the list-driven normals kernel (false = not applicable, the caller runs the plain chain).
+    bool gradient_chain_act() {
+        const bool tiled = variant / 10000 == 1 || (variant / 10000 != 2 && (double)n_list_n > 0.75 * (double)(L.nx + 4) * (L.ny + 4) * (L.nz + 4));
+        if (tiled || !d_act_raw) return false;
+        const int bl = 128, nb = act.count();
+        unsigned char *P_ = d_act_raw, *M_ = d_act_raw + nb;
+        MF_CUDA(cudaMemsetAsync(d_act_raw, 0, 2 * (size_t)nb, stream));
+        k_act_scan<T><<<dim3(ceil_div(L.PX, bl), L.PY, L.PZ), bl, 0, stream>>>(L, act, P_, M_); check_launch();
+        k_act_dilate<<<ceil_div(nb, bl), bl, 0, stream>>>(act, P_, M_, d_act_quiet); check_launch();
+        count(2);
+        if (n_list_phi) { k_extrap_phi<T><<<ceil_div(n_list_phi, bl), bl, 0, stream>>>(L, d_list_phi, d_mask_phi, n_list_phi); check_launch(); count(); }
+        if (n_list_n) { k_normals_act<T><<<ceil_div(n_list_n, bl), bl, 0, stream>>>(L, d_list_n, d_brick_n, d_act_quiet, d_live_n, d_near, n_list_n); check_launch(); count(); }
+        if (n_list_alter) { k_alter<T><<<ceil_div(n_list_alter, bl), bl, 0, stream>>>(L, d_list_alter, d_sn[0], d_sn[1], d_sn[2], n_list_alter); check_launch(); count(); }
+        if (n_list_cn) { k_extrap_cn_act<T><<<ceil_div(n_list_cn, bl), bl, 0, stream>>>(L, d_list_cn, d_mask_cn, d_brick_cn, d_act_quiet, d_live_cn, d_near, n_list_cn); check_launch(); count(); }
+        cn_consistent = true;
+        return true;
     }
 
     // persistent grid of the collide kernels: CTAS resident CTAs per SM.  MFLBM_MAX_CTAS caps it (tests: a small lattice

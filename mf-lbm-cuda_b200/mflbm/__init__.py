@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 import subprocess
 from pathlib import Path
 
@@ -201,6 +202,12 @@ class Solver:
         self._slab = slab
         self.nx = int(slab.nx_local) if slab is not None else int(params.nx)
         self.ny, self.nz = int(params.ny), int(params.nz)
+        # the library reads MFLBM_ACTIVITY when a solver is created (gradient chain with the interface-activity map,
+        # csrc/kernels_activity.cuh; results are identical); recorded here so that callers can report it
+        try:
+            self.activity = int(os.environ.get("MFLBM_ACTIVITY", "0") or 0) != 0
+        except ValueError:
+            self.activity = False
         rc = self._fn("create")(C.byref(params), C.byref(slab) if slab is not None else None, device, stream, C.byref(self.h))
         self._check(rc)
 

@@ -1,4 +1,6 @@
 """CUDA path (through the C ABI) against the C oracle on the same seeded inputs.  All tests need a GPU."""
+import os
+
 import numpy as np
 import pytest
 
@@ -195,3 +197,82 @@ def test_full_size_run_is_deterministic(gpu_lib, prec):
         assert np.array_equal(a, b), (k + 1, int((a != b).sum()))
     for s in pair:
         s.close()
+
+
+# The activity map is opt-in (MFLBM_ACTIVITY=1) until these tests have been seen green on a B200; they run with
+# MFLBM_TEST_ACTIVITY=1 so that an unverified optional path cannot stop the parity suite of the default path.
+needs_activity_optin = pytest.mark.skipif(not os.environ.get("MFLBM_TEST_ACTIVITY"), reason="opt-in path: set MFLBM_TEST_ACTIVITY=1")
+
+
+def _pair_with_and_without_activity(monkeypatch, make):
+    """two solvers over the same input: plain gradient chain / chain with the interface-activity map (MFLBM_ACTIVITY is read
+    when a solver is created)"""
+    monkeypatch.delenv("MFLBM_ACTIVITY", raising=False)
+    plain = make()
+    monkeypatch.setenv("MFLBM_ACTIVITY", "1")
+    act = make()
+    monkeypatch.delenv("MFLBM_ACTIVITY", raising=False)
+    return plain, act
+
+
+def _assert_states_identical(plain, act, where):
+    a, b = plain.download_state(), act.download_state()
+    assert sorted(a) == sorted(b)
+    for k in sorted(a):
+        assert np.array_equal(a[k], b[k], equal_nan=True), (where, k, int((a[k] != b[k]).sum()))
+
+
+@needs_activity_optin
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("name", ["pack_velocity", "tube_pressure", "periodic_drop", "imbibition_plate2"])
+def test_activity_map_is_bit_identical(gpu_lib, monkeypatch, name, prec):
+    """kernels_activity.cuh: where every non-solid phi of a 27-brick neighbourhood is exactly +1 (or -1) the chain kernels
+    skip their stencils and store what the full kernels would store.  Every array - phi at the solid-boundary sites and the
+    zeroed normals included - must equal the plain chain's bit for bit, step loop and graph replay alike."""
+    o, ctl, solid = common.make_oracle(name, prec)
+    plain, act = _pair_with_and_without_activity(monkeypatch, lambda: common.solver_from_oracle(o, ctl, prec))
+    for s in (plain, act):
+        for n in range(1, 4):
+            s.step(n)
+    _assert_states_identical(plain, act, "3 steps")
+    for s in (plain, act):
+        s.run(4, 57)
+    _assert_states_identical(plain, act, "60 steps")
+    o.run(1, 60)
+    st = act.download_state()
+    for k in ("pdf", "phi"):
+        assert relerr(st[k], o.arr(k)) <= TOL[prec], (k, relerr(st[k], o.arr(k)))
+    plain.close(); act.close()
+
+
+@needs_activity_optin
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_activity_map_follows_a_moving_interface(gpu_lib, monkeypatch, prec):
+    """A lattice large enough for most bricks to be quiet (64 x 48 x 128 pack, interface at z = 40), driven hard enough
+    (Ca 0.05) for the front to sweep bricks from quiet to active and back: sites whose normals were non-zero must be zeroed
+    when their brick falls quiet again, held extrapolated values must be dropped when it wakes up."""
+    import bench
+    import mflbm
+    nx, ny, nz = 64, 48, 128
+    ctl = bench.workload_control(nx, ny, nz)
+    ctl.update(initial_interface_position=40.0, capillary_number=5e-2)
+    solid = bench.workload_geometry(nx, ny, nz, seed=5)
+    W = bench.inlet_profile(ctl, prec)
+    P = mflbm.derive_params(ctl, prec)
+
+    def make():
+        s = mflbm.Solver(P, prec)
+        s.preprocess_geometry(solid)
+        s.init_state(1, ctl["initial_interface_position"], W_in=W)
+        return s
+
+    plain, act = _pair_with_and_without_activity(monkeypatch, make)
+    _assert_states_identical(plain, act, "initial state")
+    nt = 1
+    for chunk in (1, 1, 98, 300):
+        for s in (plain, act):
+            s.run(nt, chunk)
+        nt += chunk
+        _assert_states_identical(plain, act, f"{nt - 1} steps")
+    assert plain.monitor()["nan_detected"] == 0
+    plain.close(); act.close()
