@@ -72,6 +72,8 @@ struct Solver {
     ActGrid act{};
     unsigned char *d_act_raw = nullptr, *d_act_quiet = nullptr;   // [2][bricks] P | M flags of one chain; [bricks] verdict
     int *d_brick_n = nullptr, *d_brick_cn = nullptr;              // brick of every entry of d_list_n / d_list_cn
+    cudaStream_t act_stream = nullptr;                            // lane of k_extrap_phi while the map is being built
+    cudaEvent_t ev_act_fork = nullptr, ev_act_join = nullptr;
     int n_list_phi = 0, n_list_cn = 0, n_list_alter = 0, n_list_alter_all = 0, n_list_n = 0;
     long long counts[4] = {0, 0, 0, 0};
     long long n_fluid = 0;
@@ -128,6 +130,11 @@ struct Solver {
         if (const char* v = getenv("MFLBM_VARIANT")) variant = atoi(v);
         if (const char* v = getenv("MFLBM_MAX_CTAS")) max_ctas = atoi(v);
         if (const char* v = getenv("MFLBM_ACTIVITY")) activity = atoi(v) != 0;
+        if (activity) {
+            MF_CUDA(cudaStreamCreateWithFlags(&act_stream, cudaStreamNonBlocking));
+            MF_CUDA(cudaEventCreateWithFlags(&ev_act_fork, cudaEventDisableTiming));
+            MF_CUDA(cudaEventCreateWithFlags(&ev_act_join, cudaEventDisableTiming));
+        }
         MF_CUDA(cudaSetDevice(device));
         MF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
         if (strm) { stream = (cudaStream_t)strm; own_stream = false; }
@@ -206,6 +213,9 @@ struct Solver {
         for (int kind = 0; kind < 3; kind++) for (int side = 0; side < 2; side++) { dfree(d_send[kind][side]); d_recv[kind][side] = nullptr; }
         if (h_mon) { cudaFreeHost(h_mon); h_mon = nullptr; }
         if (aux_stream) { cudaStreamDestroy(aux_stream); aux_stream = nullptr; }
+        if (act_stream) { cudaStreamDestroy(act_stream); act_stream = nullptr; }
+        if (ev_act_fork) { cudaEventDestroy(ev_act_fork); ev_act_fork = nullptr; }
+        if (ev_act_join) { cudaEventDestroy(ev_act_join); ev_act_join = nullptr; }
         if (ev_fork) { cudaEventDestroy(ev_fork); ev_fork = nullptr; }
         if (ev_join) { cudaEventDestroy(ev_join); ev_join = nullptr; }
         if (own_stream && stream) cudaStreamDestroy(stream);
@@ -582,11 +592,17 @@ struct Solver {
         if (tiled || !d_act_raw) return false;
         const int bl = 128, nb = act.count();
         unsigned char *P_ = d_act_raw, *M_ = d_act_raw + nb;
+        // two lanes (event fork / join, also inside a captured graph): the phi extrapolation writes solid-boundary sites only
+        // and the scan reads non-solid sites only, so the latency-bound gather kernel hides behind the streaming pass
+        MF_CUDA(cudaEventRecord(ev_act_fork, stream));
+        MF_CUDA(cudaStreamWaitEvent(act_stream, ev_act_fork, 0));
+        if (n_list_phi) { k_extrap_phi<T><<<ceil_div(n_list_phi, bl), bl, 0, act_stream>>>(L, d_list_phi, d_mask_phi, n_list_phi); check_launch(); count(); }
+        MF_CUDA(cudaEventRecord(ev_act_join, act_stream));
         MF_CUDA(cudaMemsetAsync(d_act_raw, 0, 2 * (size_t)nb, stream));
         k_act_scan<T><<<dim3(ceil_div(L.PX, bl), L.PY, L.PZ), bl, 0, stream>>>(L, act, P_, M_); check_launch();
         k_act_dilate<<<ceil_div(nb, bl), bl, 0, stream>>>(act, P_, M_, d_act_quiet); check_launch();
         count(2);
-        if (n_list_phi) { k_extrap_phi<T><<<ceil_div(n_list_phi, bl), bl, 0, stream>>>(L, d_list_phi, d_mask_phi, n_list_phi); check_launch(); count(); }
+        MF_CUDA(cudaStreamWaitEvent(stream, ev_act_join, 0));
         if (n_list_n) { k_normals_act<T><<<ceil_div(n_list_n, bl), bl, 0, stream>>>(L, d_list_n, d_brick_n, d_act_quiet, d_live_n, d_near, n_list_n); check_launch(); count(); }
         if (n_list_alter) { k_alter<T><<<ceil_div(n_list_alter, bl), bl, 0, stream>>>(L, d_list_alter, d_sn[0], d_sn[1], d_sn[2], n_list_alter); check_launch(); count(); }
         if (n_list_cn) { k_extrap_cn_act<T><<<ceil_div(n_list_cn, bl), bl, 0, stream>>>(L, d_list_cn, d_mask_cn, d_brick_cn, d_act_quiet, d_live_cn, d_near, n_list_cn); check_launch(); count(); }
