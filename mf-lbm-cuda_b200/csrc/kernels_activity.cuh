@@ -23,7 +23,7 @@
 //                  and slab halos need no special case)
 //   k_act_dilate   quiet[b] over the 27 bricks around b:  0 = both kinds present (an interface may be near: evaluate),
 //                  1 = every non-solid site is within eps of +1, 2 = of -1, 3 = no non-solid site at all
-// The 27-brick neighbourhood reaches >= 4 sites in every direction, so k_normals_act / k_extrap_cn_act below store exactly
+// The 27-brick neighbourhood reaches >= 4 sites in every direction, so k_normals_act / k_alter_act / k_extrap_cn_act below store exactly
 // what the full kernels would store at the sites of a quiet brick, and skip their gathers.  k_extrap_phi always runs in
 // full (its result there is s only to within rounding).
 #pragma once
@@ -120,6 +120,16 @@ __global__ void __launch_bounds__(128, 16) k_normals_act(const Lattice<T> L, con
         raise_near(L, near, u);
     }
     L.cn_x[u] = gx; L.cn_y[u] = gy; L.cn_z[u] = gz; L.c_norm[u] = nrm;
+}
+
+// k_alter with the quiet shortcut: c_norm is zero there (k_normals_act), the wetting rotation leaves such sites alone (:816)
+template <typename T>
+__global__ void k_alter_act(const Lattice<T> L, const int* __restrict__ list, const int* __restrict__ brick, const unsigned char* __restrict__ quiet,
+                            const T* __restrict__ snx, const T* __restrict__ sny, const T* __restrict__ snz, const int count) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    if (quiet[brick[t]] != 0) return;
+    alter_site(L, list, snx, sny, snz, t);
 }
 
 // k_extrap_cn with the quiet shortcut: every neighbour's normal is zero, near[c2] cannot have been raised in this chain

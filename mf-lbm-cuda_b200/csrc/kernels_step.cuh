@@ -121,10 +121,8 @@ __global__ void k_zero_solid_normals(const Lattice<T> L) {
 // geometrical wetting model on fluid-boundary nodes: rotate cn so that n_w . cn = cos(theta), <= 4 secant
 // iterations (:809-878).  snx/sny/snz: solid-surface normals in list order.
 template <typename T>
-__global__ void k_alter(const Lattice<T> L, const int* __restrict__ list, const T* __restrict__ snx, const T* __restrict__ sny,
-                        const T* __restrict__ snz, const int count) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= count) return;
+__device__ __forceinline__ void alter_site(const Lattice<T>& L, const int* __restrict__ list, const T* __restrict__ snx, const T* __restrict__ sny,
+                                           const T* __restrict__ snz, const int t) {
     const int c2 = list[t];
     const T lambda = lit<T>(0.5), local_eps = lit<T>(1e-6), ct = L.cos_theta;
     if (!(L.c_norm[c2] > local_eps)) return;
@@ -154,6 +152,14 @@ __global__ void k_alter(const Lattice<T> L, const int* __restrict__ list, const 
         tmp = lit<T>(1.) / ((lit<T>(1e-30)) + sqrt(vcx2 * vcx2 + vcy2 * vcy2 + vcz2 * vcz2));
         L.cn_x[c2] = vcx2 * tmp; L.cn_y[c2] = vcy2 * tmp; L.cn_z[c2] = vcz2 * tmp;
     }
+}
+
+template <typename T>
+__global__ void k_alter(const Lattice<T> L, const int* __restrict__ list, const T* __restrict__ snx, const T* __restrict__ sny,
+                        const T* __restrict__ snz, const int count) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    alter_site(L, list, snx, sny, snz, t);
 }
 
 // cn at solid-boundary nodes <- weighted mean of the fluid neighbours' cn (:880-906); mask as in k_extrap_phi.

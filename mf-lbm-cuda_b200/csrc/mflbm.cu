@@ -71,7 +71,7 @@ struct Solver {
     bool activity = false;
     ActGrid act{};
     unsigned char *d_act_raw = nullptr, *d_act_quiet = nullptr;   // [2][bricks] P | M flags of one chain; [bricks] verdict
-    int *d_brick_n = nullptr, *d_brick_cn = nullptr;              // brick of every entry of d_list_n / d_list_cn
+    int *d_brick_n = nullptr, *d_brick_cn = nullptr, *d_brick_alter = nullptr;   // brick of every entry of d_list_n / d_list_cn / d_list_alter
     cudaStream_t act_stream = nullptr;                            // lane of k_extrap_phi while the map is being built
     cudaEvent_t ev_act_fork = nullptr, ev_act_join = nullptr;
     int n_list_phi = 0, n_list_cn = 0, n_list_alter = 0, n_list_alter_all = 0, n_list_n = 0;
@@ -207,7 +207,7 @@ struct Solver {
         dfree(d_list_phi); dfree(d_mask_phi); dfree(d_list_cn); dfree(d_mask_cn); dfree(d_list_alter); dfree(d_list_n);
         for (auto& q : d_sn) dfree(q);
         dfree(d_live_n); dfree(d_live_cn); dfree(d_live_u); dfree(d_near);
-        dfree(d_act_raw); dfree(d_act_quiet); dfree(d_brick_n); dfree(d_brick_cn);
+        dfree(d_act_raw); dfree(d_act_quiet); dfree(d_brick_n); dfree(d_brick_cn); dfree(d_brick_alter);
         dfree(d_mon); dfree(d_phi_old); dfree(d_p2p); d_flags = nullptr;
         if (d_stage) { cudaFree(d_stage); d_stage = nullptr; }
         for (int kind = 0; kind < 3; kind++) for (int side = 0; side < 2; side++) { dfree(d_send[kind][side]); d_recv[kind][side] = nullptr; }
@@ -276,7 +276,7 @@ struct Solver {
         int offq[19];
         for (int q = 0; q < 19; q++) offq[q] = ex(q) + PX * (ey(q) + PY * ez(q));
         std::vector<int> cmap((size_t)PN, -1), flu, passive, lphi, mphi, lcn, mcn, lalt_in, lalt_out, ln, zstart((size_t)nz + 2, 0);
-        std::vector<int> bcn, bn;   // activity map: brick of every list entry
+        std::vector<int> bcn, bn, balt;   // activity map: brick of every list entry (balt: the [-1..n+2]^3 part of the alter list)
         act.nbx = ceil_div(L.PX, ACT_BX); act.nby = ceil_div(L.PY, ACT_BY); act.nbz = ceil_div(L.PZ, ACT_BZ);
         flu.reserve((size_t)nx * ny * nz / 2);
         counts[0] = counts[1] = counts[2] = counts[3] = 0;
@@ -303,7 +303,7 @@ struct Solver {
                     }
                 } else if (t == -1) {
                     counts[1]++; if (in3) counts[3]++;
-                    if (in2) lalt_in.push_back(u); else lalt_out.push_back(u);   // :814 [-1..n+2]
+                    if (in2) { lalt_in.push_back(u); if (activity) balt.push_back(brick); } else lalt_out.push_back(u);   // :814 [-1..n+2]
                 }
             }
         }
@@ -354,7 +354,7 @@ struct Solver {
         MF_CUDA(cudaMalloc((void**)&d_live_n, std::max(n_list_n, 1))); MF_CUDA(cudaMalloc((void**)&d_live_cn, std::max(n_list_cn, 1)));
         dfree(d_act_raw); dfree(d_act_quiet);
         if (activity) {
-            up(d_brick_n, bn); up(d_brick_cn, bcn);
+            up(d_brick_n, bn); up(d_brick_cn, bcn); up(d_brick_alter, balt);
             MF_CUDA(cudaMalloc((void**)&d_act_raw, 2 * (size_t)act.count())); MF_CUDA(cudaMalloc((void**)&d_act_quiet, (size_t)act.count()));
         }
         mark_all_live();
@@ -604,7 +604,7 @@ struct Solver {
         count(2);
         MF_CUDA(cudaStreamWaitEvent(stream, ev_act_join, 0));
         if (n_list_n) { k_normals_act<T><<<ceil_div(n_list_n, bl), bl, 0, stream>>>(L, d_list_n, d_brick_n, d_act_quiet, d_live_n, d_near, n_list_n); check_launch(); count(); }
-        if (n_list_alter) { k_alter<T><<<ceil_div(n_list_alter, bl), bl, 0, stream>>>(L, d_list_alter, d_sn[0], d_sn[1], d_sn[2], n_list_alter); check_launch(); count(); }
+        if (n_list_alter) { k_alter_act<T><<<ceil_div(n_list_alter, bl), bl, 0, stream>>>(L, d_list_alter, d_brick_alter, d_act_quiet, d_sn[0], d_sn[1], d_sn[2], n_list_alter); check_launch(); count(); }
         if (n_list_cn) { k_extrap_cn_act<T><<<ceil_div(n_list_cn, bl), bl, 0, stream>>>(L, d_list_cn, d_mask_cn, d_brick_cn, d_act_quiet, d_live_cn, d_near, n_list_cn); check_launch(); count(); }
         cn_consistent = true;
         return true;
