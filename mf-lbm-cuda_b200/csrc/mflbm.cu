@@ -69,6 +69,7 @@ struct Solver {
     int grad_tx = 0;                                           // x extent of its tiles
     // interface-activity map (kernels_activity.cuh), opt-in with MFLBM_ACTIVITY=1
     bool activity = false;
+    bool bc_lanes = false;   // MFLBM_LANES=1 (opt-in): the outlet kernel runs next to the inlet kernel on the second lane
     ActGrid act{};
     unsigned char *d_act_raw = nullptr, *d_act_quiet = nullptr;   // [2][bricks] P | M flags of one chain; [bricks] verdict
     int *d_brick_n = nullptr, *d_brick_cn = nullptr, *d_brick_alter = nullptr;   // brick of every entry of d_list_n / d_list_cn / d_list_alter
@@ -130,7 +131,8 @@ struct Solver {
         if (const char* v = getenv("MFLBM_VARIANT")) variant = atoi(v);
         if (const char* v = getenv("MFLBM_MAX_CTAS")) max_ctas = atoi(v);
         if (const char* v = getenv("MFLBM_ACTIVITY")) activity = atoi(v) != 0;
-        if (activity) {
+        if (const char* v = getenv("MFLBM_LANES")) bc_lanes = atoi(v) != 0;
+        if (activity || bc_lanes) {
             MF_CUDA(cudaStreamCreateWithFlags(&act_stream, cudaStreamNonBlocking));
             MF_CUDA(cudaEventCreateWithFlags(&ev_act_fork, cudaEventDisableTiming));
             MF_CUDA(cudaEventCreateWithFlags(&ev_act_join, cudaEventDisableTiming));
@@ -701,10 +703,17 @@ struct Solver {
         }
         const dim3 gp(ceil_div(L.nx, b.x), ceil_div(L.ny, b.y), 1);
         if (open_z()) {
+            // the inlet kernels touch planes k <= 2, the outlet kernels planes k >= nz - 1 (and the convective buffers): with
+            // MFLBM_LANES=1 they run side by side (both are latency-bound plane kernels of ~15 us).  The fork is recorded
+            // before the inlet launch, so the outlet lane only waits for what precedes both.
+            const bool fork = bc_lanes && L.nz >= 8 && P.inlet_BC != 0 && P.outlet_BC != 0;
+            cudaStream_t so = fork ? act_stream : stream;
+            if (fork) { MF_CUDA(cudaEventRecord(ev_act_fork, stream)); MF_CUDA(cudaStreamWaitEvent(act_stream, ev_act_fork, 0)); }
             if (P.inlet_BC == 1) { if (odd) k_inlet_velocity<T, true><<<gp, b, 0, stream>>>(L, 1, L.nx); else k_inlet_velocity<T, false><<<gp, b, 0, stream>>>(L, 1, L.nx); count(); }
             else if (P.inlet_BC == 2) { if (odd) k_inlet_pressure<T, true><<<gp, b, 0, stream>>>(L, 1, L.nx); else k_inlet_pressure<T, false><<<gp, b, 0, stream>>>(L, 1, L.nx); count(); }
-            if (P.outlet_BC == 1) { if (odd) k_outlet_convective<T, true><<<gp, b, 0, stream>>>(L, 1, L.nx); else k_outlet_convective<T, false><<<gp, b, 0, stream>>>(L, 1, L.nx); count(); }
-            else if (P.outlet_BC == 2) { if (odd) k_outlet_pressure<T, true><<<gp, b, 0, stream>>>(L, 1, L.nx); else k_outlet_pressure<T, false><<<gp, b, 0, stream>>>(L, 1, L.nx); count(); }
+            if (P.outlet_BC == 1) { if (odd) k_outlet_convective<T, true><<<gp, b, 0, so>>>(L, 1, L.nx); else k_outlet_convective<T, false><<<gp, b, 0, so>>>(L, 1, L.nx); count(); }
+            else if (P.outlet_BC == 2) { if (odd) k_outlet_pressure<T, true><<<gp, b, 0, so>>>(L, 1, L.nx); else k_outlet_pressure<T, false><<<gp, b, 0, so>>>(L, 1, L.nx); count(); }
+            if (fork) { MF_CUDA(cudaEventRecord(ev_act_join, act_stream)); MF_CUDA(cudaStreamWaitEvent(stream, ev_act_join, 0)); }
             check_launch();
         }
         if (P.porous_plate_cmd != 0) {
