@@ -368,6 +368,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="N > 1: halo messages through peer memory (default) or NCCL send/recv")
+    ap.add_argument("--partition", default="equal", choices=["equal", "balanced"],
+                    help="N > 1: equal-width x-slabs, or cuts that balance fluid nodes + halo cost per rank (slab.balanced_cuts)")
+    ap.add_argument("--halo-cost", type=float, default=10.0,
+                    help="--partition balanced: cost of one neighbour per face site, in fluid-node updates (f64 256^2 faces: ~104 us = 10.5)")
     ap.add_argument("--activity", type=int, default=None, choices=[0, 1],
                     help="gradient chain with the interface-activity map (kernels_activity.cuh); default: the library's (MFLBM_ACTIVITY)")
     ap.add_argument("--geometry", default="pack", choices=["pack", "open"], help="open = empty duct, diagnostic only (not the benchmark workload)")

@@ -70,6 +70,40 @@ def partition(nx_global: int, world: int, rank: int) -> SlabRange:
     return SlabRange(rank, world, x0, nx_local)
 
 
+def balanced_cuts(col_cost, world: int, side_cost: float = 0.0, min_width: int = 4) -> list[int]:
+    """x cuts [0, c1, ..., nx] that equalise  sum(col_cost over the slab's columns) + side_cost * (neighbours of the slab).
+
+    col_cost[i]: work of global column i+1 (its fluid nodes: the collide kernels run one thread per fluid node); side_cost: what
+    one neighbour costs a slab per step (halo pack / unpack kernels, arrival waits, the chain's redundant ghost columns), in the
+    same unit.  End slabs have one neighbour, interior slabs two, so equal widths leave the end ranks waiting; in a random pack
+    the fluid count per slab also varies by a few per cent.  Deterministic: every rank computes the same cuts."""
+    col_cost = np.asarray(col_cost, dtype=np.float64)
+    nx = int(col_cost.size)
+    if world < 1 or nx < world * min_width:
+        raise ValueError(f"{nx} columns over {world} slabs: a slab must be at least {min_width} columns wide (phi halo)")
+    cs = np.cumsum(col_cost)
+    target = (cs[-1] + (2 * world - 2) * side_cost) / world
+    cuts = [0]
+    for r in range(world - 1):
+        want = (r + 1) * target - side_cost * (2 * (r + 1) - 1)      # column cost left of the cut: ranks 0..r carry 2(r+1)-1 sides
+        c = int(np.searchsorted(cs, want))                           # cs[c] >= want > cs[c-1]: cutting after column c or c+1
+        if c < nx and (c == 0 or abs(cs[c] - want) < abs(cs[c - 1] - want)):
+            c += 1
+        c = max(c, cuts[-1] + min_width)
+        c = min(c, nx - (world - 1 - r) * min_width)
+        cuts.append(c)
+    cuts.append(nx)
+    return cuts
+
+
+def partition_balanced(col_cost, world: int, rank: int, side_cost: float = 0.0) -> SlabRange:
+    """the slab of `rank` under balanced_cuts (same SlabRange as partition())"""
+    if not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    cuts = balanced_cuts(col_cost, world, side_cost)
+    return SlabRange(rank, world, cuts[rank] + 1, cuts[rank + 1] - cuts[rank])
+
+
 class SlabStepper:
     """Per-step sequencing of one slab: compute phases interleaved with the two halo exchanges.
 
@@ -269,6 +303,15 @@ def bench_slabs(args, rank: int, world: int, local: int) -> dict | None:
     nxg = strong if strong else S * world      # strong scaling: fixed NX x S x S lattice; weak: S^3 per GPU
     ctl = B.workload_control(nxg, S, S)
     rng = partition(nxg, world, rank)
+    if getattr(args, "partition", "equal") == "balanced" and world > 1:
+        # every rank counts the fluid nodes of its equal-width columns, the counts are gathered, and all ranks derive the same
+        # cost-balanced cuts (fluid nodes + a per-neighbour halo cost expressed in fluid-node updates per face site)
+        w = B.workload_geometry_window(nxg, S, S, rng.x0, rng.x1, kind=args.geometry)
+        mine = (w[:, :, rng.x0 - 1:rng.x1] == 0).sum(axis=(0, 1)).astype(np.float64)
+        del w
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+        rng = partition_balanced(np.concatenate(parts), world, rank, side_cost=float(args.halo_cost) * S * S)
     params = mflbm.derive_params(ctl, prec)
     stream = torch.cuda.Stream(device=local)
     with torch.cuda.stream(stream):
@@ -346,7 +389,8 @@ def bench_slabs(args, rank: int, world: int, local: int) -> dict | None:
                        "lattice": [nxg, S, S], "fluid_nodes": n_fluid, "porosity": n_fluid / n_site, "parallelism": f"{world} x-slabs, halos " + ("pushed into peer memory over NVLink (CUDA IPC), arrival flags, no collective" if getattr(slab, "p2p", False) else "NCCL send/recv"),
                        "l2": "state per GPU >> 126 MB L2 (inputs larger than L2, no flush needed)",
                        "fluid_mlups": n_fluid * args.steps / 1e6 / (ms * 1e-3), "geometry_preprocess_s": t_geo,
-                       "saturation_full_domain": mon["saturation_full_domain"], "halo_exchanges_per_step": 2},
+                       "saturation_full_domain": mon["saturation_full_domain"], "halo_exchanges_per_step": 2,
+                       "partition": getattr(args, "partition", "equal"), "slab_width_rank0": rng.nx_local},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src, "bytes_model": "78*sizeof(real)*N_fluid + N_site per step, per GPU", "bytes_per_step": bytes_step / world},
             "e2e": {"value": n_site * args.steps / 1e6 / t_e2e if t_e2e else None, "unit": "MLUPS", "h2d_bytes_per_step": h2d * world / args.steps,

@@ -30,3 +30,6 @@ PY
   python profiles/summarize.py launches $O/${TAG}_launches_${p}_act.csv > $O/${TAG}_launches_${p}_act.txt 2>&1
   head -16 $O/${TAG}_launches_${p}_act.txt | cut -c1-140
 done
+# multi-GPU (separate gpurun --gpus N calls; N = 2, 4, 8), equal vs cost-balanced cuts, plain vs activity map:
+#   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus N \
+#       --steps 500 --warmup 50 --no-e2e --no-cpu-baseline [--partition balanced] [--activity 1]

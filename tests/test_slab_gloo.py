@@ -22,7 +22,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, name, prec, nsteps, outdir):
+def _worker(rank, world, port, name, prec, nsteps, outdir, balanced=False):
     import torch
     import torch.distributed as dist
     import common
@@ -33,6 +33,14 @@ def _worker(rank, world, port, name, prec, nsteps, outdir):
     try:
         o, ctl, solid = common.make_oracle(name, prec)
         rng = slab.partition(o.nx, world, rank)
+        if balanced:
+            # the bench's --partition balanced protocol: every rank counts the fluid nodes of its equal-width columns, the counts
+            # are gathered, all ranks derive the same cost-balanced cuts
+            fluid = o.arr("walls")[2:-2, 2:-2, 2:-2] == 0
+            mine = fluid[:, :, rng.x0 - 1:rng.x1].sum(axis=(0, 1)).astype(np.float64)
+            parts = [None] * world
+            dist.all_gather_object(parts, mine)
+            rng = slab.partition_balanced(np.concatenate(parts), world, rank, side_cost=0.6 * o.ny * o.nz)
         backend = OracleSlab(o, rng)
         st = slab.SlabStepper(backend, rng)
         st.run(1, nsteps)
@@ -66,6 +74,46 @@ def test_slabs_over_gloo_equal_single_domain(tmp_path, name, prec, world, nsteps
         assert got.shape == want.shape, (k, got.shape, want.shape)
         assert not np.isnan(got).any(), f"{k}: NaN - a column was used before it was exchanged"
         assert np.array_equal(got, want), (k, float(np.abs(got - want).max()))
+
+
+def test_balanced_slabs_over_gloo_equal_single_domain(tmp_path):
+    """cost-balanced cuts (slab.balanced_cuts: wide end slabs, narrow interior ones) through the same protocol"""
+    import common
+    name, prec, world, nsteps = "pack_velocity", "f64", 3, 6
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, name, prec, nsteps, str(tmp_path), True), nprocs=world, join=True)
+    ref, ctl, solid = common.make_oracle(name, prec)
+    ref.run(1, nsteps)
+    parts = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    widths = [p["phi"].shape[-1] for p in parts]
+    assert widths[1] < widths[0] and widths[1] < widths[2], widths      # the interior slab pays for two neighbours
+    for k in ("pdf", "phi", "cn_x", "cn_y", "cn_z", "c_norm", "curv"):
+        got = np.concatenate([p[k] for p in parts], axis=-1)
+        assert np.array_equal(got, ref.arr(k)), k
+
+
+def test_balanced_cuts():
+    from mflbm import slab
+    rng = np.random.default_rng(3)
+    for nx, world in ((64, 2), (257, 4), (2048, 8), (40, 8)):
+        col = rng.uniform(0.5, 1.5, nx) * 1000.0
+        for side in (0.0, 5000.0):
+            cuts = slab.balanced_cuts(col, world, side)
+            assert cuts[0] == 0 and cuts[-1] == nx and len(cuts) == world + 1
+            w = np.diff(cuts)
+            assert w.min() >= 4
+            rs = [slab.partition_balanced(col, world, r, side) for r in range(world)]
+            assert rs[0].x0 == 1 and rs[-1].x1 == nx and all(a.x1 + 1 == b.x0 for a, b in zip(rs, rs[1:]))
+            if nx >= 64:   # costs equal to within two columns' worth
+                cost = [col[cuts[r]:cuts[r + 1]].sum() + side * ((r > 0) + (r < world - 1)) for r in range(world)]
+                assert max(cost) - min(cost) <= 2 * col.max() + 1e-9, (nx, world, side, cost)
+    # uniform columns, no halo cost: the equal-width partition
+    assert slab.balanced_cuts(np.ones(1024), 4) == [0, 256, 512, 768, 1024]
+    # the 8-slab weak-scaling shape: end slabs wider than interior ones
+    w = np.diff(slab.balanced_cuts(np.full(2048, 29000.0), 8, 10 * 65536.0))
+    assert w[0] == w[-1] and w[0] > w[1] and len(set(w[1:-1])) <= 2
+    with pytest.raises(ValueError):
+        slab.balanced_cuts(np.ones(10), 4)
 
 
 def test_partition_covers_the_lattice():
