@@ -255,6 +255,20 @@ class CudaSlab:
         if not self.p2p and why:
             print(f"[rank {r.rank}] peer-memory halo transport unavailable ({why}); using NCCL send/recv", flush=True)
 
+    def save_checkpoint(self, path, stepper: "SlabStepper", nx_global: int, ntime_next: int, dist) -> None:
+        """collective: settle the slabs, download every rank's state and write the reference-format checkpoint file"""
+        stepper.settle()
+        st = self.solver.download_state(fields=("pdf", "phi"), convective=self.solver.params.outlet_BC == 1)
+        write_checkpoint_slabs(path, self.rng, nx_global, st, ntime_next, float(self.solver.params.force_z), float(self.solver.params.rho_in), dist)
+
+    def load_checkpoint(self, path, nx_global: int) -> int:
+        """restart this slab from a checkpoint file written by any decomposition; returns the step index to continue with"""
+        P = self.solver.params
+        c = read_checkpoint_slab(path, self.rng, nx_global, int(P.ny), int(P.nz), self.solver.rt, P.outlet_BC == 1)
+        self.solver.upload_state(pdf=c["pdf"], phi=c["phi"], f_convec=c.get("f_convec"), g_convec=c.get("g_convec"), phi_convec=c.get("phi_convec"))
+        self.solver.color_gradient()
+        return c["ntime_next"]
+
     def halo_push(self, kind):
         self.solver.halo_push(kind)
 
@@ -287,6 +301,86 @@ def reduce_monitor(m: dict, rng: SlabRange, params, dist, device=None) -> dict:
     out["saturation"] = out["vol1_sum"] / (out["vol1_sum"] + out["vol2_sum"])
     out["saturation_full_domain"] = out["vol1_full"] / (out["vol1_full"] + out["vol2_full"])
     out["ca"] = ((out["fl1_avg"] + out["fl2_avg"]) / float(params.A_xy)) * float(params.la_nu1) / float(params.lbm_gamma)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# checkpoint of a decomposed lattice in the reference's single-file layout (results/out2.checkpoint/id0000,
+# /root/reference/src/IO_multiphase.cpp:252-305, read back by src/Init_multiphase.cpp:501-538):
+#     int32 ntime + 1 | T force_z | T rho_in | pdf[2][19][nz+2][ny+2][nx+2] | phi[nz+8][ny+8][nx+8]
+#     | convective outlet only: f_convec[19][ny+2][nx+2] | g_convec[19][ny+2][nx+2] | phi_convec[ny+2][nx+2]
+# Every rank writes (reads) the x columns it owns straight into (from) the one file through a memory map: no funnel
+# through rank 0, and a file written by N slabs restarts on M slabs or in the single-GPU programs.
+# ----------------------------------------------------------------------------------------------------------
+def checkpoint_layout(nx: int, ny: int, nz: int, dtype, convective: bool) -> tuple[dict, int]:
+    """{field: (byte offset, shape, x ghost width)} of the global file and its total size"""
+    s = np.dtype(dtype).itemsize
+    off = 4 + 2 * s
+    out = {}
+    for name, shape, g in (("pdf", (2, 19, nz + 2, ny + 2, nx + 2), 1), ("phi", (nz + 8, ny + 8, nx + 8), 4)) + (
+            (("f_convec", (19, ny + 2, nx + 2), 1), ("g_convec", (19, ny + 2, nx + 2), 1), ("phi_convec", (ny + 2, nx + 2), 1)) if convective else ()):
+        out[name] = (off, shape, g)
+        off += int(np.prod(shape)) * s
+    return out, off
+
+
+def _owned_columns(rng: SlabRange, g: int) -> tuple[slice, slice]:
+    """(local, global) index slices along x of the columns `rng` owns in an array with g ghost columns: its real columns,
+    plus the ghost columns of the lattice itself on a side without a neighbour"""
+    lo = 1 if rng.has_left else 1 - g            # local x, inclusive
+    hi = rng.nx_local if rng.has_right else rng.nx_local + g
+    return slice(lo + g - 1, hi + g), slice(rng.x0 + lo + g - 2, rng.x0 + hi + g - 1)
+
+
+def write_checkpoint_slabs(path, rng: SlabRange, nx_global: int, local: dict, ntime_next: int, force_z: float, rho_in: float, dist=None) -> None:
+    """local: this slab's arrays in the reference layout of an (nx_local, ny, nz) lattice - what Solver.download_state returns
+    after SlabStepper.settle(): "pdf" [2,19,nz+2,ny+2,nxl+2], "phi" [nz+8,ny+8,nxl+8], with a convective outlet also "f_convec",
+    "g_convec" [19,ny+2,nxl+2] and "phi_convec" [ny+2,nxl+2] (flat arrays are reshaped).  Collective over `dist` when world > 1."""
+    pdf = np.asarray(local["pdf"])
+    dtype = pdf.dtype
+    nxl = rng.nx_local
+    nz, ny = pdf.shape[-3] - 2, pdf.shape[-2] - 2
+    convective = local.get("f_convec") is not None
+    layout, total = checkpoint_layout(nx_global, ny, nz, dtype, convective)
+    multi = rng.world > 1 and dist is not None
+    if rng.rank == 0:
+        with open(path, "wb") as f:
+            f.write(np.int32(ntime_next).tobytes())
+            f.write(np.asarray([force_z, rho_in], dtype=dtype).tobytes())
+            f.truncate(total)
+    if multi:
+        dist.barrier()
+    mm = np.memmap(path, dtype=np.uint8, mode="r+")
+    if mm.size != total:
+        raise IOError(f"{path}: {mm.size} bytes, expected {total}")
+    for name, (off, gshape, g) in layout.items():
+        lshape = gshape[:-1] + (nxl + 2 * g,)
+        a = np.asarray(local[name], dtype=dtype).reshape(lshape)
+        dst = np.ndarray(gshape, dtype=dtype, buffer=mm, offset=off)
+        ls, gs = _owned_columns(rng, g)
+        dst[..., gs] = a[..., ls]
+    mm.flush()
+    del mm
+    if multi:
+        dist.barrier()
+
+
+def read_checkpoint_slab(path, rng: SlabRange, nx_global: int, ny: int, nz: int, dtype, convective: bool) -> dict:
+    """This slab's part of a checkpoint file, ghost columns included (1 for the PDFs and the convective buffers, 4 for phi: the
+    neighbour's real columns, i.e. what the halo exchanges would have delivered), in the layout Solver.upload_state takes.
+    Returns the arrays plus "ntime_next", "force_z", "rho_in".  Restart: upload_state(pdf, phi, convective buffers), then
+    color_gradient() rebuilds cn_* / c_norm from phi as the reference does (src/main.cpp:112)."""
+    layout, total = checkpoint_layout(nx_global, ny, nz, dtype, convective)
+    mm = np.memmap(path, dtype=np.uint8, mode="r")
+    if mm.size != total:
+        raise IOError(f"{path}: {mm.size} bytes, expected {total} for a {nx_global} x {ny} x {nz} lattice")
+    s = np.dtype(dtype).itemsize
+    out = {"ntime_next": int(np.frombuffer(mm, np.int32, 1, 0)[0])}
+    out["force_z"], out["rho_in"] = (float(v) for v in np.frombuffer(mm, dtype, 2, 4))
+    for name, (off, gshape, g) in layout.items():
+        src = np.ndarray(gshape, dtype=dtype, buffer=mm, offset=off)
+        out[name] = np.ascontiguousarray(src[..., rng.x0 - 1:rng.x0 - 1 + rng.nx_local + 2 * g])   # global x0-g .. x1+g
+    del mm
     return out
 
 

@@ -129,6 +129,78 @@ def test_cuda_slabs_on_one_gpu_equal_single_domain(gpu_lib, name, prec, world, n
     ref.close()
 
 
+@pytest.mark.skipif(not os.environ.get("MFLBM_TEST_ACTIVITY"), reason="written after the round's GPU budget was spent: opt-in (MFLBM_TEST_ACTIVITY=1) until seen green on a B200")
+@pytest.mark.parametrize("name,prec,nsteps", [("pack_velocity", "f64", 8), ("tube_pressure", "f32", 7)])
+def test_slab_checkpoint_restart_on_another_decomposition(gpu_lib, tmp_path, name, prec, nsteps):
+    """3 CUDA slabs step, settle and write ONE checkpoint file in the reference layout (slab.write_checkpoint_slabs); 2 slabs
+    and a single domain restart from it (CudaSlab.load_checkpoint: upload pdf / phi / convective buffers, rebuild the colour
+    gradient) and continue; both must equal the uninterrupted single-domain run bit for bit."""
+    import torch
+    import mflbm
+    from mflbm import slab
+    o, ctl, solid = common.make_oracle(name, prec)
+    P = mflbm.derive_params(ctl, prec)
+    interior = (o.arr("walls_global") != 0).astype(np.int8)
+    opt, z0 = ctl["initial_fluid_distribution_option"], ctl["initial_interface_position"]
+    W = o.arr("W_in")
+    more = 6
+    ref = mflbm.Solver(P, prec)
+    ref.preprocess_geometry(interior)
+    ref.init_state(opt, z0, W_in=W)
+    for n in range(nsteps + more):
+        ref.step(1 + n)
+    want = ref.download_state()
+    ref.close()
+    path = tmp_path / "id0000"
+    stream = torch.cuda.Stream()
+
+    def make(world, init):
+        out = []
+        for r in range(world):
+            rng = slab.partition(o.nx, world, r)
+            cs = slab.CudaSlab(P, prec, rng, 0, stream=stream)
+            cs.solver.preprocess_geometry(interior)
+            Wl = np.ascontiguousarray(W[:, rng.x0 - 1:rng.x1 + 2])
+            if init:
+                cs.solver.init_state(opt, z0, W_in=Wl)
+            else:
+                cs.solver.upload_state(W_in=Wl)
+            out.append(cs)
+        return out
+
+    with torch.cuda.stream(stream):
+        first = make(3, True)
+        chain = LocalChain(first)
+        for n in range(nsteps):
+            chain.step(1 + n)
+        if nsteps % 2 == 0:
+            chain.exchange(1)      # SlabStepper.settle()
+        for cs in first:           # rank order: rank 0 creates the file
+            st = cs.solver.download_state(fields=("pdf", "phi"), convective=P.outlet_BC == 1)
+            slab.write_checkpoint_slabs(path, cs.rng, o.nx, st, nsteps + 1, float(P.force_z), float(P.rho_in))
+        for cs in first:
+            cs.solver.close()
+        for world in (2, 1):
+            again = make(world, False)
+            for cs in again:
+                assert cs.load_checkpoint(path, o.nx) == nsteps + 1
+            if world == 1:         # a plain solver: no halo buffers
+                for n in range(nsteps, nsteps + more):
+                    again[0].solver.step(1 + n)
+            else:
+                chain = LocalChain(again)
+                for n in range(nsteps, nsteps + more):
+                    chain.step(1 + n)
+                if (nsteps + more) % 2 == 0:
+                    chain.exchange(1)
+            parts = [owned(cs.solver.download_state(), cs.rng, o.nx) for cs in again]
+            for k in ("pdf", "phi", "cn_x", "cn_y", "cn_z", "c_norm"):
+                got = np.concatenate([p[k] for p in parts], axis=-1)
+                assert np.array_equal(got, want[k]), (world, k)
+            for cs in again:
+                cs.solver.close()
+
+
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 def test_full_size_decomposition_invariance_256(gpu_lib, prec):
     """BASELINE configs 2/3 at full size (256^3 sphere pack drainage, velocity inlet + convective outlet, theta 45): the

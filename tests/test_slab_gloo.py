@@ -48,6 +48,14 @@ def _worker(rank, world, port, name, prec, nsteps, outdir, balanced=False):
         st.settle()
         mine = backend.owned()
         np.savez(Path(outdir) / f"rank{rank}.npz", **mine)
+        # checkpoint in the reference's single-file layout, every rank writing its own columns: the local arrays are this slab's
+        # window of the (NaN-poisoned) full-domain arrays, i.e. what a slab solver's download_state returns
+        win = lambda a, g: a[..., rng.x0 - 1:rng.x0 - 1 + rng.nx_local + 2 * g]
+        local = dict(pdf=win(backend.pdf, 1), phi=win(backend.phi, 4))
+        if ctl["outlet_BC"] == 1:
+            local.update({k: win(o.arr(k).reshape((-1, o.ny + 2, o.nx + 2)) if k != "phi_convec" else o.arr(k).reshape(o.ny + 2, o.nx + 2), 1)
+                          for k in ("f_convec", "g_convec", "phi_convec")})
+        slab.write_checkpoint_slabs(Path(outdir) / "id0000", rng, o.nx, local, nsteps + 1, 0.25, 1.5, dist)
         # monitor reduction: per-slab sums -> global (gloo all_reduce)
         dist.barrier()
     finally:
@@ -90,6 +98,41 @@ def test_balanced_slabs_over_gloo_equal_single_domain(tmp_path):
     for k in ("pdf", "phi", "cn_x", "cn_y", "cn_z", "c_norm", "curv"):
         got = np.concatenate([p[k] for p in parts], axis=-1)
         assert np.array_equal(got, ref.arr(k)), k
+
+
+@pytest.mark.parametrize("name,prec,world,nsteps", [("pack_velocity", "f64", 3, 6), ("tube_pressure", "f32", 2, 5)])
+def test_slab_checkpoint_equals_single_domain_file(tmp_path, name, prec, world, nsteps):
+    """N slabs write one checkpoint file in the reference layout (src/IO_multiphase.cpp:252-305), each rank its own columns through
+    a memory map: byte-identical to the file a single domain writes, and readable slab by slab by any other decomposition."""
+    import common
+    from mflbm import slab
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, name, prec, nsteps, str(tmp_path)), nprocs=world, join=True)
+    ref, ctl, solid = common.make_oracle(name, prec)
+    ref.run(1, nsteps)
+    conv = ctl["outlet_BC"] == 1
+    full = dict(pdf=ref.arr("pdf"), phi=ref.arr("phi"))
+    if conv:
+        full.update(f_convec=ref.arr("f_convec").reshape(19, ref.ny + 2, ref.nx + 2), g_convec=ref.arr("g_convec").reshape(19, ref.ny + 2, ref.nx + 2),
+                    phi_convec=ref.arr("phi_convec").reshape(ref.ny + 2, ref.nx + 2))
+    single = tmp_path / "single_id0000"
+    slab.write_checkpoint_slabs(single, slab.partition(ref.nx, 1, 0), ref.nx, full, nsteps + 1, 0.25, 1.5)
+    assert single.read_bytes() == (tmp_path / "id0000").read_bytes()
+    # the host driver's reader (tests/test_host_driver.py) understands it
+    from test_host_driver import read_checkpoint
+    c = read_checkpoint(single, ref.nx, ref.ny, ref.nz, full["pdf"].dtype, conv)
+    assert c["ntime"] == nsteps + 1 and np.array_equal(c["pdf"], full["pdf"]) and np.array_equal(c["phi"], full["phi"])
+    # scatter: a different decomposition reads its slabs, ghost columns included
+    for w2 in (1, 2, 4):
+        for r in range(w2):
+            rng = slab.partition(ref.nx, w2, r)
+            got = slab.read_checkpoint_slab(tmp_path / "id0000", rng, ref.nx, ref.ny, ref.nz, full["pdf"].dtype, conv)
+            assert got["ntime_next"] == nsteps + 1 and got["force_z"] == 0.25 and got["rho_in"] == 1.5
+            for k, a in full.items():
+                g = 4 if k == "phi" else 1
+                assert np.array_equal(got[k], a[..., rng.x0 - 1:rng.x0 - 1 + rng.nx_local + 2 * g]), (w2, r, k)
+    with pytest.raises(IOError):
+        slab.read_checkpoint_slab(tmp_path / "id0000", slab.partition(ref.nx + 1, 1, 0), ref.nx + 1, ref.ny, ref.nz, full["pdf"].dtype, conv)
 
 
 def test_balanced_cuts():
