@@ -385,6 +385,43 @@ def read_checkpoint_slab(path, rng: SlabRange, nx_global: int, ny: int, nz: int,
 
 
 # ----------------------------------------------------------------------------------------------------------
+# phase-field output of a decomposed lattice: the reference's legacy-VTK "small_" file (VTK_legacy_writer_3D type 2,
+# /root/reference/src/IO_multiphase.cpp:500-716: STRUCTURED_POINTS, one big-endian float per interior node, phi zeroed in
+# solids), every rank writing its own x columns of the one file.
+# ----------------------------------------------------------------------------------------------------------
+def vtk_header(nx: int, ny: int, nz: int, name: str = "phi", typ: str = "float") -> bytes:
+    return (f"# vtk DataFile Version 3.0\nvtk output\nBINARY\nDATASET STRUCTURED_POINTS\nDIMENSIONS {nx} {ny} {nz}\n"
+            f"ORIGIN 1 1 1\nSPACING 1 1 1\nPOINT_DATA {nx * ny * nz}\nSCALARS {name} {typ}\nLOOKUP_TABLE default\n").encode()
+
+
+def write_vtk_phase_slabs(path, rng: SlabRange, nx_global: int, phi_local: np.ndarray, solid_local: np.ndarray, dist=None) -> None:
+    """phi_local: this slab's phi in the 4-ghost reference layout [nz+8, ny+8, nxl+8] (Solver.download_state); solid_local: its
+    interior wall flags [nz, ny, nxl] (non-zero = solid).  Collective over `dist` when world > 1."""
+    nz, ny, nxl = solid_local.shape
+    if phi_local.shape != (nz + 8, ny + 8, nxl + 8) or nxl != rng.nx_local:
+        raise ValueError("phi_local / solid_local do not match the slab")
+    head = vtk_header(nx_global, ny, nz)
+    total = len(head) + 4 * nx_global * ny * nz
+    multi = rng.world > 1 and dist is not None
+    if rng.rank == 0:
+        with open(path, "wb") as f:
+            f.write(head)
+            f.truncate(total)
+    if multi:
+        dist.barrier()
+    mm = np.memmap(path, dtype=np.uint8, mode="r+")
+    if mm.size != total:
+        raise IOError(f"{path}: {mm.size} bytes, expected {total}")
+    field = np.ndarray((nz, ny, nx_global), dtype=">f4", buffer=mm, offset=len(head))
+    v = np.where(solid_local != 0, 0.0, phi_local[4:-4, 4:-4, 4:-4]).astype(np.float32)
+    field[:, :, rng.x0 - 1:rng.x0 - 1 + nxl] = v
+    mm.flush()
+    del mm
+    if multi:
+        dist.barrier()
+
+
+# ----------------------------------------------------------------------------------------------------------
 # bench leg for N > 1 (called by bench.py under torchrun): weak scaling, (S*N) x S x S cut into N slabs
 # ----------------------------------------------------------------------------------------------------------
 def bench_slabs(args, rank: int, world: int, local: int) -> dict | None:

@@ -56,6 +56,8 @@ def _worker(rank, world, port, name, prec, nsteps, outdir, balanced=False):
             local.update({k: win(o.arr(k).reshape((-1, o.ny + 2, o.nx + 2)) if k != "phi_convec" else o.arr(k).reshape(o.ny + 2, o.nx + 2), 1)
                           for k in ("f_convec", "g_convec", "phi_convec")})
         slab.write_checkpoint_slabs(Path(outdir) / "id0000", rng, o.nx, local, nsteps + 1, 0.25, 1.5, dist)
+        solid_local = (o.arr("walls_global") != 0)[:, :, rng.x0 - 1:rng.x1]
+        slab.write_vtk_phase_slabs(Path(outdir) / "small.vtk", rng, o.nx, win(backend.phi, 4), solid_local, dist)
         # monitor reduction: per-slab sums -> global (gloo all_reduce)
         dist.barrier()
     finally:
@@ -131,6 +133,16 @@ def test_slab_checkpoint_equals_single_domain_file(tmp_path, name, prec, world, 
             for k, a in full.items():
                 g = 4 if k == "phi" else 1
                 assert np.array_equal(got[k], a[..., rng.x0 - 1:rng.x0 - 1 + rng.nx_local + 2 * g]), (w2, r, k)
+    # phase-field VTK file written by the slabs: the reference's "small_" format, phi zeroed in solids
+    from test_host_driver import read_vtk
+    header, npts, fields = read_vtk(tmp_path / "small.vtk")
+    assert header[4] == f"DIMENSIONS {ref.nx} {ref.ny} {ref.nz}" and npts == ref.nx * ref.ny * ref.nz
+    typ, payload = fields["phi"]
+    assert typ == "float" and len(payload) == 4 * npts
+    got = np.frombuffer(payload, ">f4").reshape(ref.nz, ref.ny, ref.nx)
+    solid_g = ref.arr("walls_global") != 0
+    want = np.where(solid_g, 0.0, ref.arr("phi")[4:-4, 4:-4, 4:-4]).astype(np.float32)
+    assert np.array_equal(got, want)
     with pytest.raises(IOError):
         slab.read_checkpoint_slab(tmp_path / "id0000", slab.partition(ref.nx + 1, 1, 0), ref.nx + 1, ref.ny, ref.nz, full["pdf"].dtype, conv)
 
