@@ -39,10 +39,13 @@ FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
 # ----------------------------------------------------------------------------------------------------------
 # workload
 # ----------------------------------------------------------------------------------------------------------
-def workload_control(nx: int, ny: int, nz: int) -> dict:
+def workload_control(nx: int, ny: int, nz: int, case: str = "drainage") -> dict:
+    """drainage (BASELINE configs[1-3]): the lattice starts full of fluid 2 and fluid 1 is injected (option 1, saturation_injection 1);
+    imbibition (configs[4]): the roles are swapped (option 2, saturation_injection 0)"""
     import refcase as rc
     ctl = dict(rc.DEFAULT_CONTROL)
-    ctl.update(nxGlobal=nx, nyGlobal=ny, nzGlobal=nz, initial_fluid_distribution_option=1, saturation_injection=1.0, theta=45,
+    opt, inj = (1, 1.0) if case == "drainage" else (2, 0.0)
+    ctl.update(nxGlobal=nx, nyGlobal=ny, nzGlobal=nz, initial_fluid_distribution_option=opt, saturation_injection=inj, theta=45,
                initial_interface_position=8.0, inlet_BC=1, outlet_BC=1, capillary_number=1e-4, n_exclude_inlet=10, n_exclude_outlet=10,
                fluid1_viscosity=0.04, fluid2_viscosity=0.4, surface_tension=0.03, RK_beta=0.95, body_force_0=0.0)
     return ctl
@@ -207,15 +210,15 @@ def run_ours(args) -> dict:
     S = args.size
     NX = args.global_nx or S
     prec = args.prec
-    ctl = workload_control(NX, S, S)
-    solid = workload_geometry(NX, S, S, kind=args.geometry)
+    ctl = workload_control(NX, S, S, args.case)
+    solid = workload_geometry(NX, S, S, seed=args.seed, kind=args.geometry)
     stream = torch.cuda.Stream()
     solver = mflbm.Solver(mflbm.derive_params(ctl, prec), prec, device=local, stream=stream.cuda_stream)
     t0 = time.perf_counter()
     solver.preprocess_geometry(solid)
     t_geo = time.perf_counter() - t0
     W = inlet_profile(ctl, prec)
-    solver.init_state(1, ctl["initial_interface_position"], W_in=W)
+    solver.init_state(ctl["initial_fluid_distribution_option"], ctl["initial_interface_position"], W_in=W)
     n_fluid, n_site = solver.num_fluid_nodes, NX * S * S
     dims = f"{S}^3" if NX == S else f"{NX}x{S}x{S}"
     # ---- device-resident timing -------------------------------------------------------------------
@@ -292,7 +295,7 @@ def run_ours(args) -> dict:
         "scaling": "strong" if args.global_nx else "weak",
         "vs_baseline": None, "dtype": prec, "data": "synthetic",
         "config": {"workload": (f"{dims} random sphere pack (radius 12, porosity ~0.4)" if args.geometry == "pack" else f"DIAGNOSTIC {dims} empty duct") +
-                               f", drainage, velocity inlet + convective outlet, theta 45, {prec}",
+                               f", {args.case}, velocity inlet + convective outlet, theta 45, {prec}",
                    "lattice": [NX, S, S], "fluid_nodes": n_fluid, "porosity": n_fluid / n_site, "parallelism": "1 GPU",
                    "l2": f"state {(38 * s_bytes * n_fluid) / 1e9:.2f}+ GB >> 126 MB L2 (inputs larger than L2, no flush needed)",
                    "fluid_mlups": n_fluid * args.steps / 1e6 / (ms * 1e-3), "geometry_preprocess_s": t_geo,
@@ -334,8 +337,8 @@ def run_reference(args) -> dict:
     if not exe.exists():
         base["unavailable"] = f"{exe} missing (oracle/build_ref.sh needs /root/reference)"
         return base
-    ctl = workload_control(NX, S, S)
-    solid = workload_geometry(NX, S, S)
+    ctl = workload_control(NX, S, S, args.case)
+    solid = workload_geometry(NX, S, S, seed=args.seed)
     solid_file = solid.copy()   # the reference applies the x/y walls itself (src/Misc.cpp:67-78); harmless to pre-apply
     with tempfile.TemporaryDirectory() as td:
         td = Path(td)
@@ -347,7 +350,7 @@ def run_reference(args) -> dict:
         host = dict(l.split() for l in (out / "host_timing.txt").read_text().splitlines())
     mlups = float(tim["mlups"])
     base.update({"value": mlups, "ms_per_step": float(tim["ms_per_step"]),
-                 "config": {"workload": f"{dims} random sphere pack (radius 12, porosity ~0.4), drainage, velocity inlet + convective outlet, theta 45, {prec}",
+                 "config": {"workload": f"{dims} random sphere pack (radius 12, porosity ~0.4), {args.case}, velocity inlet + convective outlet, theta 45, {prec}",
                             "what": "reference CUDA kernels (unmodified sources, nvcc sm_100 -O3, block 128x1x1) via main_iteration_kernel_GPU()",
                             "host_setup_s": float(host["initialization_basic_multi_s"]), "wall_s": wall},
                  "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": 1, "kind": "reference",
@@ -368,6 +371,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="N > 1: halo messages through peer memory (default) or NCCL send/recv")
+    ap.add_argument("--case", default="drainage", choices=["drainage", "imbibition"], help="imbibition = BASELINE configs[4]")
+    ap.add_argument("--seed", type=int, default=20240229, help="sphere-pack seed (configs[3]: 20240230)")
     ap.add_argument("--partition", default="equal", choices=["equal", "balanced"],
                     help="N > 1: equal-width x-slabs, or cuts that balance fluid nodes + halo cost per rank (slab.balanced_cuts)")
     ap.add_argument("--halo-cost", type=float, default=10.0,

@@ -432,12 +432,13 @@ def bench_slabs(args, rank: int, world: int, local: int) -> dict | None:
     S, prec = args.size, args.prec
     strong = int(getattr(args, "global_nx", 0) or 0)
     nxg = strong if strong else S * world      # strong scaling: fixed NX x S x S lattice; weak: S^3 per GPU
-    ctl = B.workload_control(nxg, S, S)
+    case, seed = getattr(args, "case", "drainage"), int(getattr(args, "seed", 20240229))
+    ctl = B.workload_control(nxg, S, S, case)
     rng = partition(nxg, world, rank)
     if getattr(args, "partition", "equal") == "balanced" and world > 1:
         # every rank counts the fluid nodes of its equal-width columns, the counts are gathered, and all ranks derive the same
         # cost-balanced cuts (fluid nodes + a per-neighbour halo cost expressed in fluid-node updates per face site)
-        w = B.workload_geometry_window(nxg, S, S, rng.x0, rng.x1, kind=args.geometry)
+        w = B.workload_geometry_window(nxg, S, S, rng.x0, rng.x1, seed=seed, kind=args.geometry)
         mine = (w[:, :, rng.x0 - 1:rng.x1] == 0).sum(axis=(0, 1)).astype(np.float64)
         del w
         parts = [None] * world
@@ -448,12 +449,12 @@ def bench_slabs(args, rank: int, world: int, local: int) -> dict | None:
     with torch.cuda.stream(stream):
         slab = CudaSlab(params, prec, rng, local, stream=stream)
         t0 = time.perf_counter()
-        solid = B.workload_geometry_window(nxg, S, S, rng.x0 - 12, rng.x1 + 12, kind=args.geometry)
+        solid = B.workload_geometry_window(nxg, S, S, rng.x0 - 12, rng.x1 + 12, seed=seed, kind=args.geometry)
         slab.solver.preprocess_geometry(solid)
         t_geo = time.perf_counter() - t0
         W = B.inlet_profile(ctl, prec)
         W_local = np.ascontiguousarray(W[:, rng.x0 - 1:rng.x1 + 2])   # local columns 0..nx+1 of the global profile
-        slab.solver.init_state(1, ctl["initial_interface_position"], W_in=W_local)
+        slab.solver.init_state(ctl["initial_fluid_distribution_option"], ctl["initial_interface_position"], W_in=W_local)
         if getattr(args, "halo", "p2p") == "p2p":
             slab.connect_p2p(dist)
         stepper = SlabStepper(slab, rng)
@@ -516,7 +517,7 @@ def bench_slabs(args, rank: int, world: int, local: int) -> dict | None:
             "metric": "multiphase MLUPS (all lattice sites, reference definition src/main.cpp:270)", "value": n_site * args.steps / 1e6 / (ms * 1e-3),
             "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": prec, "data": "synthetic",
-            "config": {"workload": f"{nxg}x{S}x{S} random sphere pack (radius 12, porosity ~0.4)" + ("" if strong else f" = {S}^3 per GPU") + f", drainage, velocity inlet + convective outlet, theta 45, {prec}",
+            "config": {"workload": f"{nxg}x{S}x{S} random sphere pack (radius 12, porosity ~0.4)" + ("" if strong else f" = {S}^3 per GPU") + f", {case}, velocity inlet + convective outlet, theta 45, {prec}",
                        "lattice": [nxg, S, S], "fluid_nodes": n_fluid, "porosity": n_fluid / n_site, "parallelism": f"{world} x-slabs, halos " + ("pushed into peer memory over NVLink (CUDA IPC), arrival flags, no collective" if getattr(slab, "p2p", False) else "NCCL send/recv"),
                        "l2": "state per GPU >> 126 MB L2 (inputs larger than L2, no flush needed)",
                        "fluid_mlups": n_fluid * args.steps / 1e6 / (ms * 1e-3), "geometry_preprocess_s": t_geo,
