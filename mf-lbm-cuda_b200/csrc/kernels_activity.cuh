@@ -23,9 +23,9 @@
 //                  and slab halos need no special case)
 //   k_act_dilate   quiet[b] over the 27 bricks around b:  0 = both kinds present (an interface may be near: evaluate),
 //                  1 = every non-solid site is within eps of +1, 2 = of -1, 3 = no non-solid site at all
-// The 27-brick neighbourhood reaches >= 4 sites in every direction, so k_normals_act / k_alter_act / k_extrap_cn_act below store exactly
-// what the full kernels would store at the sites of a quiet brick, and skip their gathers.  k_extrap_phi always runs in
-// full (its result there is s only to within rounding).
+// The 27-brick neighbourhood reaches >= 4 sites in every direction, so k_normals_act / k_alter_act / k_extrap_cn_act below
+// store exactly what the full kernels would store at the sites of a quiet brick, and skip their gathers.  k_extrap_phi
+// always runs in full (its result there is s only to within rounding).
 #pragma once
 #include "core.cuh"
 #include "kernels_step.cuh"
