@@ -369,7 +369,7 @@ def main():
     ap.add_argument("--global-nx", type=int, default=0, help="strong scaling: the lattice is NX x S x S whatever the number of GPUs")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg: profiling runs, and --size 512 at N > 1 (the leg keeps two host copies of every rank's state, 36 GB per rank in f64)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="N > 1: halo messages through peer memory (default) or NCCL send/recv")
     ap.add_argument("--case", default="drainage", choices=["drainage", "imbibition"], help="imbibition = BASELINE configs[4]")
     ap.add_argument("--seed", type=int, default=20240229, help="sphere-pack seed (configs[3]: 20240230)")
