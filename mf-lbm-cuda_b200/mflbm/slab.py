@@ -290,13 +290,20 @@ def reduce_monitor(m: dict, rng: SlabRange, params, dist, device=None) -> dict:
     import torch
     keys = ["vol1_sum", "vol2_sum", "mass1_sum", "mass2_sum", "vol1_full", "vol2_full", "mass1_full", "mass2_full",
             "fl1_avg", "fl2_avg", "fl1_avg_whole", "fl2_avg_whole"]
-    sums = torch.tensor([m[k] for k in keys] + list(m["kinetic_energy"]), dtype=torch.float64, device=device)
+    keys += [k for k in ("pre_w_sum", "pre_nw_sum", "n_w", "n_nw", "outlet_phase1_count") if k in m]   # capillary-pressure / breakthrough monitors (src/Monitor.cpp:376-459)
+    sums = torch.tensor([float(m[k]) for k in keys] + list(m["kinetic_energy"]), dtype=torch.float64, device=device)
     mx = torch.tensor([m["umax"], float(m["nan_detected"])], dtype=torch.float64, device=device)
     if rng.world > 1:
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     out = dict(zip(keys, sums[:len(keys)].tolist()))
     out["kinetic_energy"] = sums[len(keys):].tolist()
+    if "profiles" in m:   # the 7 per-slice sums behind results/out1.output/profile/* (src/Monitor.cpp:34-80): additive over slabs
+        names = sorted(m["profiles"])
+        prof = torch.tensor(np.stack([np.asarray(m["profiles"][k], dtype=np.float64) for k in names]), dtype=torch.float64, device=device)
+        if rng.world > 1:
+            dist.all_reduce(prof, op=dist.ReduceOp.SUM)
+        out["profiles"] = {k: prof[i].cpu().numpy() for i, k in enumerate(names)}
     out["umax"], out["nan_detected"] = float(mx[0]), int(mx[1])
     out["saturation"] = out["vol1_sum"] / (out["vol1_sum"] + out["vol2_sum"])
     out["saturation_full_domain"] = out["vol1_full"] / (out["vol1_full"] + out["vol2_full"])

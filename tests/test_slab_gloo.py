@@ -147,6 +147,41 @@ def test_slab_checkpoint_equals_single_domain_file(tmp_path, name, prec, world, 
         slab.read_checkpoint_slab(tmp_path / "id0000", slab.partition(ref.nx + 1, 1, 0), ref.nx + 1, ref.ny, ref.nz, full["pdf"].dtype, conv)
 
 
+def _monitor_worker(rank, world, port, outdir):
+    import json
+    import types
+    import torch.distributed as dist
+    from mflbm import slab
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        r = rank + 1.0
+        m = dict(vol1_sum=1.0 * r, vol2_sum=3.0 * r, mass1_sum=r, mass2_sum=r, vol1_full=2.0 * r, vol2_full=2.0 * r, mass1_full=r, mass2_full=r,
+                 fl1_avg=0.5 * r, fl2_avg=0.25 * r, fl1_avg_whole=r, fl2_avg_whole=r, kinetic_energy=[r, 2 * r], umax=0.1 * r, nan_detected=int(rank == 1),
+                 pre_w_sum=10.0 * r, pre_nw_sum=20.0 * r, n_w=4 * (rank + 1), n_nw=2 * (rank + 1), outlet_phase1_count=rank,
+                 profiles={k: np.full(5, r) * (i + 1) for i, k in enumerate(("fl1", "fl2", "pre", "mass1", "mass2", "vol1", "vol2"))})
+        params = types.SimpleNamespace(A_xy=4.0, la_nu1=0.5, lbm_gamma=0.25)
+        out = slab.reduce_monitor(m, slab.partition(16, world, rank), params, dist)
+        out["profiles"] = {k: v.tolist() for k, v in out["profiles"].items()}
+        (Path(outdir) / f"mon{rank}.json").write_text(json.dumps(out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_monitor_reduction_over_gloo(tmp_path):
+    """per-slab monitor sums -> global figures (SUM / MAX all_reduce), the per-slice profiles and the capillary-pressure sums"""
+    import json
+    world = 3
+    mp.spawn(_monitor_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    outs = [json.loads((tmp_path / f"mon{r}.json").read_text()) for r in range(world)]
+    assert all(o == outs[0] for o in outs)            # every rank holds the same global figures
+    o = outs[0]
+    assert o["vol1_sum"] == 6.0 and o["vol2_sum"] == 18.0 and o["saturation"] == 0.25 and o["saturation_full_domain"] == 0.5
+    assert o["kinetic_energy"] == [6.0, 12.0] and abs(o["umax"] - 0.3) < 1e-15 and o["nan_detected"] == 1
+    assert o["pre_w_sum"] == 60.0 and o["n_w"] == 24.0 and o["n_nw"] == 12.0 and o["outlet_phase1_count"] == 3.0
+    assert o["ca"] == ((3.0 + 1.5) / 4.0) * 0.5 / 0.25
+    assert o["profiles"]["fl1"] == [6.0] * 5 and o["profiles"]["vol2"] == [42.0] * 5
+
+
 def test_balanced_cuts():
     from mflbm import slab
     rng = np.random.default_rng(3)
