@@ -78,3 +78,16 @@ def test_criterion_on_the_benchmark_workload(prec):
     nonsolid = wt <= 0
     frac = np.count_nonzero(quiet4 & nonsolid) / np.count_nonzero(nonsolid)
     assert frac > 0.5, frac
+
+
+def test_python_constants_mirror_the_kernel_header():
+    """the numpy emulation above must test the criterion the CUDA code applies: same brick extents, same tolerances"""
+    import re
+    from pathlib import Path
+    src = (Path(__file__).resolve().parent.parent / "mf-lbm-cuda_b200" / "csrc" / "kernels_activity.cuh").read_text()
+    m = re.search(r"ACT_BX = (\d+), ACT_BY = (\d+), ACT_BZ = (\d+)", src)
+    assert m and tuple(int(v) for v in m.groups()) == (BX, BY, BZ)
+    d = re.search(r"act_eps<double>\(\) \{ return ([0-9.e+-]+); \}", src)
+    f = re.search(r"act_eps<float>\(\) \{ return ([0-9.e+-]+)f; \}", src)
+    assert d and float(d.group(1)) == EPS["f64"]
+    assert f and float(f.group(1)) == EPS["f32"]
