@@ -418,25 +418,35 @@ __device__ __forceinline__ void halo_publish(const HaloSync& hs) {
         }
     }
 }
-__device__ __forceinline__ void halo_await(const HaloSync& hs) {
-    if (!hs.flag) return;
+// false: the message did not arrive (now or earlier - the error word is sticky, so every later wait gives up at once and
+// the state stops changing through halos); the caller then leaves the lattice untouched and the host sees the error at
+// its next synchronisation, download or run call (Solver::check_halo_error)
+__device__ __forceinline__ bool halo_await(const HaloSync& hs) {
+    if (!hs.flag) return true;
+    __shared__ int ok_s;
     if (threadIdx.x == 0 && threadIdx.y == 0) {
-        const unsigned want = *reinterpret_cast<volatile unsigned*>(hs.seq);
-        const long long t0 = clock64();
-        // sequence numbers only grow; the signed difference survives wrap-around
-        while ((int)(*reinterpret_cast<volatile unsigned*>(hs.flag) - want) < 0) {
-            __nanosleep(64);
-            if (clock64() - t0 > HALO_TIMEOUT_CYCLES) { if (hs.error) *hs.error = 1u + (unsigned)(hs.flag - (hs.error - 31)); break; }
+        int ok = 1;
+        if (hs.error && *reinterpret_cast<volatile unsigned*>(hs.error) != 0u) ok = 0;
+        else {
+            const unsigned want = *reinterpret_cast<volatile unsigned*>(hs.seq);
+            const long long t0 = clock64();
+            // sequence numbers only grow; the signed difference survives wrap-around
+            while ((int)(*reinterpret_cast<volatile unsigned*>(hs.flag) - want) < 0) {
+                __nanosleep(64);
+                if (clock64() - t0 > HALO_TIMEOUT_CYCLES) { if (hs.error) *hs.error = 1u + (unsigned)(hs.flag - (hs.error - 31)); ok = 0; break; }
+            }
         }
         __threadfence_system();
+        ok_s = ok;
     }
     __syncthreads();
+    return ok_s != 0;
 }
 
 // copy column `col` of the ten slots (PLUS ? ex=+1 : ex=-1) between the lattice and a buffer
 template <typename T, bool PLUS, bool PACK>
 __global__ void k_halo_pdf(const Lattice<T> L, T* __restrict__ buf, const int col, const HaloSync hs) {
-    if (!PACK) halo_await(hs);
+    if (!PACK && !halo_await(hs)) return;
     const int y = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
     if (y < L.NY1) {
         const int plane = L.NY1 * L.NZ1;
@@ -459,7 +469,7 @@ __global__ void k_halo_pdf(const Lattice<T> L, T* __restrict__ buf, const int co
 // copy 4 phi columns starting at local column `col0` between the lattice and a buffer
 template <typename T, bool PACK>
 __global__ void k_halo_phi(const Lattice<T> L, T* __restrict__ buf, const int col0, const HaloSync hs) {
-    if (!PACK) halo_await(hs);
+    if (!PACK && !halo_await(hs)) return;
     const int y = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;   // 0-based over the 4-ghost extents
     if (y < L.PY) {
         const int plane = L.PY * L.PZ;

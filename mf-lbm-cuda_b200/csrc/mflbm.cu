@@ -83,6 +83,16 @@ struct Solver {
     // staging buffer for layout conversion at the boundary
     void* d_stage = nullptr;
     size_t stage_bytes = 0;
+    // state upload / download: a ring of RING_NB staging buffers; the PCIe copies run on copy_stream, the layout kernels
+    // on `stream`, chained with events, so that array n+1 crosses the bus while array n is being permuted (the first
+    // version did copy -> kernel -> host synchronisation 38 times through one buffer)
+    static constexpr int RING_NB = 3;
+    void* d_ring[RING_NB] = {nullptr, nullptr, nullptr};
+    size_t ring_bytes = 0;
+    int ring_pos = 0;
+    bool ring_used[RING_NB] = {false, false, false};
+    cudaEvent_t ev_ring_copy[RING_NB] = {nullptr, nullptr, nullptr}, ev_ring_kernel[RING_NB] = {nullptr, nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;
     // monitor
     double* d_mon = nullptr;
     double* h_mon = nullptr;
@@ -126,8 +136,56 @@ struct Solver {
     }
     void drop_stage() { if (d_stage) { cudaStreamSynchronize(stream); cudaFree(d_stage); d_stage = nullptr; stage_bytes = 0; } }
 
+    void ring_reserve(size_t bytes) {
+        if (!copy_stream) {
+            MF_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+            for (int b = 0; b < RING_NB; b++) {
+                MF_CUDA(cudaEventCreateWithFlags(&ev_ring_copy[b], cudaEventDisableTiming));
+                MF_CUDA(cudaEventCreateWithFlags(&ev_ring_kernel[b], cudaEventDisableTiming));
+            }
+        }
+        if (bytes <= ring_bytes) return;
+        ring_drain(true);
+        for (int b = 0; b < RING_NB; b++) MF_CUDA(cudaMalloc(&d_ring[b], bytes));
+        ring_bytes = bytes;
+    }
+    // host array -> staging buffer (copy_stream) -> launch(staging pointer) on `stream`; returns without waiting
+    template <typename F>
+    void ring_upload(const void* host, size_t bytes, F&& launch) {
+        const int b = ring_pos;
+        ring_pos = (ring_pos + 1) % RING_NB;
+        if (ring_used[b]) MF_CUDA(cudaStreamWaitEvent(copy_stream, ev_ring_kernel[b], 0));   // its last reader has finished
+        MF_CUDA(cudaMemcpyAsync(d_ring[b], host, bytes, cudaMemcpyHostToDevice, copy_stream));
+        MF_CUDA(cudaEventRecord(ev_ring_copy[b], copy_stream));
+        MF_CUDA(cudaStreamWaitEvent(stream, ev_ring_copy[b], 0));
+        launch(d_ring[b]);
+        MF_CUDA(cudaEventRecord(ev_ring_kernel[b], stream));
+        ring_used[b] = true;
+    }
+    // launch(staging pointer) on `stream` -> staging buffer -> host array (copy_stream)
+    template <typename F>
+    void ring_download(void* host, size_t bytes, F&& launch) {
+        const int b = ring_pos;
+        ring_pos = (ring_pos + 1) % RING_NB;
+        if (ring_used[b]) MF_CUDA(cudaStreamWaitEvent(stream, ev_ring_copy[b], 0));   // its last copy has left
+        launch(d_ring[b]);
+        MF_CUDA(cudaEventRecord(ev_ring_kernel[b], stream));
+        MF_CUDA(cudaStreamWaitEvent(copy_stream, ev_ring_kernel[b], 0));
+        MF_CUDA(cudaMemcpyAsync(host, d_ring[b], bytes, cudaMemcpyDeviceToHost, copy_stream));
+        MF_CUDA(cudaEventRecord(ev_ring_copy[b], copy_stream));
+        ring_used[b] = true;
+    }
+    void ring_drain(bool release) {
+        if (copy_stream) cudaStreamSynchronize(copy_stream);
+        if (stream) cudaStreamSynchronize(stream);
+        for (int b = 0; b < RING_NB; b++) ring_used[b] = false;
+        ring_pos = 0;
+        if (release) { for (int b = 0; b < RING_NB; b++) if (d_ring[b]) { cudaFree(d_ring[b]); d_ring[b] = nullptr; } ring_bytes = 0; }
+    }
+
     void create(const Params* p, const mflbm_slab* sl, int dev, void* strm) {
         device = dev;
+        MF_CUDA(cudaSetDevice(device));   // before any stream / event is created: they belong to the current device
         if (const char* v = getenv("MFLBM_VARIANT")) variant = atoi(v);
         if (const char* v = getenv("MFLBM_MAX_CTAS")) max_ctas = atoi(v);
         if (const char* v = getenv("MFLBM_ACTIVITY")) activity = atoi(v) != 0;
@@ -137,7 +195,6 @@ struct Solver {
             MF_CUDA(cudaEventCreateWithFlags(&ev_act_fork, cudaEventDisableTiming));
             MF_CUDA(cudaEventCreateWithFlags(&ev_act_join, cudaEventDisableTiming));
         }
-        MF_CUDA(cudaSetDevice(device));
         MF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
         if (strm) { stream = (cudaStream_t)strm; own_stream = false; }
         else { MF_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true; }
@@ -212,6 +269,12 @@ struct Solver {
         dfree(d_act_raw); dfree(d_act_quiet); dfree(d_brick_n); dfree(d_brick_cn); dfree(d_brick_alter);
         dfree(d_mon); dfree(d_phi_old); dfree(d_p2p); d_flags = nullptr;
         if (d_stage) { cudaFree(d_stage); d_stage = nullptr; }
+        ring_drain(true);
+        for (int b = 0; b < RING_NB; b++) {
+            if (ev_ring_copy[b]) { cudaEventDestroy(ev_ring_copy[b]); ev_ring_copy[b] = nullptr; }
+            if (ev_ring_kernel[b]) { cudaEventDestroy(ev_ring_kernel[b]); ev_ring_kernel[b] = nullptr; }
+        }
+        if (copy_stream) { cudaStreamDestroy(copy_stream); copy_stream = nullptr; }
         for (int kind = 0; kind < 3; kind++) for (int side = 0; side < 2; side++) { dfree(d_send[kind][side]); d_recv[kind][side] = nullptr; }
         if (h_mon) { cudaFreeHost(h_mon); h_mon = nullptr; }
         if (aux_stream) { cudaStreamDestroy(aux_stream); aux_stream = nullptr; }
@@ -248,19 +311,16 @@ struct Solver {
     dim3 grid_box(int G, int bx) const { return dim3(ceil_div(L.nx + 2 * G, bx), L.ny + 2 * G, L.nz + 2 * G); }
 
     // reference-layout array (ghost width G) on the host <-> U-grid array on the device
+    // (asynchronous: the caller drains the ring before the host arrays may be reused / read)
     template <typename S>
     void to_u(const S* host, S* d_u, int G, long long n) {
-        S* st = (S*)stage(sizeof(S) * n);
-        MF_CUDA(cudaMemcpyAsync(st, host, sizeof(S) * n, cudaMemcpyHostToDevice, stream));
-        k_repitch<T, S, true><<<grid_box(G, 128), 128, 0, stream>>>(L, G, st, d_u); check_launch(); count();
-        MF_CUDA(cudaStreamSynchronize(stream));   // the staging buffer is reused by the next array
+        ring_reserve(sizeof(S) * n);
+        ring_upload(host, sizeof(S) * n, [&](void* st) { k_repitch<T, S, true><<<grid_box(G, 128), 128, 0, stream>>>(L, G, (S*)st, d_u); check_launch(); count(); });
     }
     template <typename S>
     void from_u(S* host, S* d_u, int G, long long n) {
-        S* st = (S*)stage(sizeof(S) * n);
-        k_repitch<T, S, false><<<grid_box(G, 128), 128, 0, stream>>>(L, G, st, d_u); check_launch(); count();
-        MF_CUDA(cudaMemcpyAsync(host, st, sizeof(S) * n, cudaMemcpyDeviceToHost, stream));
-        MF_CUDA(cudaStreamSynchronize(stream));
+        ring_reserve(sizeof(S) * n);
+        ring_download(host, sizeof(S) * n, [&](void* st) { k_repitch<T, S, false><<<grid_box(G, 128), 128, 0, stream>>>(L, G, (S*)st, d_u); check_launch(); count(); });
     }
 
     // ------------------------------------------------------------------------------------------------
@@ -466,14 +526,11 @@ struct Solver {
     void upload_state(const T* pdf, const T* phi, const T* cnx, const T* cny, const T* cnz, const T* cnorm, const T* curv,
                       const T* Win, const T* fconv, const T* gconv, const T* phiconv) {
         if (!have_geometry) MF_FAIL("upload_state before geometry (the PDF site order depends on it)");
+        ring_reserve(sizeof(T) * (size_t)N4);
         if (pdf) {
             const dim3 g = grid_box(1, 128);
-            for (int s = 0; s < 38; s++) {
-                T* st = (T*)stage(sizeof(T) * N1);
-                MF_CUDA(cudaMemcpyAsync(st, pdf + (size_t)s * N1, sizeof(T) * N1, cudaMemcpyHostToDevice, stream));
-                k_pdf_slot<T, true><<<g, 128, 0, stream>>>(L, st, s); check_launch(); count();
-                MF_CUDA(cudaStreamSynchronize(stream));
-            }
+            for (int s = 0; s < 38; s++)
+                ring_upload(pdf + (size_t)s * N1, sizeof(T) * N1, [&](void* st) { k_pdf_slot<T, true><<<g, 128, 0, stream>>>(L, (T*)st, s); check_launch(); count(); });
         }
         if (phi) to_u<T>(phi, d_phi, 4, N4);
         if (cnx) to_u<T>(cnx, d_cnx, 2, N2);
@@ -487,20 +544,17 @@ struct Solver {
         (void)curv;   // curv is a pure function of cn_* (CSF_Forces, :908-1003): recomputed where it is consumed, never stored
         auto up = [&](T* d, const T* h, long long n) { if (h) MF_CUDA(cudaMemcpyAsync(d, h, sizeof(T) * n, cudaMemcpyHostToDevice, stream)); };
         up(d_Win, Win, NP); up(d_fconv, fconv, NP * 19); up(d_gconv, gconv, NP * 19); up(d_phiconv, phiconv, NP);
-        MF_CUDA(cudaStreamSynchronize(stream));
-        drop_stage();
+        ring_drain(true);
     }
 
     void download_state(T* pdf, T* phi, T* cnx, T* cny, T* cnz, T* cnorm, T* curv, T* fconv, T* gconv, T* phiconv) {
         if (!have_geometry) MF_FAIL("download_state before geometry");
+        check_halo_error();   // a state behind a lost halo message must not reach a checkpoint
+        ring_reserve(sizeof(T) * (size_t)N4);
         if (pdf) {
             const dim3 g = grid_box(1, 128);
-            for (int s = 0; s < 38; s++) {
-                T* st = (T*)stage(sizeof(T) * N1);
-                k_pdf_slot<T, false><<<g, 128, 0, stream>>>(L, st, s); check_launch(); count();
-                MF_CUDA(cudaMemcpyAsync(pdf + (size_t)s * N1, st, sizeof(T) * N1, cudaMemcpyDeviceToHost, stream));
-                MF_CUDA(cudaStreamSynchronize(stream));
-            }
+            for (int s = 0; s < 38; s++)
+                ring_download(pdf + (size_t)s * N1, sizeof(T) * N1, [&](void* st) { k_pdf_slot<T, false><<<g, 128, 0, stream>>>(L, (T*)st, s); check_launch(); count(); });
         }
         if (phi) from_u<T>(phi, d_phi, 4, N4);
         if (cnx) from_u<T>(cnx, d_cnx, 2, N2);
@@ -508,16 +562,14 @@ struct Solver {
         if (cnz) from_u<T>(cnz, d_cnz, 2, N2);
         if (cnorm) from_u<T>(cnorm, d_cnorm, 2, N2);
         if (curv) {   // the stepping path keeps curv at fluid nodes only; give the caller the reference's dense array (:908-1003 over [1..n]^3)
-            T* st = (T*)stage(sizeof(T) * N1);
-            MF_CUDA(cudaMemsetAsync(st, 0, sizeof(T) * N1, stream));
-            k_curvature_dense<T><<<dim3(ceil_div(L.nx, 128), L.ny, L.nz), 128, 0, stream>>>(L, st); check_launch(); count();
-            MF_CUDA(cudaMemcpyAsync(curv, st, sizeof(T) * N1, cudaMemcpyDeviceToHost, stream));
-            MF_CUDA(cudaStreamSynchronize(stream));
+            ring_download(curv, sizeof(T) * N1, [&](void* st) {
+                MF_CUDA(cudaMemsetAsync(st, 0, sizeof(T) * N1, stream));
+                k_curvature_dense<T><<<dim3(ceil_div(L.nx, 128), L.ny, L.nz), 128, 0, stream>>>(L, (T*)st); check_launch(); count();
+            });
         }
         auto dn = [&](T* h, const T* d, long long n) { if (h) MF_CUDA(cudaMemcpyAsync(h, d, sizeof(T) * n, cudaMemcpyDeviceToHost, stream)); };
         dn(fconv, d_fconv, NP * 19); dn(gconv, d_gconv, NP * 19); dn(phiconv, d_phiconv, NP);
-        MF_CUDA(cudaStreamSynchronize(stream));
-        drop_stage();
+        ring_drain(true);
     }
 
     // the cn_* / c_norm arrays hold values the chain did not write (fresh geometry, upload, init): every entry must be stored once
@@ -536,7 +588,7 @@ struct Solver {
         if (!phi_s4 && (option < 1 || option > 5)) MF_FAIL("initial_fluid_distribution_option %d not supported on the device (1..5)", option);
         const int bx = 128;
         MF_CUDA(cudaMemsetAsync(d_phi, 0, sizeof(T) * PN, stream));
-        if (phi_s4) { to_u<T>(phi_s4, d_phi, 4, N4); drop_stage(); }
+        if (phi_s4) { to_u<T>(phi_s4, d_phi, 4, N4); ring_drain(true); }
         else { k_init_phi<T><<<grid_box(4, bx), bx, 0, stream>>>(L, option, interface_z0, (int)P.ny, (int)P.nz, open_z() ? 1 : 0); count(); }
         check_launch();
         k_init_pdf<T><<<grid_box(1, bx), bx, 0, stream>>>(L, P.outlet_BC == 1 ? 1 : 0); check_launch();
@@ -743,6 +795,7 @@ struct Solver {
     void run(int ntime_first, int nsteps) {
         if (nsteps <= 0) return;
         if (!have_geometry) MF_FAIL("step before geometry");
+        if (is_slab && (slab.has_left || slab.has_right)) check_halo_error();   // fail fast once a message has been lost
         int nt = ntime_first, left = nsteps;
         // the collide launch carries bulk_skip = cn_consistent as an argument: step once outside the graph after arrays came
         // from outside, so that the captured pair has the fast setting in both of its collide launches
@@ -835,6 +888,7 @@ struct Solver {
 
     void download_macro(T* rho, T* u, T* v, T* w) {
         if (!have_geometry) MF_FAIL("download_macro before geometry");
+        check_halo_error();
         T* out[4] = {rho, u, v, w};
         int n = 0;
         for (auto q : out) n += q != nullptr;
@@ -971,8 +1025,19 @@ using namespace mflbm;
     catch (const std::exception& e) { g_last_error = e.what(); return 2; } \
     catch (...) { g_last_error = "unknown error"; return 3; }
 
+// every entry point runs with the solver's device current and restores the caller's afterwards (a caller that drives
+// several devices from one thread, e.g. mflbm_run with x-slabs, must not launch onto foreign streams)
+struct DeviceGuard {
+    int prev = -1, want = -1;
+    explicit DeviceGuard(int dev) : want(dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != want && cudaSetDevice(want) != cudaSuccess) throw Error{"cudaSetDevice failed for the solver's device"};
+    }
+    ~DeviceGuard() { if (prev >= 0 && prev != want) cudaSetDevice(prev); }
+};
 #define MF_SOLVER(P, REAL) reinterpret_cast<Solver<REAL>*>(s)
 #define MF_NEED(s) if (!(s)) throw Error{"null solver handle"}
+#define MF_ENTER(P, REAL) MF_NEED(s); DeviceGuard device_guard_(MF_SOLVER(P, REAL)->device)
 
 #define MFLBM_DEFINE_API(P, REAL)                                                                                                     \
     extern "C" int mflbm_##P##_create(const mflbm_##P##_params* params, const mflbm_slab* slab, int device, void* stream,                 \
@@ -980,58 +1045,61 @@ using namespace mflbm;
         MF_GUARD({                                                                                                                        \
             if (!params || !out) throw Error{"create: null argument"};                                                                    \
             auto* sv = new Solver<REAL>();                                                                                                \
+            DeviceGuard device_guard_(device);                                                                                            \
             try { sv->create(params, slab, device, stream); } catch (...) { sv->destroy(); delete sv; throw; }                            \
             *out = reinterpret_cast<mflbm_##P##_solver*>(sv);                                                                             \
         })                                                                                                                                \
     }                                                                                                                                     \
-    extern "C" int mflbm_##P##_destroy(mflbm_##P##_solver* s) { MF_GUARD({ if (s) { MF_SOLVER(P, REAL)->destroy(); delete MF_SOLVER(P, REAL); } }) } \
+    extern "C" int mflbm_##P##_destroy(mflbm_##P##_solver* s) {                                                                          \
+        MF_GUARD({ if (s) { DeviceGuard device_guard_(MF_SOLVER(P, REAL)->device); MF_SOLVER(P, REAL)->destroy(); delete MF_SOLVER(P, REAL); } }) \
+    }                                                                                                                                     \
     extern "C" int mflbm_##P##_set_params(mflbm_##P##_solver* s, const mflbm_##P##_params* params) {                                      \
-        MF_GUARD({ MF_NEED(s); if (!params) throw Error{"null params"}; MF_SOLVER(P, REAL)->set_params(params); })                        \
+        MF_GUARD({ MF_ENTER(P, REAL); if (!params) throw Error{"null params"}; MF_SOLVER(P, REAL)->set_params(params); })                        \
     }                                                                                                                                     \
     extern "C" int mflbm_##P##_upload_geometry(mflbm_##P##_solver* s, const int32_t* walls, const int32_t* walls_type, const REAL* s_nx,   \
                                                const REAL* s_ny, const REAL* s_nz) {                                                      \
-        MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->upload_geometry(walls, walls_type, s_nx, s_ny, s_nz); })                               \
+        MF_GUARD({ MF_ENTER(P, REAL); MF_SOLVER(P, REAL)->upload_geometry(walls, walls_type, s_nx, s_ny, s_nz); })                               \
     }                                                                                                                                     \
     extern "C" int mflbm_##P##_preprocess_geometry(mflbm_##P##_solver* s, const int8_t* w) {                                              \
-        MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->preprocess_geometry(w); })                                                             \
+        MF_GUARD({ MF_ENTER(P, REAL); MF_SOLVER(P, REAL)->preprocess_geometry(w); })                                                             \
     }                                                                                                                                     \
     extern "C" int mflbm_##P##_download_geometry(mflbm_##P##_solver* s, int32_t* walls, int32_t* walls_type, REAL* s_nx, REAL* s_ny,       \
                                                  REAL* s_nz, int64_t* counts) {                                                           \
-        MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->download_geometry(walls, walls_type, s_nx, s_ny, s_nz, counts); })                     \
+        MF_GUARD({ MF_ENTER(P, REAL); MF_SOLVER(P, REAL)->download_geometry(walls, walls_type, s_nx, s_ny, s_nz, counts); })                     \
     }                                                                                                                                     \
     extern "C" int mflbm_##P##_upload_state(mflbm_##P##_solver* s, const REAL* pdf, const REAL* phi, const REAL* cn_x, const REAL* cn_y,   \
                                             const REAL* cn_z, const REAL* c_norm, const REAL* curv, const REAL* W_in, const REAL* f_convec, \
                                             const REAL* g_convec, const REAL* phi_convec) {                                               \
-        MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->upload_state(pdf, phi, cn_x, cn_y, cn_z, c_norm, curv, W_in, f_convec, g_convec, phi_convec); }) \
+        MF_GUARD({ MF_ENTER(P, REAL); MF_SOLVER(P, REAL)->upload_state(pdf, phi, cn_x, cn_y, cn_z, c_norm, curv, W_in, f_convec, g_convec, phi_convec); }) \
     }                                                                                                                                     \
     extern "C" int mflbm_##P##_init_state(mflbm_##P##_solver* s, int option, REAL interface_z0, const REAL* W_in) {                       \
-        MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->init_state(option, interface_z0, W_in); })                                             \
+        MF_GUARD({ MF_ENTER(P, REAL); MF_SOLVER(P, REAL)->init_state(option, interface_z0, W_in); })                                             \
     }                                                                                                                                     \
     extern "C" int mflbm_##P##_init_state_from_phi(mflbm_##P##_solver* s, const REAL* phi, const REAL* W_in) {                            \
-        MF_GUARD({ MF_NEED(s); if (!phi) throw Error{"init_state_from_phi: null phi"}; MF_SOLVER(P, REAL)->init_state(0, REAL(0), W_in, phi); }) \
+        MF_GUARD({ MF_ENTER(P, REAL); if (!phi) throw Error{"init_state_from_phi: null phi"}; MF_SOLVER(P, REAL)->init_state(0, REAL(0), W_in, phi); }) \
     }                                                                                                                                     \
     extern "C" int mflbm_##P##_download_state(mflbm_##P##_solver* s, REAL* pdf, REAL* phi, REAL* cn_x, REAL* cn_y, REAL* cn_z,             \
                                               REAL* c_norm, REAL* curv, REAL* f_convec, REAL* g_convec, REAL* phi_convec) {               \
-        MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->download_state(pdf, phi, cn_x, cn_y, cn_z, c_norm, curv, f_convec, g_convec, phi_convec); }) \
+        MF_GUARD({ MF_ENTER(P, REAL); MF_SOLVER(P, REAL)->download_state(pdf, phi, cn_x, cn_y, cn_z, c_norm, curv, f_convec, g_convec, phi_convec); }) \
     }                                                                                                                                     \
-    extern "C" int mflbm_##P##_step(mflbm_##P##_solver* s, int ntime) { MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->step(ntime); }) }       \
+    extern "C" int mflbm_##P##_step(mflbm_##P##_solver* s, int ntime) { MF_GUARD({ MF_ENTER(P, REAL); MF_SOLVER(P, REAL)->step(ntime); }) }       \
     extern "C" int mflbm_##P##_run(mflbm_##P##_solver* s, int ntime_first, int nsteps) {                                                  \
-        MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->run(ntime_first, nsteps); })                                                           \
+        MF_GUARD({ MF_ENTER(P, REAL); MF_SOLVER(P, REAL)->run(ntime_first, nsteps); })                                                           \
     }                                                                                                                                     \
-    extern "C" int mflbm_##P##_color_gradient(mflbm_##P##_solver* s) { MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->gradient_chain(); }) } \
-    extern "C" int mflbm_##P##_monitor(mflbm_##P##_solver* s, mflbm_monitor_out* out) { MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->monitor(out); }) } \
+    extern "C" int mflbm_##P##_color_gradient(mflbm_##P##_solver* s) { MF_GUARD({ MF_ENTER(P, REAL); MF_SOLVER(P, REAL)->gradient_chain(); }) } \
+    extern "C" int mflbm_##P##_monitor(mflbm_##P##_solver* s, mflbm_monitor_out* out) { MF_GUARD({ MF_ENTER(P, REAL); MF_SOLVER(P, REAL)->monitor(out); }) } \
     extern "C" int mflbm_##P##_phi_change(mflbm_##P##_solver* s, int seed, double* d_phi_max) {                                           \
-        MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->phi_change(seed, d_phi_max); })                                                        \
+        MF_GUARD({ MF_ENTER(P, REAL); MF_SOLVER(P, REAL)->phi_change(seed, d_phi_max); })                                                        \
     }                                                                                                                                     \
     extern "C" int mflbm_##P##_download_macro(mflbm_##P##_solver* s, REAL* rho, REAL* u, REAL* v, REAL* w) {                              \
-        MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->download_macro(rho, u, v, w); })                                                       \
+        MF_GUARD({ MF_ENTER(P, REAL); MF_SOLVER(P, REAL)->download_macro(rho, u, v, w); })                                                       \
     }                                                                                                                                     \
     extern "C" int mflbm_##P##_sync(mflbm_##P##_solver* s) {                                                                              \
-        MF_GUARD({ MF_NEED(s); MF_CUDA(cudaStreamSynchronize(MF_SOLVER(P, REAL)->stream)); MF_SOLVER(P, REAL)->check_halo_error(); })      \
+        MF_GUARD({ MF_ENTER(P, REAL); MF_CUDA(cudaStreamSynchronize(MF_SOLVER(P, REAL)->stream)); MF_SOLVER(P, REAL)->check_halo_error(); })      \
     }                                                                                                                                     \
     extern "C" int mflbm_##P##_halo_buffers(mflbm_##P##_solver* s, int kind, int side, REAL** send, REAL** recv, int64_t* count) {        \
         MF_GUARD({                                                                                                                        \
-            MF_NEED(s);                                                                                                                   \
+            MF_ENTER(P, REAL);                                                                                                                   \
             if (kind < 0 || kind > 2 || side < 0 || side > 1) throw Error{"halo_buffers: bad kind/side"};                                 \
             if (!MF_SOLVER(P, REAL)->is_slab) throw Error{"halo_buffers on a non-slab solver"};                                           \
             if (send) *send = MF_SOLVER(P, REAL)->d_send[kind][side];                                                                     \
@@ -1039,11 +1107,11 @@ using namespace mflbm;
             if (count) *count = MF_SOLVER(P, REAL)->halo_count(kind);                                                                     \
         })                                                                                                                                \
     }                                                                                                                                     \
-    extern "C" int mflbm_##P##_halo_pack(mflbm_##P##_solver* s, int kind) { MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->halo_pack(kind); }) } \
-    extern "C" int mflbm_##P##_halo_unpack(mflbm_##P##_solver* s, int kind) { MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->halo_unpack(kind); }) } \
+    extern "C" int mflbm_##P##_halo_pack(mflbm_##P##_solver* s, int kind) { MF_GUARD({ MF_ENTER(P, REAL); MF_SOLVER(P, REAL)->halo_pack(kind); }) } \
+    extern "C" int mflbm_##P##_halo_unpack(mflbm_##P##_solver* s, int kind) { MF_GUARD({ MF_ENTER(P, REAL); MF_SOLVER(P, REAL)->halo_unpack(kind); }) } \
     extern "C" int mflbm_##P##_halo_p2p_local(mflbm_##P##_solver* s, int kind, int side, REAL** recv, uint32_t** flag) {                  \
         MF_GUARD({                                                                                                                        \
-            MF_NEED(s);                                                                                                                   \
+            MF_ENTER(P, REAL);                                                                                                                   \
             if (kind < 0 || kind > 2 || side < 0 || side > 1) throw Error{"halo_p2p_local: bad kind/side"};                               \
             if (!MF_SOLVER(P, REAL)->is_slab) throw Error{"halo_p2p_local on a non-slab solver"};                                         \
             if (recv) *recv = MF_SOLVER(P, REAL)->d_recv[kind][side];                                                                     \
@@ -1052,19 +1120,19 @@ using namespace mflbm;
     }                                                                                                                                     \
     extern "C" int mflbm_##P##_halo_p2p_region(mflbm_##P##_solver* s, void** base, int64_t* bytes) {                                      \
         MF_GUARD({                                                                                                                        \
-            MF_NEED(s);                                                                                                                   \
+            MF_ENTER(P, REAL);                                                                                                                   \
             if (!MF_SOLVER(P, REAL)->is_slab) throw Error{"halo_p2p_region on a non-slab solver"};                                        \
             if (base) *base = MF_SOLVER(P, REAL)->d_p2p;                                                                                  \
             if (bytes) *bytes = (int64_t)MF_SOLVER(P, REAL)->p2p_bytes;                                                                   \
         })                                                                                                                                \
     }                                                                                                                                     \
     extern "C" int mflbm_##P##_halo_p2p_connect(mflbm_##P##_solver* s, int kind, int side, REAL* peer_recv, uint32_t* peer_flag) {        \
-        MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->halo_connect(kind, side, peer_recv, peer_flag); })                                     \
+        MF_GUARD({ MF_ENTER(P, REAL); MF_SOLVER(P, REAL)->halo_connect(kind, side, peer_recv, peer_flag); })                                     \
     }                                                                                                                                     \
-    extern "C" int mflbm_##P##_halo_push(mflbm_##P##_solver* s, int kind) { MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->halo_pack(kind, true); }) } \
-    extern "C" int mflbm_##P##_halo_unpack_wait(mflbm_##P##_solver* s, int kind) { MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->halo_unpack(kind, true); }) } \
+    extern "C" int mflbm_##P##_halo_push(mflbm_##P##_solver* s, int kind) { MF_GUARD({ MF_ENTER(P, REAL); MF_SOLVER(P, REAL)->halo_pack(kind, true); }) } \
+    extern "C" int mflbm_##P##_halo_unpack_wait(mflbm_##P##_solver* s, int kind) { MF_GUARD({ MF_ENTER(P, REAL); MF_SOLVER(P, REAL)->halo_unpack(kind, true); }) } \
     extern "C" int mflbm_##P##_step_phase(mflbm_##P##_solver* s, int ntime, int phase) {                                                  \
-        MF_GUARD({ MF_NEED(s); MF_SOLVER(P, REAL)->step_phase(ntime, phase); })                                                           \
+        MF_GUARD({ MF_ENTER(P, REAL); MF_SOLVER(P, REAL)->step_phase(ntime, phase); })                                                           \
     }                                                                                                                                     \
     extern "C" int64_t mflbm_##P##_num_fluid_nodes(mflbm_##P##_solver* s) { return s ? MF_SOLVER(P, REAL)->n_fluid : -1; }                \
     extern "C" int64_t mflbm_##P##_kernel_launches(mflbm_##P##_solver* s) { return s ? MF_SOLVER(P, REAL)->launches : -1; }               \

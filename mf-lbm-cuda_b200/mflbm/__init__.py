@@ -291,6 +291,17 @@ class Solver:
         rc = self._fn("init_state_from_phi")(self.h, self._in(phi, self.rt, self._shape(4)), self._in(W_in, self.rt, (self.ny + 2, self.nx + 2)))
         self._check(rc)
 
+    def state_shapes(self, convective: bool | None = None) -> dict:
+        """shapes of the arrays download_state returns (reference layouts), e.g. to allocate pinned host buffers"""
+        if convective is None:
+            convective = self.params.outlet_BC == 1
+        s1, s2, s4 = self._shape(1), self._shape(2), self._shape(4)
+        pl = (self.ny + 2, self.nx + 2)
+        out = dict(pdf=(2, 19) + s1, phi=s4, cn_x=s2, cn_y=s2, cn_z=s2, c_norm=s2, curv=s1)
+        if convective:
+            out.update(f_convec=(19,) + pl, g_convec=(19,) + pl, phi_convec=pl)
+        return out
+
     def download_state(self, convective: bool | None = None, fields=None) -> dict:
         """fields: optional subset of ("pdf","phi","cn_x","cn_y","cn_z","c_norm","curv") to fetch (default all)"""
         if convective is None:
@@ -426,3 +437,10 @@ def ipc_import(handle: bytes) -> int:
     if lib.mflbm_ipc_import(C.create_string_buffer(handle, 64), C.byref(out)) != 0:
         raise MflbmError(lib.mflbm_last_error().decode())
     return out.value
+
+
+def ipc_release(device_ptr: int) -> None:
+    """close a mapping opened by ipc_import"""
+    lib = load_library()
+    if lib.mflbm_ipc_release(C.c_void_p(device_ptr)) != 0:
+        raise MflbmError(lib.mflbm_last_error().decode())

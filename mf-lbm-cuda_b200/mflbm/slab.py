@@ -261,13 +261,31 @@ class CudaSlab:
         st = self.solver.download_state(fields=("pdf", "phi"), convective=self.solver.params.outlet_BC == 1)
         write_checkpoint_slabs(path, self.rng, nx_global, st, ntime_next, float(self.solver.params.force_z), float(self.solver.params.rho_in), dist)
 
-    def load_checkpoint(self, path, nx_global: int) -> int:
-        """restart this slab from a checkpoint file written by any decomposition; returns the step index to continue with"""
+    def load_checkpoint(self, path, nx_global: int, W_in=None, rho_in_new: bool = False) -> int:
+        """Restart this slab from a checkpoint file written by any decomposition; returns the step index to continue with.
+        As in the reference's restart (/root/reference/src/Init_multiphase.cpp:519-520) and in mflbm_run, force_z and rho_in come
+        from the file (rho_in_new = True keeps the control file's rho_in, `rho_in_new` key).  W_in: this slab's columns of the
+        inlet velocity profile (needed unless init_state has already uploaded it)."""
         P = self.solver.params
         c = read_checkpoint_slab(path, self.rng, nx_global, int(P.ny), int(P.nz), self.solver.rt, P.outlet_BC == 1)
-        self.solver.upload_state(pdf=c["pdf"], phi=c["phi"], f_convec=c.get("f_convec"), g_convec=c.get("g_convec"), phi_convec=c.get("phi_convec"))
+        P.force_z = c["force_z"]
+        if not rho_in_new:
+            P.rho_in = c["rho_in"]
+        self.solver.set_params(P)
+        self.solver.upload_state(pdf=c["pdf"], phi=c["phi"], W_in=W_in, f_convec=c.get("f_convec"), g_convec=c.get("g_convec"), phi_convec=c.get("phi_convec"))
         self.solver.color_gradient()
         return c["ntime_next"]
+
+    def close(self) -> None:
+        """destroy the solver and close the CUDA IPC mappings of the neighbours' buffers"""
+        import mflbm
+        self.solver.close()
+        for pbase in getattr(self, "_peer_bases", {}).values():
+            try:
+                mflbm.ipc_release(pbase)
+            except Exception:
+                pass
+        self._peer_bases = {}
 
     def halo_push(self, kind):
         self.solver.halo_push(kind)
@@ -426,117 +444,3 @@ def write_vtk_phase_slabs(path, rng: SlabRange, nx_global: int, phi_local: np.nd
     del mm
     if multi:
         dist.barrier()
-
-
-# ----------------------------------------------------------------------------------------------------------
-# bench leg for N > 1 (called by bench.py under torchrun): weak scaling, (S*N) x S x S cut into N slabs
-# ----------------------------------------------------------------------------------------------------------
-def bench_slabs(args, rank: int, world: int, local: int) -> dict | None:
-    import torch
-    import torch.distributed as dist
-    import bench as B
-    import mflbm
-    S, prec = args.size, args.prec
-    strong = int(getattr(args, "global_nx", 0) or 0)
-    nxg = strong if strong else S * world      # strong scaling: fixed NX x S x S lattice; weak: S^3 per GPU
-    case, seed = getattr(args, "case", "drainage"), int(getattr(args, "seed", 20240229))
-    ctl = B.workload_control(nxg, S, S, case)
-    rng = partition(nxg, world, rank)
-    if getattr(args, "partition", "equal") == "balanced" and world > 1:
-        # every rank counts the fluid nodes of its equal-width columns, the counts are gathered, and all ranks derive the same
-        # cost-balanced cuts (fluid nodes + a per-neighbour halo cost expressed in fluid-node updates per face site)
-        w = B.workload_geometry_window(nxg, S, S, rng.x0, rng.x1, seed=seed, kind=args.geometry)
-        mine = (w[:, :, rng.x0 - 1:rng.x1] == 0).sum(axis=(0, 1)).astype(np.float64)
-        del w
-        parts = [None] * world
-        dist.all_gather_object(parts, mine)
-        rng = partition_balanced(np.concatenate(parts), world, rank, side_cost=float(args.halo_cost) * S * S)
-    params = mflbm.derive_params(ctl, prec)
-    stream = torch.cuda.Stream(device=local)
-    with torch.cuda.stream(stream):
-        slab = CudaSlab(params, prec, rng, local, stream=stream)
-        t0 = time.perf_counter()
-        solid = B.workload_geometry_window(nxg, S, S, rng.x0 - 12, rng.x1 + 12, seed=seed, kind=args.geometry)
-        slab.solver.preprocess_geometry(solid)
-        t_geo = time.perf_counter() - t0
-        W = B.inlet_profile(ctl, prec)
-        W_local = np.ascontiguousarray(W[:, rng.x0 - 1:rng.x1 + 2])   # local columns 0..nx+1 of the global profile
-        slab.solver.init_state(ctl["initial_fluid_distribution_option"], ctl["initial_interface_position"], W_in=W_local)
-        if getattr(args, "halo", "p2p") == "p2p":
-            slab.connect_p2p(dist)
-        stepper = SlabStepper(slab, rng)
-        stepper.run(1, args.warmup)
-        nt = 1 + args.warmup
-        torch.cuda.synchronize()
-        dist.barrier()
-        l0 = slab.solver.kernel_launches
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with B.ClockSampler(local) as clk:
-            torch.cuda.synchronize()
-            e0.record(stream)
-            stepper.run(nt, args.steps)
-            e1.record(stream)
-            torch.cuda.synchronize()
-            dist.barrier()
-        nt += args.steps
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        ms = float(ms[0])
-        launches = slab.solver.kernel_launches - l0
-        nf = torch.tensor([slab.solver.num_fluid_nodes], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(nf, op=dist.ReduceOp.SUM)
-        n_fluid = int(nf[0])
-        mon = reduce_monitor(slab.solver.monitor(), rng, params, dist, device=f"cuda:{local}")
-        # ---- end to end through the C ABI: pinned host state -> device, K steps, monitor + state back ----------
-        h2d, t_e2e = 0, None
-        if not getattr(args, "no_e2e", False):
-            st = slab.solver.download_state()
-            pinned = {k: torch.from_numpy(v).pin_memory() for k, v in st.items()}
-            host = {k: v.numpy() for k, v in pinned.items()}
-            h2d = sum(v.nbytes for v in host.values())
-            torch.cuda.synchronize()
-            dist.barrier()
-            t0 = time.perf_counter()
-            slab.solver.upload_state(**{k: host[k] for k in ("pdf", "phi", "cn_x", "cn_y", "cn_z", "c_norm", "curv")},
-                                     f_convec=host.get("f_convec"), g_convec=host.get("g_convec"), phi_convec=host.get("phi_convec"))
-            t1 = time.perf_counter()
-            stepper.run(nt, args.steps)
-            t2 = time.perf_counter()
-            reduce_monitor(slab.solver.monitor(), rng, params, dist, device=f"cuda:{local}")
-            t3 = time.perf_counter()
-            slab.solver.download_state_into(host)
-            torch.cuda.synchronize()
-            if os.environ.get("MFLBM_BENCH_DEBUG"):
-                print(f"[rank {rank}] e2e: upload {t1 - t0:.3f} s, run (enqueue) {t2 - t1:.3f} s, monitor {t3 - t2:.3f} s, download {time.perf_counter() - t3:.3f} s", file=sys.stderr, flush=True)
-            te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            t_e2e = float(te[0])
-    n_site = nxg * S * S
-    s_bytes = 8 if prec == "f64" else 4
-    bytes_step = 78 * s_bytes * n_fluid + n_site
-    peak, peak_src = B.hbm_peak()
-    ms_step = ms / args.steps
-    achieved = bytes_step / world / (ms_step * 1e-3) / 1e9    # per GPU
-    out = None
-    if rank == 0:
-        assert mon["nan_detected"] == 0, "simulation produced non-finite values"
-        out = {
-            "metric": "multiphase MLUPS (all lattice sites, reference definition src/main.cpp:270)", "value": n_site * args.steps / 1e6 / (ms * 1e-3),
-            "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": prec, "data": "synthetic",
-            "config": {"workload": f"{nxg}x{S}x{S} random sphere pack (radius 12, porosity ~0.4)" + ("" if strong else f" = {S}^3 per GPU") + f", {case}, velocity inlet + convective outlet, theta 45, {prec}",
-                       "lattice": [nxg, S, S], "fluid_nodes": n_fluid, "porosity": n_fluid / n_site, "parallelism": f"{world} x-slabs, halos " + ("pushed into peer memory over NVLink (CUDA IPC), arrival flags, no collective" if getattr(slab, "p2p", False) else "NCCL send/recv"),
-                       "l2": "state per GPU >> 126 MB L2 (inputs larger than L2, no flush needed)",
-                       "fluid_mlups": n_fluid * args.steps / 1e6 / (ms * 1e-3), "geometry_preprocess_s": t_geo,
-                       "saturation_full_domain": mon["saturation_full_domain"], "halo_exchanges_per_step": 2,
-                       "partition": getattr(args, "partition", "equal"), "slab_width_rank0": rng.nx_local},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "peak_source": peak_src, "bytes_model": "78*sizeof(real)*N_fluid + N_site per step, per GPU", "bytes_per_step": bytes_step / world},
-            "e2e": {"value": n_site * args.steps / 1e6 / t_e2e if t_e2e else None, "unit": "MLUPS", "h2d_bytes_per_step": h2d * world / args.steps,
-                    "d2h_bytes_per_step": h2d * world / args.steps,
-                    "what": "per rank: upload_state from pinned host + K steps + monitor (all_reduce) + download_state, through the C ABI"},
-            "gpu_launches": int(launches) * world,
-            "clocks": clk.summary(),
-        }
-    slab.solver.close()
-    return out

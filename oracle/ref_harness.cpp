@@ -12,7 +12,14 @@
 //   ref_gpu_f32 / ref_gpu_f64   nvcc, links the reference's two .cu files: adds time stepping.
 //
 // Usage (cwd must contain input/simulation_control.txt, input/job_status.txt, ...):
-//   ref_xxx <outdir> [--dump n1,n2,...] [--monitor n1,n2,...] [--time WARMUP STEPS]
+//   ref_xxx <outdir> [--dump n1,n2,...] [--monitor n1,n2,...] [--time WARMUP STEPS] [--e2e K] [--block X,Y,Z]
+//
+// --e2e K (after everything else): the end-to-end cost of K steps for a caller that owns HOST arrays, measured with the
+// reference's own transfer code: MemAllocate_multi_GPU(1) (cudaMalloc + H2D of the whole state,
+// src/Init_multiphase_GPU.cu:72-97, the state half of initialization_GPU()), K calls of main_iteration_kernel_GPU() with
+// the timers set so that its D2H block (src/main_iteration_GPU.cu:2058-2076) fires on the last step only.  Geometry
+// stays resident.  Written to e2e.txt.
+// --block X,Y,Z overrides block_Threads_X/Y/Z of the control file (tuning runs of the baseline).
 //
 // The include block below mirrors src/main.cpp:11-27 because the reference keeps all state in globals
 // that are *defined* by these headers.
@@ -135,15 +142,18 @@ static void device_to_host() {
 #endif
 
 int main(int argc, char** argv) {
-    if (argc < 2) { fprintf(stderr, "usage: %s <outdir> [--dump a,b,..] [--monitor a,b,..] [--time W K]\n", argv[0]); return 1; }
+    if (argc < 2) { fprintf(stderr, "usage: %s <outdir> [--dump a,b,..] [--monitor a,b,..] [--time W K] [--e2e K] [--block X,Y,Z]\n", argv[0]); return 1; }
     std::string outdir = argv[1];
     std::set<int> dumps, monitors;
-    int time_warm = -1, time_steps = 0;
+    int time_warm = -1, time_steps = 0, e2e_steps = 0;
+    std::vector<int> block_override;
     for (int a = 2; a < argc; a++) {
         std::string s = argv[a];
         if (s == "--dump" && a + 1 < argc) dumps = parse_list(argv[++a]);
         else if (s == "--monitor" && a + 1 < argc) monitors = parse_list(argv[++a]);
         else if (s == "--time" && a + 2 < argc) { time_warm = atoi(argv[++a]); time_steps = atoi(argv[++a]); }
+        else if (s == "--e2e" && a + 1 < argc) { e2e_steps = atoi(argv[++a]); }
+        else if (s == "--block" && a + 1 < argc) { std::stringstream ss(argv[++a]); std::string tok; while (std::getline(ss, tok, ',')) block_override.push_back(std::stoi(tok)); }
         else { fprintf(stderr, "bad arg %s\n", s.c_str()); return 1; }
     }
     fs::create_directories(outdir);
@@ -179,7 +189,8 @@ int main(int argc, char** argv) {
     for (int d : dumps) last = std::max(last, d);
     for (int d : monitors) last = std::max(last, d);
     if (time_warm >= 0) last = std::max(last, time_warm + time_steps);
-    if (last > 0) {
+    if (last > 0 || e2e_steps > 0) {
+        if (block_override.size() == 3) { block_Threads_X = block_override[0]; block_Threads_Y = block_override[1]; block_Threads_Z = block_override[2]; }
         initialization_GPU();
         copyConstantData();
         FILE* fmon = nullptr;
@@ -215,6 +226,38 @@ int main(int argc, char** argv) {
             fprintf(fp, "steps %d\nseconds %.9f\nms_per_step %.6f\nmlups %.3f\n", time_steps, timed_s, 1e3 * timed_s / time_steps, mlups);
             fclose(fp);
             printf("REF_TIMING steps=%d seconds=%.6f mlups=%.3f\n", time_steps, timed_s, mlups);
+        }
+        if (e2e_steps > 0) {
+            // the host arrays take the device state (as after a timer step), the device copy of the state is dropped
+            device_to_host();
+            MemAllocate_multi_GPU(0);
+            CK(cudaDeviceSynchronize());
+            const int first = ntime, lastn = ntime + e2e_steps - 1;
+            if (e2e_steps >= first) { fprintf(stderr, "--e2e: K must be smaller than the current step index\n"); return 1; }
+            ntime_monitor = ntime_animation = ntime_visual = 2000000000;
+            ntime_clock_sum = lastn;   // ntime % ntime_clock_sum == 0 only at ntime == lastn inside the window
+            auto e0 = chrono::steady_clock::now();
+            MemAllocate_multi_GPU(1);
+            CK(cudaDeviceSynchronize());
+            auto e1 = chrono::steady_clock::now();
+            for (ntime = first; ntime <= lastn; ntime++) main_iteration_kernel_GPU();
+            CK(cudaDeviceSynchronize());
+            auto e2 = chrono::steady_clock::now();
+            const double s_up = chrono::duration<double>(e1 - e0).count(), s_all = chrono::duration<double>(e2 - e0).count();
+            auto e3 = chrono::steady_clock::now();
+            monitor();   // the reference's monitor is a host loop over the downloaded arrays (src/Monitor.cpp:17); timed apart
+            const double s_mon = chrono::duration<double>(chrono::steady_clock::now() - e3).count();
+            const long long plane = NXG1 * NYG1 * (long long)sizeof(T_P);
+            const long long conv = outlet_BC == 1 ? 39 * plane : 0;
+            const long long h2d = 2 * mem_size_s1_TP + plane + mem_size_f1_TP + 4 * mem_size_s2_TP + conv + mem_size_s4_TP;
+            const long long d2h = mem_size_s4_TP + mem_size_s1_TP + 4 * mem_size_s2_TP + mem_size_f1_TP;
+            std::string f = outdir + "/e2e.txt";
+            FILE* fp = fopen(f.c_str(), "w");
+            const double mlups = (double)nxGlobal * nyGlobal * nzGlobal * e2e_steps / (1e6 * s_all);
+            fprintf(fp, "steps %d\nseconds %.9f\nupload_seconds %.9f\nhost_monitor_seconds %.9f\nmlups %.3f\nh2d_bytes %lld\nd2h_bytes %lld\n",
+                    e2e_steps, s_all, s_up, s_mon, mlups, h2d, d2h);
+            fclose(fp);
+            printf("REF_E2E steps=%d seconds=%.6f upload=%.6f mlups=%.3f\n", e2e_steps, s_all, s_up, mlups);
         }
     }
 #else
