@@ -293,6 +293,7 @@ def measure_single(args, prec: str, local: int, want_e2e: bool) -> dict:
             solver.sync()
     mon = solver.monitor()
     assert mon["nan_detected"] == 0, "simulation produced non-finite values"
+    chain_bricks = solver.chain_bricks() if solver.chain == "brick" else None
     ms_step = ms / args.steps
     traffic = None
     tf = REPO / "profiles" / "traffic.json"
@@ -303,7 +304,7 @@ def measure_single(args, prec: str, local: int, want_e2e: bool) -> dict:
             traffic = None
     rec = {"prec": prec, "lattice": [NX, S, S], "n_fluid": n_fluid, "n_site": n_site, "ms": ms, "ms_per_step": ms_step,
            "mlups": n_site * args.steps / 1e6 / (ms * 1e-3), "launches": int(launches), "t_geo": t_geo, "clocks": clk.summary(),
-           "saturation_full_domain": mon["saturation_full_domain"], "activity": solver.activity,
+           "saturation_full_domain": mon["saturation_full_domain"], "chain": solver.chain, "chain_bricks": chain_bricks,
            "roofline": roofline_record(prec, n_fluid, n_site, ms_step, t_odd, t_even, traffic), "e2e": None}
     # ---- end to end through the C ABI with host buffers ---------------------------------------------
     if want_e2e:
@@ -362,7 +363,8 @@ def run_ours(args) -> dict:
                    "lattice": [NX, S, S], "fluid_nodes": r["n_fluid"], "porosity": r["n_fluid"] / r["n_site"], "parallelism": "1 GPU",
                    "l2": f"state {(38 * s_bytes * r['n_fluid']) / 1e9:.2f}+ GB >> 126 MB L2 (inputs larger than L2, no flush needed)",
                    "fluid_mlups": r["n_fluid"] * args.steps / 1e6 / (r["ms"] * 1e-3), "geometry_preprocess_s": r["t_geo"],
-                   "saturation_full_domain": r["saturation_full_domain"], "activity_map": r["activity"]},
+                   "saturation_full_domain": r["saturation_full_domain"], "gradient_chain": r["chain"],
+                   "chain_bricks_processed_of_total": r["chain_bricks"]},
         "roofline": r["roofline"],
         "e2e": r["e2e"] if r["e2e"] is not None else {"value": None, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "skipped": "--no-e2e"},
         "gpu_launches": r["launches"],
@@ -634,8 +636,8 @@ def main():
                     help="N > 1: equal-width x-slabs, or cuts that balance fluid nodes + halo cost per rank (slab.balanced_cuts)")
     ap.add_argument("--halo-cost", type=float, default=10.0,
                     help="--partition balanced: cost of one neighbour per face site, in fluid-node updates (f64 256^2 faces: ~104 us = 10.5)")
-    ap.add_argument("--activity", type=int, default=None, choices=[0, 1],
-                    help="gradient chain with the interface-activity map (kernels_activity.cuh); default: the library's (MFLBM_ACTIVITY)")
+    ap.add_argument("--chain", default=None, choices=["brick", "list"],
+                    help="gradient chain: brick by brick where an interface can be (kernels_chain.cuh, default) or the four list kernels (kernels_step.cuh)")
     ap.add_argument("--geometry", default="pack", choices=["pack", "open"], help="open = empty duct, diagnostic only (not the benchmark workload)")
     ap.add_argument("--ref-block", default="", help="--impl reference: block_Threads_X,Y,Z override (the shipped control file has 128,1,1)")
     args = ap.parse_args()
@@ -652,8 +654,8 @@ def main():
         args.size = 512 if multi else 256
     if not args.case:
         args.case = "imbibition" if multi else "drainage"
-    if args.activity is not None:
-        os.environ["MFLBM_ACTIVITY"] = str(args.activity)   # read by the library when a solver is created
+    if args.chain is not None:
+        os.environ["MFLBM_CHAIN"] = args.chain   # read by the library when a solver is created
     if args.impl == "reference":
         out = run_reference(args)
     else:

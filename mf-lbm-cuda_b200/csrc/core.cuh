@@ -61,6 +61,18 @@ template <typename T> __host__ __device__ constexpr T w_equ(int q) { return q ==
 template <typename T>
 struct alignas(2 * sizeof(T)) Pair { T a, b; };
 
+// n / d for n < 2^31 and a divisor fixed at set-up time: (n * mul) >> shift with mul = ceil(2^shift / d), shift = 31 + ceil(log2 d)
+// (exact for every n < 2^31; mul < 2^32).  Used to turn a U index back into coordinates inside the hot kernels.
+struct FastDiv { unsigned mul; unsigned shift; };
+inline FastDiv make_fastdiv(unsigned d) {
+    unsigned l = 0;
+    while ((1ull << l) < d) l++;
+    const unsigned shift = 31 + l;
+    const unsigned long long mul = ((1ull << shift) + d - 1) / d;
+    return FastDiv{(unsigned)mul, shift};
+}
+__host__ __device__ __forceinline__ unsigned fastdiv(unsigned n, FastDiv dv) { return (unsigned)(((unsigned long long)n * dv.mul) >> dv.shift); }
+
 template <typename T>
 struct Lattice {
     int nx, ny, nz;          // real nodes of this lattice (slab-local nx)
@@ -86,6 +98,13 @@ struct Lattice {
     T lbm_gamma, force_z, la_nui1, la_nui2, lbm_beta, RK_weight2, phi_inlet, relaxation, sa_inject, uin_avg, cos_theta;
     T rho_in, rho_out;
     int Z_porous_plate, porous_plate_cmd;
+    // interface-activity bricks (kernels_chain.cuh): bricks per axis, divisors that decode a U index / a brick index, the
+    // brick flags (k_chain_pre, k_act_scan) and the flags per group of 32 fluid entries the collide kernels raise
+    // (nullptr: the list chain is in use, nothing is raised)
+    int nbx, nby, nbz;
+    FastDiv dv_sz, dv_px, dv_nbxy, dv_nbx;
+    unsigned char* act_p; unsigned char* act_m;
+    unsigned char* grp_p; unsigned char* grp_m;
 
     __device__ __forceinline__ int u(int x, int y, int z) const { return (x + 3) + PX * ((y + 3) + PY * (z + 3)); }
     __device__ __forceinline__ int off(int q) const { return ex(q) + sy * ey(q) + sz * ez(q); }

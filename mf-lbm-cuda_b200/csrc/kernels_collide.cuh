@@ -63,6 +63,9 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 constexpr int COLLIDE_TILE = 128;
 
+// kernels_chain.cuh: flags of the interface-activity map, raised where phi is produced
+template <typename T> __device__ __forceinline__ void raise_activity(const Lattice<T>& L, const int t, const T phi, const unsigned mask);
+
 // surface-tension inputs of one node (:143-150): cn and 0.5*gamma*curv*c_norm
 template <typename T>
 __device__ __forceinline__ void node_force(const Lattice<T>& L, const int u, const T cnorm, const bool bulk_skip, T& cnx, T& cny, T& cnz, T& tmp) {
@@ -167,14 +170,15 @@ __global__ void __launch_bounds__(COLLIDE_EVEN_THREADS, CTAS) k_collide_even_tma
         if (live) {
             uint64_t* const bar = &empty[s];
             const int leader = __ffs(live_mask) - 1;
-            collide_node<T, MRT>(L, g1, g2, cnx, cny, cnz, tmp, [&](const T phi_loc) {
-                L.phi[u] = phi_loc;
+            const T phi_loc = collide_node<T, MRT>(L, g1, g2, cnx, cny, cnz, tmp, [&](const T phi_now) {
+                L.phi[u] = phi_now;
                 __syncwarp(live_mask);
                 if ((tid & 31) == leader) mbar_arrive(bar);
             });
             Pair<T>* __restrict__ po = L.pairs(0) + t;
 #pragma unroll
             for (int q = 0; q < 19; q++) po[(long long)q * NC] = Pair<T>{g1[q], g2[q]};
+            if (L.grp_p) raise_activity(L, t, phi_loc, live_mask);   // after the stage has gone back and the stores are on their way
         } else if (live_mask == 0u && (tid & 31) == 0) {
             mbar_arrive(&empty[s]);   // a warp past the last fluid entry
         }
@@ -306,6 +310,8 @@ __global__ void __launch_bounds__((NCONS + 1) * COLLIDE_TILE, CTAS) k_collide_od
         const int t = tile * COLLIDE_TILE + ct;
         const int u = S.u[ct];
         const bool live = u >= 0;
+        const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+        T phi_keep = T(0);
         if (live) {
             const T cnorm = S.cn[ct];
             T cnx, cny, cnz, tmp;
@@ -321,10 +327,12 @@ __global__ void __launch_bounds__((NCONS + 1) * COLLIDE_TILE, CTAS) k_collide_od
                 const int dst = S.nb[q - 1][ct];
                 L.pairs(opc(q))[dst] = Pair<T>{g1[q], g2[q]};
             }
+            phi_keep = phi_loc;
         }
         // every value and every entry of the stage has been consumed by an issued store (see the even kernel)
         __syncwarp();
         if ((ct & 31) == 0) mbar_arrive(&empty[st]);
+        if (live && L.grp_p) raise_activity(L, t, phi_keep, live_mask);
     }
 }
 

@@ -119,15 +119,12 @@ __global__ void k_zero_solid_normals(const Lattice<T> L) {
 }
 
 // geometrical wetting model on fluid-boundary nodes: rotate cn so that n_w . cn = cos(theta), <= 4 secant
-// iterations (:809-878).  snx/sny/snz: solid-surface normals in list order.
+// iterations (:809-878).
+// on values in registers:
 template <typename T>
-__device__ __forceinline__ void alter_site(const Lattice<T>& L, const int* __restrict__ list, const T* __restrict__ snx, const T* __restrict__ sny,
-                                           const T* __restrict__ snz, const int t) {
-    const int c2 = list[t];
-    const T lambda = lit<T>(0.5), local_eps = lit<T>(1e-6), ct = L.cos_theta;
-    if (!(L.c_norm[c2] > local_eps)) return;
-    const T nwx = snx[t], nwy = sny[t], nwz = snz[t];
-    T vcx0 = L.cn_x[c2], vcy0 = L.cn_y[c2], vcz0 = L.cn_z[c2];
+__device__ __forceinline__ void alter_values(const T ct, const T nwx, const T nwy, const T nwz, T& cx, T& cy, T& cz) {
+    const T lambda = lit<T>(0.5), local_eps = lit<T>(1e-6);
+    T vcx0 = cx, vcy0 = cy, vcz0 = cz;
     T vcx1 = vcx0 - lambda * (vcx0 + nwx), vcy1 = vcy0 - lambda * (vcy0 + nwy), vcz1 = vcz0 - lambda * (vcz0 + nwz);
     T vcx2, vcy2, vcz2, err0, err1, err2, tmp;
     err0 = (nwx * vcx0 + nwy * vcy0 + nwz * vcz0) - ct;
@@ -150,16 +147,25 @@ __device__ __forceinline__ void alter_site(const Lattice<T>& L, const int* __res
             }
         }
         tmp = lit<T>(1.) / ((lit<T>(1e-30)) + sqrt(vcx2 * vcx2 + vcy2 * vcy2 + vcz2 * vcz2));
-        L.cn_x[c2] = vcx2 * tmp; L.cn_y[c2] = vcy2 * tmp; L.cn_z[c2] = vcz2 * tmp;
+        cx = vcx2 * tmp; cy = vcy2 * tmp; cz = vcz2 * tmp;
     }
 }
 
+
+// list version: fluid-boundary sites of the whole U grid in brick order (Solver::finish_geometry), snx/sny/snz their solid-surface
+// normals in list order; the kernel's range is [-1 .. n+2]^3 (:814)
 template <typename T>
 __global__ void k_alter(const Lattice<T> L, const int* __restrict__ list, const T* __restrict__ snx, const T* __restrict__ sny,
                         const T* __restrict__ snz, const int count) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
-    alter_site(L, list, snx, sny, snz, t);
+    const int c2 = list[t];
+    const int Z = c2 / L.sz, r = c2 - Z * L.sz, Y = r / L.PX, X = r - Y * L.PX;
+    if (X < 2 || X > L.nx + 5 || Y < 2 || Y > L.ny + 5 || Z < 2 || Z > L.nz + 5) return;
+    if (!(L.c_norm[c2] > lit<T>(1e-6))) return;
+    T cx = L.cn_x[c2], cy = L.cn_y[c2], cz = L.cn_z[c2];
+    alter_values<T>(L.cos_theta, snx[t], sny[t], snz[t], cx, cy, cz);
+    L.cn_x[c2] = cx; L.cn_y[c2] = cy; L.cn_z[c2] = cz;
 }
 
 // cn at solid-boundary nodes <- weighted mean of the fluid neighbours' cn (:880-906); mask as in k_extrap_phi.

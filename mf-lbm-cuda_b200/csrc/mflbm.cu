@@ -14,9 +14,9 @@
 #include "core.cuh"
 #include "kernels_step.cuh"
 #include "kernels_collide.cuh"
-#include "kernels_gradient.cuh"
-#include "kernels_activity.cuh"
+#include "kernels_chain.cuh"
 #include "kernels_aux.cuh"
+#include "scan.cuh"
 
 namespace mflbm {
 
@@ -64,16 +64,26 @@ struct Solver {
     int *d_list_phi = nullptr, *d_mask_phi = nullptr, *d_list_cn = nullptr, *d_mask_cn = nullptr, *d_list_alter = nullptr, *d_list_n = nullptr;
     T* d_sn[3] = {nullptr, nullptr, nullptr};   // solid-surface normals in d_list_alter order
     unsigned char *d_live_n = nullptr, *d_live_cn = nullptr;   // per list entry: outputs may be non-zero (k_normals, k_extrap_cn)
-    unsigned char* d_live_u = nullptr;                         // the same per U site, for the tiled normals kernel
     unsigned char* d_near = nullptr;                           // per U site: a neighbour got a non-zero normal in this chain (kernels_step.cuh)
-    int grad_tx = 0;                                           // x extent of its tiles
-    // interface-activity map (kernels_activity.cuh), opt-in with MFLBM_ACTIVITY=1
-    bool activity = false;
+    // gradient chain evaluated brick by brick where an interface can be (kernels_chain.cuh; MFLBM_CHAIN=list selects the
+    // four list kernels of kernels_step.cuh instead, MFLBM_ACT_SCAN=1 takes the brick flags from a scan of phi instead of the
+    // collide kernels - both for cross-checks, results are identical)
+    bool brick_chain = true, act_scan = false;
     bool bc_lanes = false;   // MFLBM_LANES=1 (opt-in): the outlet kernel runs next to the inlet kernel on the second lane
-    ActGrid act{};
-    unsigned char *d_act_raw = nullptr, *d_act_quiet = nullptr;   // [2][bricks] P | M flags of one chain; [bricks] verdict
-    int *d_brick_n = nullptr, *d_brick_cn = nullptr, *d_brick_alter = nullptr;   // brick of every entry of d_list_n / d_list_cn / d_list_alter
-    cudaStream_t act_stream = nullptr;                            // lane of k_extrap_phi while the map is being built
+    BrickGrid bricks{};
+    unsigned char* d_act = nullptr;      // [3 sets][P | M][bricks]: sets 0 / 1 are raised by the collide kernel of even / odd steps, set 2 by k_act_scan
+    unsigned char* d_quiet = nullptr;    // [bricks] verdict of the previous chain
+    int *d_active = nullptr, *d_n_active = nullptr;   // bricks to process in this chain, their number
+    int *d_shell = nullptr, n_shell = 0;              // non-solid sites outside the real box
+    int *d_bc_list = nullptr, *d_bc_mask = nullptr, n_bc = 0;   // solid-boundary sites whose phi a boundary kernel copies (k_chain_pre)
+    int* d_alt_start = nullptr;                       // [bricks + 1] first fluid-boundary entry of every brick (d_list_alter, d_sn)
+    int *d_sb_start = nullptr, *d_sb_list = nullptr, *d_sb_mask = nullptr;   // solid-boundary sites of [0..n+1]^3 brick by brick (k_chain_extrap_cn)
+    unsigned char* d_grp = nullptr;                   // [P | M][groups of 32 fluid entries]: raised by the collide kernels, spread and cleared by k_chain_pre
+    int *d_grp_start = nullptr, *d_grp_bricks = nullptr, n_groups = 0;     // bricks touched by every group (CSR)
+    T* d_phi_base = nullptr;                          // allocations of phi / types with 16 guard elements on both sides
+    signed char* d_types_base = nullptr;
+    CUtensorMap tm_phi{};                             // 3-D tensor map of phi over the U grid, box 16 x 8 x 8 (k_chain_normals)
+    cudaStream_t act_stream = nullptr;                            // second lane (MFLBM_LANES)
     cudaEvent_t ev_act_fork = nullptr, ev_act_join = nullptr;
     int n_list_phi = 0, n_list_cn = 0, n_list_alter = 0, n_list_alter_all = 0, n_list_n = 0;
     long long counts[4] = {0, 0, 0, 0};
@@ -188,9 +198,10 @@ struct Solver {
         MF_CUDA(cudaSetDevice(device));   // before any stream / event is created: they belong to the current device
         if (const char* v = getenv("MFLBM_VARIANT")) variant = atoi(v);
         if (const char* v = getenv("MFLBM_MAX_CTAS")) max_ctas = atoi(v);
-        if (const char* v = getenv("MFLBM_ACTIVITY")) activity = atoi(v) != 0;
+        if (const char* v = getenv("MFLBM_CHAIN")) brick_chain = strcmp(v, "list") != 0;
+        if (const char* v = getenv("MFLBM_ACT_SCAN")) act_scan = atoi(v) != 0;
         if (const char* v = getenv("MFLBM_LANES")) bc_lanes = atoi(v) != 0;
-        if (activity || bc_lanes) {
+        if (bc_lanes) {
             MF_CUDA(cudaStreamCreateWithFlags(&act_stream, cudaStreamNonBlocking));
             MF_CUDA(cudaEventCreateWithFlags(&ev_act_fork, cudaEventDisableTiming));
             MF_CUDA(cudaEventCreateWithFlags(&ev_act_join, cudaEventDisableTiming));
@@ -216,14 +227,25 @@ struct Solver {
         PN = (long long)L.PX * L.PY * L.PZ;
         if (PN >= (1LL << 31)) MF_FAIL("lattice (or slab) exceeds 2^31 cells per field; decompose into more slabs");
         L.sy = L.PX; L.sz = L.PX * L.PY; L.NC = 0; L.n_fluid = 0;   // the PDF slots are sized by the geometry (finish_geometry)
-        zalloc((void**)&d_phi, sizeof(T) * PN);
+        zalloc((void**)&d_phi_base, sizeof(T) * (PN + 32)); d_phi = d_phi_base + 16;
         zalloc((void**)&d_cnx, sizeof(T) * PN); zalloc((void**)&d_cny, sizeof(T) * PN); zalloc((void**)&d_cnz, sizeof(T) * PN);
         zalloc((void**)&d_cnorm, sizeof(T) * PN);
         zalloc((void**)&d_Win, sizeof(T) * NP);
         zalloc((void**)&d_fconv, sizeof(T) * NP * 19); zalloc((void**)&d_gconv, sizeof(T) * NP * 19); zalloc((void**)&d_phiconv, sizeof(T) * NP);
-        zalloc((void**)&d_types, PN); zalloc((void**)&d_cmap, sizeof(int) * PN);
-        zalloc((void**)&d_live_u, PN); zalloc((void**)&d_near, PN);
-        grad_tx = std::min(16 * ceil_div(L.nx + 4, 16), 512);
+        zalloc((void**)&d_types_base, PN + 32); d_types = d_types_base + 16;
+        zalloc((void**)&d_cmap, sizeof(int) * PN);
+        bricks.nbx = L.PX / BR_X; bricks.nby = ceil_div(L.PY, BR_Y); bricks.nbz = ceil_div(L.PZ, BR_Z);
+        L.nbx = bricks.nbx; L.nby = bricks.nby; L.nbz = bricks.nbz;
+        L.dv_sz = make_fastdiv((unsigned)(L.PX * L.PY)); L.dv_px = make_fastdiv((unsigned)L.PX);
+        L.dv_nbxy = make_fastdiv((unsigned)(bricks.nbx * bricks.nby)); L.dv_nbx = make_fastdiv((unsigned)bricks.nbx);
+        L.act_p = nullptr; L.act_m = nullptr; L.grp_p = nullptr; L.grp_m = nullptr;
+        if (brick_chain) {
+            make_tile_map(&tm_phi, d_phi, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, sizeof(T));
+            const size_t nb = (size_t)bricks.count();
+            zalloc((void**)&d_act, 6 * nb); zalloc((void**)&d_quiet, nb);
+            zalloc((void**)&d_active, sizeof(int) * nb); zalloc((void**)&d_n_active, sizeof(int));
+        }
+        if (!brick_chain) zalloc((void**)&d_near, PN);
         zalloc((void**)&d_zstart, sizeof(int) * (L.nz + 2));
         zalloc((void**)&d_mon, sizeof(double) * MFLBM_MON_N * L.nz);
         MF_CUDA(cudaMallocHost((void**)&h_mon, sizeof(double) * MFLBM_MON_N * L.nz));
@@ -256,17 +278,34 @@ struct Solver {
         MF_CUDA(cudaStreamSynchronize(stream));
     }
 
+    // tensor map of a U-grid array for the tiles of k_chain_normals (cuTensorMapEncodeTiled through the runtime's driver
+    // entry point: no link against libcuda)
+    void make_tile_map(CUtensorMap* map, void* base, CUtensorMapDataType type, size_t elem) {
+        typedef CUresult (*Encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        MF_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) MF_FAIL("cuTensorMapEncodeTiled is not available in this driver");
+        const cuuint64_t dims[3] = {(cuuint64_t)L.PX, (cuuint64_t)L.PY, (cuuint64_t)L.PZ};
+        const cuuint64_t strides[2] = {(cuuint64_t)L.PX * elem, (cuuint64_t)L.PX * L.PY * elem};
+        const cuuint32_t box[3] = {TL_X, TL_Y, TL_Z}, estr[3] = {1, 1, 1};
+        const CUresult r = ((Encode)fn)(map, type, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) MF_FAIL("cuTensorMapEncodeTiled failed (%d)", (int)r);
+    }
+
     void destroy() {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
         drop_graphs();
-        dfree(d_pdf); dfree(d_phi); dfree(d_cnx); dfree(d_cny); dfree(d_cnz); dfree(d_cnorm);
+        dfree(d_pdf); dfree(d_phi_base); d_phi = nullptr; dfree(d_cnx); dfree(d_cny); dfree(d_cnz); dfree(d_cnorm);
         dfree(d_Win); dfree(d_fconv); dfree(d_gconv); dfree(d_phiconv);
-        dfree(d_types); dfree(d_cmap); dfree(d_flu); dfree(d_zstart); dfree(d_wbase);
+        dfree(d_types_base); d_types = nullptr; dfree(d_cmap); dfree(d_flu); dfree(d_zstart); dfree(d_wbase);
         dfree(d_list_phi); dfree(d_mask_phi); dfree(d_list_cn); dfree(d_mask_cn); dfree(d_list_alter); dfree(d_list_n);
         for (auto& q : d_sn) dfree(q);
-        dfree(d_live_n); dfree(d_live_cn); dfree(d_live_u); dfree(d_near);
-        dfree(d_act_raw); dfree(d_act_quiet); dfree(d_brick_n); dfree(d_brick_cn); dfree(d_brick_alter);
+        dfree(d_live_n); dfree(d_live_cn); dfree(d_near);
+        dfree(d_act); dfree(d_quiet); dfree(d_active); dfree(d_n_active); dfree(d_shell); dfree(d_bc_list); dfree(d_bc_mask); dfree(d_alt_start); dfree(d_sb_start); dfree(d_sb_list); dfree(d_sb_mask); dfree(d_grp); dfree(d_grp_start); dfree(d_grp_bricks);
         dfree(d_mon); dfree(d_phi_old); dfree(d_p2p); d_flags = nullptr;
         if (d_stage) { cudaFree(d_stage); d_stage = nullptr; }
         ring_drain(true);
@@ -337,9 +376,16 @@ struct Solver {
         auto U = [&](int x, int y, int z) { return (x + 3) + PX * ((y + 3) + PY * (z + 3)); };
         int offq[19];
         for (int q = 0; q < 19; q++) offq[q] = ex(q) + PX * (ey(q) + PY * ez(q));
-        std::vector<int> cmap((size_t)PN, -1), flu, passive, lphi, mphi, lcn, mcn, lalt_in, lalt_out, ln, zstart((size_t)nz + 2, 0);
-        std::vector<int> bcn, bn, balt;   // activity map: brick of every list entry (balt: the [-1..n+2]^3 part of the alter list)
-        act.nbx = ceil_div(L.PX, ACT_BX); act.nby = ceil_div(L.PY, ACT_BY); act.nbz = ceil_div(L.PZ, ACT_BZ);
+        std::vector<int> cmap((size_t)PN, -1), flu, passive, lphi, mphi, lcn, mcn, ln, shell, lbc, mbc, zstart((size_t)nz + 2, 0);
+        // planes whose phi the boundary kernels copy into ghost layers (k_chain_pre): inlet_phi reads k = 0, the outlet kernels
+        // k = nz and nz + 1 (kernels_step.cuh), k_periodic_phi the four real layers at each end of a periodic axis
+        const bool oz = open_z();
+        auto copied = [&](int y, int z) {
+            if (oz && (z == 0 || z == nz || z == nz + 1)) return true;
+            if (P.kper && ((z >= 1 && z <= 4) || (z >= nz - 3 && z <= nz))) return true;
+            if (P.jper && ((y >= 1 && y <= 4) || (y >= ny - 3 && y <= ny))) return true;
+            return false;
+        };
         flu.reserve((size_t)nx * ny * nz / 2);
         counts[0] = counts[1] = counts[2] = counts[3] = 0;
         for (int z = -3; z <= nz + 4; z++) {
@@ -352,8 +398,8 @@ struct Solver {
                 const bool in1 = x >= 0 && x <= nx + 1 && y >= 0 && y <= ny + 1 && z >= 0 && z <= nz + 1;
                 const bool in0 = x >= 1 && x <= nx && y >= 1 && y <= ny && z >= 1 && z <= nz;
                 if (in1) { if (t <= 0 && in0) flu.push_back(u); else passive.push_back(u); }
-                const int brick = activity ? act.brick(x + 3, y + 3, z + 3) : 0;
-                if (t <= 0 && in2) { ln.push_back(u); if (activity) bn.push_back(brick); }   // k_normals: non-solid sites of [-1..n+2]^3 (:760-764)
+                if (t <= 0 && !in0 && brick_chain) shell.push_back(u);   // k_act_shell: phi there is written by boundary kernels and halos
+                if (t <= 0 && in2 && !brick_chain) ln.push_back(u);      // k_normals: non-solid sites of [-1..n+2]^3 (:760-764)
                 if (t == 2) {
                     counts[0]++;
                     if (in3) {                                           // :737 [-2..n+3]; :885 [0..n+1]
@@ -361,11 +407,11 @@ struct Solver {
                         int m = 0;
                         for (int q = 1; q < 19; q++) if (ty[(size_t)(u + offq[q])] <= 0) m |= 1 << (q - 1);
                         lphi.push_back(u); mphi.push_back(m);
-                        if (in1) { lcn.push_back(u); mcn.push_back(m); if (activity) bcn.push_back(brick); }
+                        if (brick_chain && copied(y, z)) { lbc.push_back(u); mbc.push_back(m); }
+                        if (in1 && !brick_chain) { lcn.push_back(u); mcn.push_back(m); }
                     }
                 } else if (t == -1) {
                     counts[1]++; if (in3) counts[3]++;
-                    if (in2) { lalt_in.push_back(u); if (activity) balt.push_back(brick); } else lalt_out.push_back(u);   // :814 [-1..n+2]
                 }
             }
         }
@@ -401,28 +447,63 @@ struct Solver {
         dfree(d_pdf);
         zalloc((void**)&d_pdf, sizeof(T) * NC * 38);
         L.pdf = d_pdf;
-        std::vector<int> lalt(lalt_in);
-        lalt.insert(lalt.end(), lalt_out.begin(), lalt_out.end());
         auto up = [&](int*& d, const std::vector<int>& v) {
             dfree(d);
             MF_CUDA(cudaMalloc((void**)&d, sizeof(int) * std::max<size_t>(v.size(), 1)));
             if (!v.empty()) MF_CUDA(cudaMemcpyAsync(d, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice, stream));
         };
         up(d_wbase, wbase); L.wbase = d_wbase;
-        up(d_flu, flu); up(d_list_phi, lphi); up(d_mask_phi, mphi); up(d_list_cn, lcn); up(d_mask_cn, mcn); up(d_list_alter, lalt); up(d_list_n, ln);
-        n_list_phi = (int)lphi.size(); n_list_cn = (int)lcn.size(); n_list_alter = (int)lalt_in.size(); n_list_alter_all = (int)lalt.size();
-        n_list_n = (int)ln.size();
+        up(d_flu, flu); up(d_list_phi, lphi); up(d_mask_phi, mphi); up(d_list_cn, lcn); up(d_mask_cn, mcn); up(d_list_n, ln); up(d_shell, shell); up(d_bc_list, lbc); up(d_bc_mask, mbc);
+        n_list_phi = (int)lphi.size(); n_list_cn = (int)lcn.size(); n_list_n = (int)ln.size(); n_shell = (int)shell.size(); n_bc = (int)lbc.size();
         dfree(d_live_n); dfree(d_live_cn);
         MF_CUDA(cudaMalloc((void**)&d_live_n, std::max(n_list_n, 1))); MF_CUDA(cudaMalloc((void**)&d_live_cn, std::max(n_list_cn, 1)));
-        dfree(d_act_raw); dfree(d_act_quiet);
-        if (activity) {
-            up(d_brick_n, bn); up(d_brick_cn, bcn); up(d_brick_alter, balt);
-            MF_CUDA(cudaMalloc((void**)&d_act_raw, 2 * (size_t)act.count())); MF_CUDA(cudaMalloc((void**)&d_act_quiet, (size_t)act.count()));
+        // fluid-boundary sites of the whole U grid (wetting; the kernels check their own range [-1..n+2]^3, :814) and, for the
+        // brick chain, solid-boundary sites of [0..n+1]^3 (:885), compacted brick by brick on the device: count per brick,
+        // exclusive scan, fill (sites of a brick in z,y,x order)
+        {
+            const int nb = bricks.count();
+            int* d_cnt = nullptr;
+            MF_CUDA(cudaMalloc((void**)&d_cnt, sizeof(int) * (size_t)(nb + 1)));
+            auto compact = [&](auto count_kernel, auto fill_kernel, int*& d_start, int*& d_list, int** d_mask) -> int {
+                MF_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int) * (size_t)(nb + 1), stream));
+                count_kernel<<<nb, CHAIN_THREADS, 0, stream>>>(L, d_cnt, nullptr, nullptr); check_launch(); count();
+                long long total = 0;
+                if (!d_start) MF_CUDA(cudaMalloc((void**)&d_start, sizeof(int) * (size_t)(nb + 1)));
+                MF_CUDA(exclusive_scan(d_cnt, d_start, nb + 1, stream, &total));
+                dfree(d_list);
+                MF_CUDA(cudaMalloc((void**)&d_list, sizeof(int) * (size_t)std::max<long long>(total, 1)));
+                if (d_mask) { dfree(*d_mask); MF_CUDA(cudaMalloc((void**)d_mask, sizeof(int) * (size_t)std::max<long long>(total, 1))); }
+                fill_kernel<<<nb, CHAIN_THREADS, 0, stream>>>(L, d_start, d_list, d_mask ? *d_mask : nullptr); check_launch(); count();
+                return (int)total;
+            };
+            try {
+                n_list_alter_all = compact(k_brick_sites<T, 0, 0>, k_brick_sites<T, 0, 1>, d_alt_start, d_list_alter, nullptr);
+                n_list_alter = n_list_alter_all;
+                if (brick_chain) compact(k_brick_sites<T, 1, 0>, k_brick_sites<T, 1, 1>, d_sb_start, d_sb_list, &d_sb_mask);
+            } catch (...) { cudaFree(d_cnt); throw; }
+            cudaFree(d_cnt);
         }
         mark_all_live();
         MF_CUDA(cudaMemcpyAsync(d_cmap, cmap.data(), sizeof(int) * (size_t)PN, cudaMemcpyHostToDevice, stream));
         MF_CUDA(cudaMemcpyAsync(d_zstart, zstart.data(), sizeof(int) * zstart.size(), cudaMemcpyHostToDevice, stream));
         L.n_fluid = (int)n_fluid; L.fl_u = d_flu;
+        if (brick_chain) {   // bricks touched by every group of 32 fluid entries (kernels_chain.cuh, raise_activity / k_chain_pre)
+            n_groups = ceil_div((int)n_fluid, 32);
+            dfree(d_grp); dfree(d_grp_start); dfree(d_grp_bricks);
+            zalloc((void**)&d_grp, 2 * (size_t)std::max(n_groups, 1));
+            int* d_cnt = nullptr;
+            MF_CUDA(cudaMalloc((void**)&d_cnt, sizeof(int) * (size_t)(n_groups + 1)));
+            MF_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int) * (size_t)(n_groups + 1), stream));
+            MF_CUDA(cudaMalloc((void**)&d_grp_start, sizeof(int) * (size_t)(n_groups + 1)));
+            long long total = 0;
+            cudaError_t e = cudaSuccess;
+            if (n_groups) { k_group_bricks<T, 0><<<ceil_div(n_groups, 4), 128, 0, stream>>>(L, n_groups, d_cnt, nullptr); count(); }
+            e = exclusive_scan(d_cnt, d_grp_start, n_groups + 1, stream, &total);
+            cudaFree(d_cnt);
+            MF_CUDA(e);
+            MF_CUDA(cudaMalloc((void**)&d_grp_bricks, sizeof(int) * (size_t)std::max<long long>(total, 1)));
+            if (n_groups) { k_group_bricks<T, 1><<<ceil_div(n_groups, 4), 128, 0, stream>>>(L, n_groups, d_grp_start, d_grp_bricks); check_launch(); count(); }
+        }
         for (int a = 0; a < 3; a++) {
             dfree(d_sn[a]);
             MF_CUDA(cudaMalloc((void**)&d_sn[a], sizeof(T) * std::max(n_list_alter_all, 1)));
@@ -537,7 +618,8 @@ struct Solver {
         if (cny) to_u<T>(cny, d_cny, 2, N2);
         if (cnz) to_u<T>(cnz, d_cnz, 2, N2);
         if (cnorm) to_u<T>(cnorm, d_cnorm, 2, N2);
-        if (cnx || cny || cnz || cnorm) { cn_consistent = false; mark_all_live(); drop_graphs(); }   // bulk_skip is baked into captured launches
+        if (cnx || cny || cnz || cnorm) { cn_consistent = false; drop_graphs(); }   // bulk_skip is baked into captured launches
+        if (phi || cnx || cny || cnz || cnorm) mark_all_live();
         if (cnx || cny || cnz || cnorm) {   // the caller's arrays are not trusted to hold zeros in solids
             k_zero_solid_normals<T><<<grid_box(2, 128), 128, 0, stream>>>(L); check_launch(); count();
         }
@@ -556,7 +638,12 @@ struct Solver {
             for (int s = 0; s < 38; s++)
                 ring_download(pdf + (size_t)s * N1, sizeof(T) * N1, [&](void* st) { k_pdf_slot<T, false><<<g, 128, 0, stream>>>(L, (T*)st, s); check_launch(); count(); });
         }
-        if (phi) from_u<T>(phi, d_phi, 4, N4);
+        if (phi) {
+            // the brick chain leaves phi at the solid-boundary sites of long-quiet bricks at its last evaluation (kernels_chain.cuh):
+            // the array that leaves the library holds what extrapolate_phi_toSolid (:732-755) gives for the current phi
+            if (brick_chain && n_list_phi) { k_extrap_phi<T><<<ceil_div(n_list_phi, 128), 128, 0, stream>>>(L, d_list_phi, d_mask_phi, n_list_phi); check_launch(); count(); }
+            from_u<T>(phi, d_phi, 4, N4);
+        }
         if (cnx) from_u<T>(cnx, d_cnx, 2, N2);
         if (cny) from_u<T>(cny, d_cny, 2, N2);
         if (cnz) from_u<T>(cnz, d_cnz, 2, N2);
@@ -576,7 +663,7 @@ struct Solver {
     void mark_all_live() {
         if (d_live_n) MF_CUDA(cudaMemsetAsync(d_live_n, 1, std::max(n_list_n, 1), stream));
         if (d_live_cn) MF_CUDA(cudaMemsetAsync(d_live_cn, 1, std::max(n_list_cn, 1), stream));
-        if (d_live_u) MF_CUDA(cudaMemsetAsync(d_live_u, 1, (size_t)PN, stream));
+        if (d_quiet) MF_CUDA(cudaMemsetAsync(d_quiet, 0, (size_t)bricks.count(), stream));   // every brick is processed by the next chain
     }
 
     bool open_z() const { return P.kper == 0 && P.wall_z_min == 0 && P.wall_z_max == 0; }
@@ -607,61 +694,57 @@ struct Solver {
     int phi_() const { return slab.has_right ? L.nx + 1 : L.nx; }
 
     // the colour-gradient kernels, call order of src/main_iteration_GPU.cu:2027-2049; the fifth (CSF_Forces, :2052) is
-    // fused into the collide kernel of the next step
-    void gradient_chain() {
+    // fused into the collide kernel of the next step.
+    // parity: ntime & 1 of the step whose collide kernel raised the brick flags; -1: no collide precedes this chain (initial
+    // state, restart, color_gradient through the ABI) - the flags then come from a scan of phi.
+    void gradient_chain(int parity = -1) {
         if (!have_geometry) MF_FAIL("gradient chain before geometry");
         const int bl = 128;
-        if (activity && gradient_chain_act()) return;
+        if (brick_chain) { gradient_chain_bricks(parity); return; }
+        // the list chain (kernels_step.cuh): four kernels over compact site lists, every site every step
         if (n_list_phi) { k_extrap_phi<T><<<ceil_div(n_list_phi, bl), bl, 0, stream>>>(L, d_list_phi, d_mask_phi, n_list_phi); check_launch(); count(); }
-        // Two normals kernels with bit-identical results.  The list-driven one only touches non-solid sites but gathers from
-        // global memory; the TMA-tiled one walks the dense grid with phi staged in shared memory, so its cost does not
-        // shrink with the porosity (a warp runs its 18 LDS if any lane is fluid).  Measured at 256^3: pack (porosity 0.44)
-        // 118 us list / 150 us tiled; the tiled kernel is chosen where most sites are fluid.  MFLBM_VARIANT 1xxxx / 2xxxx
-        // force the tiled / the list kernel.
-        const bool tiled = variant / 10000 == 1 || (variant / 10000 != 2 && (double)n_list_n > 0.75 * (double)(L.nx + 4) * (L.ny + 4) * (L.nz + 4));
-        if (!tiled) {
-            if (n_list_n) { k_normals<T><<<ceil_div(n_list_n, bl), bl, 0, stream>>>(L, d_list_n, d_live_n, d_near, n_list_n); check_launch(); count(); }
-        } else {
-            const size_t smem = normals_tile_smem<T>(grad_tx);
-            static thread_local int configured = -1;
-            if (configured != device) { MF_CUDA(cudaFuncSetAttribute(k_normals_tile<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)normals_tile_smem<T>(512))); configured = device; }
-            // one wave of CTAs: as many z chunks as fit next to each other on the device
-            const int xb = ceil_div(L.nx + 4, grad_tx), yb = ceil_div(L.ny + 4, GRAD_TY);
-            const int slots = num_sms * std::max(1, std::min(8, (int)((227 * 1024) / (smem + 1024))));
-            const int chunks = std::max(1, std::min(L.nz + 4, slots / std::max(1, xb * yb)));
-            const int zc = ceil_div(L.nz + 4, chunks);
-            const dim3 g(xb, yb, ceil_div(L.nz + 4, zc));
-            k_normals_tile<T><<<g, GRAD_THREADS, smem, stream>>>(L, d_live_u, d_near, grad_tx, zc); check_launch(); count();
-        }
+        if (n_list_n) { k_normals<T><<<ceil_div(n_list_n, bl), bl, 0, stream>>>(L, d_list_n, d_live_n, d_near, n_list_n); check_launch(); count(); }
         if (n_list_alter) { k_alter<T><<<ceil_div(n_list_alter, bl), bl, 0, stream>>>(L, d_list_alter, d_sn[0], d_sn[1], d_sn[2], n_list_alter); check_launch(); count(); }
         if (n_list_cn) { k_extrap_cn<T><<<ceil_div(n_list_cn, bl), bl, 0, stream>>>(L, d_list_cn, d_mask_cn, d_live_cn, d_near, n_list_cn); check_launch(); count(); }
         cn_consistent = true;
     }
 
-    // the same chain with the interface-activity map (kernels_activity.cuh): one pass over phi decides, brick by brick, where
-    // the order parameter is +1 or -1 to within 1e-7; the normals and cn-extrapolation kernels skip their stencils there.
-    // Stores are identical to the plain chain's.  Only with the list-driven normals kernel (false = not applicable, the caller runs the plain chain).
-    bool gradient_chain_act() {
-        const bool tiled = variant / 10000 == 1 || (variant / 10000 != 2 && (double)n_list_n > 0.75 * (double)(L.nx + 4) * (L.ny + 4) * (L.nz + 4));
-        if (tiled || !d_act_raw) return false;
-        const int bl = 128, nb = act.count();
-        unsigned char *P_ = d_act_raw, *M_ = d_act_raw + nb;
-        // two lanes (event fork / join, also inside a captured graph): the phi extrapolation writes solid-boundary sites only
-        // and the scan reads non-solid sites only, so the latency-bound gather kernel hides behind the streaming pass
-        MF_CUDA(cudaEventRecord(ev_act_fork, stream));
-        MF_CUDA(cudaStreamWaitEvent(act_stream, ev_act_fork, 0));
-        if (n_list_phi) { k_extrap_phi<T><<<ceil_div(n_list_phi, bl), bl, 0, act_stream>>>(L, d_list_phi, d_mask_phi, n_list_phi); check_launch(); count(); }
-        MF_CUDA(cudaEventRecord(ev_act_join, act_stream));
-        MF_CUDA(cudaMemsetAsync(d_act_raw, 0, 2 * (size_t)nb, stream));
-        k_act_scan<T><<<dim3(ceil_div(L.PX, bl), L.PY, L.PZ), bl, 0, stream>>>(L, act, P_, M_); check_launch();
-        k_act_dilate<<<ceil_div(nb, bl), bl, 0, stream>>>(act, P_, M_, d_act_quiet); check_launch();
-        count(2);
-        MF_CUDA(cudaStreamWaitEvent(stream, ev_act_join, 0));
-        if (n_list_n) { k_normals_act<T><<<ceil_div(n_list_n, bl), bl, 0, stream>>>(L, d_list_n, d_brick_n, d_act_quiet, d_live_n, d_near, n_list_n); check_launch(); count(); }
-        if (n_list_alter) { k_alter_act<T><<<ceil_div(n_list_alter, bl), bl, 0, stream>>>(L, d_list_alter, d_brick_alter, d_act_quiet, d_sn[0], d_sn[1], d_sn[2], n_list_alter); check_launch(); count(); }
-        if (n_list_cn) { k_extrap_cn_act<T><<<ceil_div(n_list_cn, bl), bl, 0, stream>>>(L, d_list_cn, d_mask_cn, d_brick_cn, d_act_quiet, d_live_cn, d_near, n_list_cn); check_launch(); count(); }
+    unsigned char* act_set(int set, int which) const { return d_act + (size_t)bricks.count() * (size_t)(2 * set + which); }
+
+    // kernels_chain.cuh: raise (collide kernels + k_act_shell, or k_act_scan) -> verdict -> process the listed bricks
+    void gradient_chain_bricks(int parity) {
+        const int bl = 128, nb = bricks.count();
+        const bool scan = parity < 0 || act_scan;
+        const int set = scan ? 2 : (parity & 1);
+        Lattice<T> La = L;
+        La.act_p = act_set(set, 0); La.act_m = act_set(set, 1);
+        La.grp_p = d_grp; La.grp_m = d_grp + std::max(n_groups, 1);
+        if (scan) {
+            MF_CUDA(cudaMemsetAsync(La.act_p, 0, 2 * (size_t)nb, stream));
+            k_act_scan<T><<<dim3(ceil_div(L.PX, bl), L.PY, L.PZ), bl, 0, stream>>>(L, La.act_p, La.act_m, d_n_active); check_launch(); count();
+            if (parity < 0) MF_CUDA(cudaMemsetAsync(d_act, 0, 4 * (size_t)nb, stream));   // whatever step comes next starts from clean sets
+            // sub-list refresh (see k_chain_pre); group flags a collide kernel may have raised are dropped with the scan's verdict
+            if (n_bc) { k_chain_pre<T><<<ceil_div(n_bc, bl), bl, 0, stream>>>(La, d_shell, 0, d_bc_list, d_bc_mask, n_bc, d_grp_start, d_grp_bricks, 0, nullptr); check_launch(); count(); }
+            if (n_groups) MF_CUDA(cudaMemsetAsync(d_grp, 0, 2 * (size_t)n_groups, stream));
+        } else {
+            k_chain_pre<T><<<std::max(1, ceil_div(n_shell + n_bc + n_groups, bl)), bl, 0, stream>>>(La, d_shell, n_shell, d_bc_list, d_bc_mask, n_bc, d_grp_start, d_grp_bricks, n_groups, d_n_active);
+            check_launch(); count();
+        }
+        // the verdict kernel clears the set the next step's collide raises into
+        unsigned char* clr = parity < 0 ? nullptr : act_set((parity & 1) ^ 1, 0);
+        k_act_verdict<<<ceil_div(nb, bl), bl, 0, stream>>>(bricks, La.act_p, La.act_m, d_quiet, d_active, d_n_active, clr, clr ? clr + nb : nullptr); check_launch(); count();
+        const int grid = std::max(1, std::min(nb, num_sms * 8)), grid_cn = std::max(1, std::min(nb, num_sms * 16));
+        BrickNormals<T> SN{d_alt_start, d_sn[0], d_sn[1], d_sn[2]};
+        k_chain_normals<T><<<grid, CHAIN_THREADS, 0, stream>>>(L, tm_phi, d_active, d_n_active, SN); check_launch(); count();
+        k_chain_extrap_cn<T><<<grid_cn, CHAIN_THREADS, 0, stream>>>(L, d_active, d_n_active, d_sb_start, d_sb_list, d_sb_mask); check_launch(); count();
         cn_consistent = true;
-        return true;
+    }
+
+    // the lattice view a collide kernel gets: with the brick chain it raises the activity flags of its groups of 32 entries
+    Lattice<T> collide_lattice(int) const {
+        Lattice<T> La = L;
+        if (brick_chain && !act_scan && d_grp) { La.grp_p = d_grp; La.grp_m = d_grp + std::max(n_groups, 1); }
+        return La;
     }
 
     // persistent grid of the collide kernels: CTAS resident CTAs per SM.  MFLBM_MAX_CTAS caps it (tests: a small lattice
@@ -676,7 +759,7 @@ struct Solver {
         constexpr size_t smem = collide_even_smem<T, NST>();
         static thread_local int configured = -1;
         if (configured != device) { MF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = device; }
-        kern<<<collide_grid(ntiles, CTAS), COLLIDE_EVEN_THREADS, smem, stream>>>(L, ntiles, cn_consistent ? 1 : 0);
+        kern<<<collide_grid(ntiles, CTAS), COLLIDE_EVEN_THREADS, smem, stream>>>(collide_lattice(0), ntiles, cn_consistent ? 1 : 0);
     }
     template <int MRT, int NST, int CTAS, int NCONS = 1, int REGS_P = 0, int REGS_C = 0>
     void launch_odd_ws() {
@@ -685,7 +768,7 @@ struct Solver {
         constexpr size_t smem = collide_odd_ws_smem<T, NST>();
         static thread_local int configured = -1;
         if (configured != device) { MF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = device; }
-        kern<<<collide_grid(ntiles, CTAS), (NCONS + 1) * COLLIDE_TILE, smem, stream>>>(L, ntiles, cn_consistent ? 1 : 0);
+        kern<<<collide_grid(ntiles, CTAS), (NCONS + 1) * COLLIDE_TILE, smem, stream>>>(collide_lattice(1), ntiles, cn_consistent ? 1 : 0);
     }
     // Stage counts are sized for the 227 KB of shared memory of an SM.  MFLBM_VARIANT = 100*e + o
     // selects other (even, odd) configurations for tuning runs, for the shipped MRT model only.
@@ -778,7 +861,7 @@ struct Solver {
         if (!have_geometry) MF_FAIL("step before geometry");
         if (phase == 0) phase_collide(ntime);
         else if (phase == 1) phase_boundaries(ntime);
-        else if (phase == 2) gradient_chain();
+        else if (phase == 2) gradient_chain(ntime & 1);
         else MF_FAIL("bad phase");
     }
 
@@ -1006,7 +1089,7 @@ struct Solver {
 #define MF_PTR(n, p) if (!strcmp(name, n)) return (void*)(p)
         MF_PTR("pdf", d_pdf); MF_PTR("phi", d_phi); MF_PTR("cn_x", d_cnx); MF_PTR("cn_y", d_cny); MF_PTR("cn_z", d_cnz); MF_PTR("c_norm", d_cnorm);
         MF_PTR("W_in", d_Win); MF_PTR("f_convec", d_fconv); MF_PTR("g_convec", d_gconv); MF_PTR("phi_convec", d_phiconv);
-        MF_PTR("types", d_types); MF_PTR("site_map", d_cmap); MF_PTR("fluid_sites", d_flu);
+        MF_PTR("types", d_types); MF_PTR("site_map", d_cmap); MF_PTR("fluid_sites", d_flu); MF_PTR("chain_bricks_processed", d_n_active);
 #undef MF_PTR
         return nullptr;
     }

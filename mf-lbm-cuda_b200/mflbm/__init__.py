@@ -202,12 +202,9 @@ class Solver:
         self._slab = slab
         self.nx = int(slab.nx_local) if slab is not None else int(params.nx)
         self.ny, self.nz = int(params.ny), int(params.nz)
-        # the library reads MFLBM_ACTIVITY when a solver is created (gradient chain with the interface-activity map,
-        # csrc/kernels_activity.cuh; results are identical); recorded here so that callers can report it
-        try:
-            self.activity = int(os.environ.get("MFLBM_ACTIVITY", "0") or 0) != 0
-        except ValueError:
-            self.activity = False
+        # the library reads MFLBM_CHAIN when a solver is created ("list": the four list kernels of kernels_step.cuh instead of
+        # the brick chain of kernels_chain.cuh; results are identical); recorded here so that callers can report it
+        self.chain = "list" if os.environ.get("MFLBM_CHAIN", "") == "list" else "brick"
         rc = self._fn("create")(C.byref(params), C.byref(slab) if slab is not None else None, device, stream, C.byref(self.h))
         self._check(rc)
 
@@ -417,6 +414,18 @@ class Solver:
     @property
     def stream(self) -> int:
         return int(self._fn("stream")(self.h) or 0)
+
+    def chain_bricks(self) -> tuple[int, int]:
+        """(bricks the last gradient chain processed, bricks of the lattice) - brick chain only (kernels_chain.cuh)"""
+        import torch
+        ptr = self.device_ptr("chain_bricks_processed")
+        nbx, nby, nbz = (16 * -(-(self.nx + 8) // 16)) // 8, -(-(self.ny + 8) // 4), -(-(self.nz + 8) // 4)
+        if not ptr:
+            return 0, nbx * nby * nbz
+        class _A:
+            __cuda_array_interface__ = {"shape": (1,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+        self.sync()
+        return int(torch.as_tensor(_A(), device="cuda")[0]), nbx * nby * nbz
 
     def device_ptr(self, name: str) -> int:
         return int(self._fn("device_ptr")(self.h, name.encode()) or 0)

@@ -1,4 +1,4 @@
-"""CPU check of the interface-activity criterion (mf-lbm-cuda_b200/csrc/kernels_activity.cuh) against the oracle.
+"""CPU check of the interface-activity criterion (mf-lbm-cuda_b200/csrc/kernels_chain.cuh) against the oracle.
 
 The CUDA chain may skip the normals / cn-extrapolation stencils at the sites of a "quiet" brick - one whose 27-brick
 neighbourhood holds no non-solid site with |phi - s| > eps (s = +1 or -1; eps = 1e-7 in double, 0 in single precision) -
@@ -84,8 +84,8 @@ def test_python_constants_mirror_the_kernel_header():
     """the numpy emulation above must test the criterion the CUDA code applies: same brick extents, same tolerances"""
     import re
     from pathlib import Path
-    src = (Path(__file__).resolve().parent.parent / "mf-lbm-cuda_b200" / "csrc" / "kernels_activity.cuh").read_text()
-    m = re.search(r"ACT_BX = (\d+), ACT_BY = (\d+), ACT_BZ = (\d+)", src)
+    src = (Path(__file__).resolve().parent.parent / "mf-lbm-cuda_b200" / "csrc" / "kernels_chain.cuh").read_text()
+    m = re.search(r"BR_X = (\d+), BR_Y = (\d+), BR_Z = (\d+)", src)
     assert m and tuple(int(v) for v in m.groups()) == (BX, BY, BZ)
     d = re.search(r"act_eps<double>\(\) \{ return ([0-9.e+-]+); \}", src)
     f = re.search(r"act_eps<float>\(\) \{ return ([0-9.e+-]+)f; \}", src)

@@ -129,7 +129,6 @@ def test_cuda_slabs_on_one_gpu_equal_single_domain(gpu_lib, name, prec, world, n
     ref.close()
 
 
-@pytest.mark.skipif(not os.environ.get("MFLBM_TEST_ACTIVITY"), reason="written after the round's GPU budget was spent: opt-in (MFLBM_TEST_ACTIVITY=1) until seen green on a B200")
 @pytest.mark.parametrize("name,prec,nsteps", [("pack_velocity", "f64", 8), ("tube_pressure", "f32", 7)])
 def test_slab_checkpoint_restart_on_another_decomposition(gpu_lib, tmp_path, name, prec, nsteps):
     """3 CUDA slabs step, settle and write ONE checkpoint file in the reference layout (slab.write_checkpoint_slabs); 2 slabs
