@@ -69,7 +69,6 @@ struct Solver {
     // four list kernels of kernels_step.cuh instead, MFLBM_ACT_SCAN=1 takes the brick flags from a scan of phi instead of the
     // collide kernels - both for cross-checks, results are identical)
     bool brick_chain = true, act_scan = false;
-    bool bc_lanes = false;   // MFLBM_LANES=1 (opt-in): the outlet kernel runs next to the inlet kernel on the second lane
     BrickGrid bricks{};
     unsigned char* d_act = nullptr;      // [3 sets][P | M][bricks]: sets 0 / 1 are raised by the collide kernel of even / odd steps, set 2 by k_act_scan
     unsigned char* d_quiet = nullptr;    // [bricks] verdict of the previous chain
@@ -83,8 +82,6 @@ struct Solver {
     T* d_phi_base = nullptr;                          // allocations of phi / types with 16 guard elements on both sides
     signed char* d_types_base = nullptr;
     CUtensorMap tm_phi{};                             // 3-D tensor map of phi over the U grid, box 16 x 8 x 8 (k_chain_normals)
-    cudaStream_t act_stream = nullptr;                            // second lane (MFLBM_LANES)
-    cudaEvent_t ev_act_fork = nullptr, ev_act_join = nullptr;
     int n_list_phi = 0, n_list_cn = 0, n_list_alter = 0, n_list_alter_all = 0, n_list_n = 0;
     long long counts[4] = {0, 0, 0, 0};
     long long n_fluid = 0;
@@ -200,12 +197,6 @@ struct Solver {
         if (const char* v = getenv("MFLBM_MAX_CTAS")) max_ctas = atoi(v);
         if (const char* v = getenv("MFLBM_CHAIN")) brick_chain = strcmp(v, "list") != 0;
         if (const char* v = getenv("MFLBM_ACT_SCAN")) act_scan = atoi(v) != 0;
-        if (const char* v = getenv("MFLBM_LANES")) bc_lanes = atoi(v) != 0;
-        if (bc_lanes) {
-            MF_CUDA(cudaStreamCreateWithFlags(&act_stream, cudaStreamNonBlocking));
-            MF_CUDA(cudaEventCreateWithFlags(&ev_act_fork, cudaEventDisableTiming));
-            MF_CUDA(cudaEventCreateWithFlags(&ev_act_join, cudaEventDisableTiming));
-        }
         MF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
         if (strm) { stream = (cudaStream_t)strm; own_stream = false; }
         else { MF_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true; }
@@ -317,9 +308,6 @@ struct Solver {
         for (int kind = 0; kind < 3; kind++) for (int side = 0; side < 2; side++) { dfree(d_send[kind][side]); d_recv[kind][side] = nullptr; }
         if (h_mon) { cudaFreeHost(h_mon); h_mon = nullptr; }
         if (aux_stream) { cudaStreamDestroy(aux_stream); aux_stream = nullptr; }
-        if (act_stream) { cudaStreamDestroy(act_stream); act_stream = nullptr; }
-        if (ev_act_fork) { cudaEventDestroy(ev_act_fork); ev_act_fork = nullptr; }
-        if (ev_act_join) { cudaEventDestroy(ev_act_join); ev_act_join = nullptr; }
         if (ev_fork) { cudaEventDestroy(ev_fork); ev_fork = nullptr; }
         if (ev_join) { cudaEventDestroy(ev_join); ev_join = nullptr; }
         if (own_stream && stream) cudaStreamDestroy(stream);
@@ -838,17 +826,12 @@ struct Solver {
         }
         const dim3 gp(ceil_div(L.nx, b.x), ceil_div(L.ny, b.y), 1);
         if (open_z()) {
-            // the inlet kernels touch planes k <= 2, the outlet kernels planes k >= nz - 1 (and the convective buffers): with
-            // MFLBM_LANES=1 they run side by side (both are latency-bound plane kernels of ~15 us).  The fork is recorded
-            // before the inlet launch, so the outlet lane only waits for what precedes both.
-            const bool fork = bc_lanes && L.nz >= 8 && P.inlet_BC != 0 && P.outlet_BC != 0;
-            cudaStream_t so = fork ? act_stream : stream;
-            if (fork) { MF_CUDA(cudaEventRecord(ev_act_fork, stream)); MF_CUDA(cudaStreamWaitEvent(act_stream, ev_act_fork, 0)); }
+            // (the inlet and outlet kernels are independent, ~15 us each and latency-bound; running them side by side on two
+            // lanes of the graph was measured and bought nothing: 16 430 vs 16 558 MLUPS, profiles/README.md r02i)
             if (P.inlet_BC == 1) { if (odd) k_inlet_velocity<T, true><<<gp, b, 0, stream>>>(L, 1, L.nx); else k_inlet_velocity<T, false><<<gp, b, 0, stream>>>(L, 1, L.nx); count(); }
             else if (P.inlet_BC == 2) { if (odd) k_inlet_pressure<T, true><<<gp, b, 0, stream>>>(L, 1, L.nx); else k_inlet_pressure<T, false><<<gp, b, 0, stream>>>(L, 1, L.nx); count(); }
-            if (P.outlet_BC == 1) { if (odd) k_outlet_convective<T, true><<<gp, b, 0, so>>>(L, 1, L.nx); else k_outlet_convective<T, false><<<gp, b, 0, so>>>(L, 1, L.nx); count(); }
-            else if (P.outlet_BC == 2) { if (odd) k_outlet_pressure<T, true><<<gp, b, 0, so>>>(L, 1, L.nx); else k_outlet_pressure<T, false><<<gp, b, 0, so>>>(L, 1, L.nx); count(); }
-            if (fork) { MF_CUDA(cudaEventRecord(ev_act_join, act_stream)); MF_CUDA(cudaStreamWaitEvent(stream, ev_act_join, 0)); }
+            if (P.outlet_BC == 1) { if (odd) k_outlet_convective<T, true><<<gp, b, 0, stream>>>(L, 1, L.nx); else k_outlet_convective<T, false><<<gp, b, 0, stream>>>(L, 1, L.nx); count(); }
+            else if (P.outlet_BC == 2) { if (odd) k_outlet_pressure<T, true><<<gp, b, 0, stream>>>(L, 1, L.nx); else k_outlet_pressure<T, false><<<gp, b, 0, stream>>>(L, 1, L.nx); count(); }
             check_launch();
         }
         if (P.porous_plate_cmd != 0) {

@@ -44,6 +44,26 @@ def derived_close(a: np.ndarray, b: np.ndarray, tol: float, weight: np.ndarray |
     return ok, f"outlier fraction {frac:.2e}, worst {worst:.3e}"
 
 
+def threshold_flips(c_norm_a: np.ndarray, c_norm_b: np.ndarray) -> tuple[int, int]:
+    """(nodes where exactly one of the two c_norm arrays is zero, nodes where the reference's is non-zero): how many nodes sit on
+    different sides of the |grad phi| < 1e-6 cut-off (/root/reference/src/main_iteration_GPU.cu:795) in the two runs"""
+    za, zb = np.asarray(c_norm_a) == 0, np.asarray(c_norm_b) == 0
+    return int(np.count_nonzero(za != zb)), int(np.count_nonzero(~zb))
+
+
+def saturation_of(phi4: np.ndarray, walls2: np.ndarray, ctl: dict) -> tuple[float, float]:
+    """saturation and saturation_full_domain of /root/reference/src/Monitor.cpp:34-120 from a phase field (4-ghost layout) and
+    the wall flags (2-ghost layout), summed in double: vol1 = sum 0.5 (1 + phi) over fluid nodes, vol2 likewise with (1 - phi);
+    `saturation` over the slices n_exclude_inlet < k <= nz - n_exclude_outlet"""
+    phi = np.asarray(phi4, dtype=np.float64)[4:-4, 4:-4, 4:-4]
+    fluid = np.asarray(walls2)[2:-2, 2:-2, 2:-2] == 0
+    v1 = (0.5 * (1.0 + phi) * fluid).sum(axis=(1, 2))
+    v2 = (0.5 * (1.0 - phi) * fluid).sum(axis=(1, 2))
+    nz = phi.shape[0]
+    lo, hi = int(ctl["n_exclude_inlet"]), nz - int(ctl["n_exclude_outlet"])
+    return float(v1[lo:hi].sum() / (v1[lo:hi].sum() + v2[lo:hi].sum())), float(v1.sum() / (v1.sum() + v2.sum()))
+
+
 def derived_weight(c_norm_ref: np.ndarray, key: str) -> np.ndarray | None:
     """weight array for derived_close: c_norm (2 ghosts) cut to the grid of `key` (curv carries 1 ghost)"""
     if key == "c_norm":

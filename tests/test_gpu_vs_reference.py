@@ -86,6 +86,10 @@ def test_cuda_matches_live_reference_gpu(gpu_lib, name, prec):
         for k in ("cn_x", "cn_y", "cn_z", "c_norm"):
             ok, msg = common.derived_close(mine[k], ref[k], TOL[prec], common.derived_weight(ref["c_norm"], k))
             assert ok, (step, k, msg)
+        # how many nodes actually sit on the other side of the |grad phi| < 1e-6 threshold (:795): derived_close tolerates
+        # 0.1 % outliers because of them; the count itself is bounded here
+        flips, carrying = common.threshold_flips(mine["c_norm"], ref["c_norm"])
+        assert flips <= max(2, 2e-3 * carrying), (step, "nodes across the c_norm threshold", flips, carrying)
         fm = common_fluid_mask(geom, 1)
         ok, msg = common.derived_close(np.where(fm, mine["curv"], 0), np.where(fm, ref["curv"], 0), TOL[prec],
                                        common.derived_weight(ref["c_norm"], "curv"))
@@ -117,7 +121,7 @@ def test_saturation_after_10k_steps_matches_reference(gpu_lib, name, prec):
         pytest.skip("oracle/_ref/ref_gpu_* not present")
     import mflbm
     marks = (2000, 6000, 10000)
-    meta, geom, states, mon = refgpu.run_reference_gpu(name, prec, steps=(), monitor=marks)
+    meta, geom, states, mon = refgpu.run_reference_gpu(name, prec, steps=(marks[-1],), monitor=marks)
     ctl, solid = common.full_control(name)
     s = mflbm.Solver(mflbm.derive_params(ctl, prec), prec)
     s.upload_geometry(geom["walls"], geom["walls_type"], geom["s_nx"], geom["s_ny"], geom["s_nz"])
@@ -134,8 +138,64 @@ def test_saturation_after_10k_steps_matches_reference(gpu_lib, name, prec):
         m = s.monitor()
         assert m["nan_detected"] == 0
         sat_ref, sat_full_ref = float(row[2]), float(row[3])
-        # FP32: the reference itself prints 6-7 significant digits of a float; 1e-6 is the north_star figure for both
-        tol = 1e-6 if prec == "f64" else 2e-5
-        assert abs(m["saturation"] - sat_ref) <= tol, (step, m["saturation"], sat_ref)
-        assert abs(m["saturation_full_domain"] - sat_full_ref) <= tol, (step, m["saturation_full_domain"], sat_full_ref)
+        # north_star: 1e-6.  The reference accumulates its volume sums sequentially in T_P (src/Monitor.cpp:52-80): in single
+        # precision that alone moves ITS number by `floor`, measured below on the reference's own fields (the reference's phi of
+        # the last mark summed in double against what the reference printed for it).  Our sums are in double.
+        floor = 0.0
+        if step == marks[-1]:
+            sat64, satfull64 = common.saturation_of(states[step]["phi"], geom["walls"], ctl)
+            floor = max(abs(sat64 - sat_ref), abs(satfull64 - sat_full_ref))
+            assert abs(m["saturation"] - sat64) <= 1e-6 and abs(m["saturation_full_domain"] - satfull64) <= 1e-6, (step, m["saturation"], sat64)
+            assert floor <= (1e-9 if prec == "f64" else 5e-5), floor
+        tol = 1e-6 + (floor if step == marks[-1] else (0.0 if prec == "f64" else 2e-5))
+        assert abs(m["saturation"] - sat_ref) <= tol, (step, m["saturation"], sat_ref, floor)
+        assert abs(m["saturation_full_domain"] - sat_full_ref) <= tol, (step, m["saturation_full_domain"], sat_full_ref, floor)
+    s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec,steps", [("f64", (2, 100)), ("f32", (100,))])
+def test_cuda_matches_live_reference_gpu_at_benchmark_size(gpu_lib, tmp_path, prec, steps):
+    """BASELINE configs[1] / [2] at full size: the 256^3 sphere-pack drainage workload of bench.py, the reference's own GPU
+    kernels run on the spot (oracle/_ref/ref_gpu_*) and ours from the same geometry arrays and the same step-0 state.
+    pdf / phi within 1e-12 (FP64) / 1e-5 (FP32) after 2 and 100 steps, the monitored saturation within 1e-6."""
+    if not rc.ref_binary("gpu", prec).exists():
+        pytest.skip("oracle/_ref/ref_gpu_* not present")
+    import shutil
+    import bench
+    import mflbm
+    n = 256
+    if shutil.disk_usage(tmp_path).free < 40e9:
+        pytest.skip("needs ~30 GB of scratch space for the reference's state dumps")
+    ctl = bench.workload_control(n, n, n)
+    solid = bench.workload_geometry(n, n, n)
+    case = tmp_path / "case"
+    full = rc.write_case(case, ctl, solid)
+    out = rc.run_ref("gpu", prec, case, tmp_path / "out", dump=steps, monitor=(steps[-1],), timeout=1800)
+    meta = rc.read_meta(out)
+    geom = rc.load_geometry(out, meta)
+    s = mflbm.Solver(mflbm.derive_params(full, prec), prec)
+    s.upload_geometry(geom["walls"], geom["walls_type"], geom["s_nx"], geom["s_ny"], geom["s_nz"])
+    st0 = rc.load_state(out, 0, meta)
+    s.upload_state(pdf=st0["pdf"], phi=st0["phi"], cn_x=st0["cn_x"], cn_y=st0["cn_y"], cn_z=st0["cn_z"], c_norm=st0["c_norm"],
+                   curv=st0["curv"], W_in=geom["W_in"], f_convec=st0.get("f_convec_bc"), g_convec=st0.get("g_convec_bc"),
+                   phi_convec=st0.get("phi_convec_bc"))
+    del st0
+    done = 0
+    for step in steps:
+        s.run(1 + done, step - done)
+        done = step
+        mine = s.download_state(fields=("pdf", "phi", "c_norm"))
+        ref = rc.load_state(out, step, meta)
+        mine["phi"].reshape(-1)[0] = ref["phi"].reshape(-1)[0]   # reference defect 2.3-2, see refgpu.py
+        for k in ("pdf", "phi"):
+            e = relerr(mine[k], ref[k])
+            assert e <= TOL[prec], (step, k, e)
+        flips, carrying = common.threshold_flips(mine["c_norm"], ref["c_norm"])
+        assert flips <= max(2, 2e-3 * carrying), (step, flips, carrying)
+        del mine, ref
+    vals = (out / "monitor.txt").read_text().split()
+    m = s.monitor()
+    tol = 1e-6 if prec == "f64" else 1e-6 + 5e-5   # FP32: + the reference's own single-precision accumulation (see the 10 k-step test)
+    assert abs(m["saturation"] - float(vals[2])) <= tol and abs(m["saturation_full_domain"] - float(vals[3])) <= tol
     s.close()

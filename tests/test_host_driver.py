@@ -159,6 +159,27 @@ STOCK_CASES = {
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 @pytest.mark.parametrize("name", sorted(STOCK_CASES))
 def test_driver_matches_stock_reference_program(gpu_lib, tmp_path, name, prec):
+    _compare_with_stock_program(tmp_path, name, prec, lambda case: run_driver(case, "--prec", prec))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("name", ["tube_pressure", "pack_velocity", "periodic_phasefield"])
+def test_shim_program_matches_stock_reference_program(gpu_lib, tmp_path, name, prec):
+    """The drop-in, compiled: the reference's own src/main.cpp + CPU sources (unmodified) with integration/mflbm_shim.cpp in
+    place of src/main_iteration_GPU.cu and src/Init_multiphase_GPU.cu, linked against libmflbm.so (oracle/build_ref.sh,
+    target shim), against the stock program on the same case directories: every output file."""
+    shim = rc.REF_BIN_DIR / f"MF_LBM_CUDA_shim_{prec}"
+    if not shim.exists():
+        pytest.skip(f"{shim} not built (oracle/build_ref.sh shim needs /root/reference)")
+
+    def run(case):
+        r = subprocess.run([str(shim)], cwd=str(case), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-2000:]
+    _compare_with_stock_program(tmp_path, name, prec, run)
+
+
+def _compare_with_stock_program(tmp_path, name, prec, run_ours):
     stock = rc.REF_BIN_DIR / f"MF_LBM_CUDA_{prec}"
     if not stock.exists():
         pytest.skip(f"{stock} not built (oracle/build_ref.sh needs /root/reference)")
@@ -168,7 +189,7 @@ def test_driver_matches_stock_reference_program(gpu_lib, tmp_path, name, prec):
     ours, ref = tmp_path / "ours", tmp_path / "ref"
     full = rc.write_case(ours, ctl, solid)
     shutil.copytree(ours, ref)
-    run_driver(ours, "--prec", prec)
+    run_ours(ours)
     r = subprocess.run([str(stock)], cwd=str(ref), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:]
     nz, ny, nx = solid.shape
@@ -294,3 +315,50 @@ def test_driver_random_initial_distribution(gpu_lib, tmp_path):
     sat = rows(tmp_path / "results" / "out1.output" / "saturation_full_domain.dat")
     assert sat.shape[0] == 1 and np.isfinite(sat).all() and 0.3 < sat[0, 1] < 0.5
     assert (tmp_path / "job_status.txt").read_text() == "simulation_reached_max_step\n"
+
+
+# the shipped control file (/root/reference/input/simulation_control.txt) with the changes SURVEY.md 8d lists for BASELINE
+# configs[0]: the bundled geometry's own dimensions (the shipped 240 x 240 x 260 do not match the 60 x 60 x 80 file), drainage
+# (option 1, saturation_injection 1), the porous plate inside the sample, 2 000 steps monitored every 200
+SHIPPED = dict(initial_fluid_distribution_option=1, benchmark_cmd=0, extreme_large_sim_cmd=0, breakthrough_check=0, steady_state_option=3,
+               convergence_criteria=1e-4, output_fieldData_precision_cmd=0, modify_geometry_cmd=0, geometry_preprocess_cmd=0,
+               porous_plate_cmd=2, Z_porous_plate=72, change_inlet_fluid_phase_cmd=0, n_exclude_inlet=10, n_exclude_outlet=10,
+               fluid1_viscosity=0.04, fluid2_viscosity=0.4, surface_tension=0.03, theta=65, RK_beta=0.95, inlet_BC=2, outlet_BC=2,
+               saturation_injection=1.0, target_inject_pore_volume=-1.0, initial_interface_position=8.0, capillary_number=100e-6,
+               body_force_0=1e-4, rho_in_new=1, rho_out_BC=0, target_fluid1_saturation=0.4, max_time_step=1999, max_time_step_benchmark=100,
+               ntime_visual=5000000, ntime_animation=10000, monitor_timer=200, monitor_profile_timer_ratio=5, computation_time_timer=2000,
+               display_steps_timer=10000, checkpoint_save_timer=1.0, checkpoint_2rd_save_timer=5.5, simulation_duration_timer=168.0,
+               d_vol_animation=-0.05, d_vol_detail=-1.0, d_vol_monitor=-0.01)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_driver_matches_stock_program_on_the_shipped_case(gpu_lib, tmp_path, prec):
+    """BASELINE configs[0]: the reference's shipped drainage case on its bundled geometry (tube_sphere 60 x 60 x 80, fixture
+    made from /root/reference/input/geometry/tube_sphere.dat by tests/golden/make_tube_sphere_fixture.py), 2 000 steps, run by
+    the reference's stock program and by mflbm_run.  Saturation within 1e-6 at every monitor step (north_star); the checkpoint
+    is compared past the 100-step horizon of the 1e-12 / 1e-5 field tolerance, hence looser."""
+    stock = rc.REF_BIN_DIR / f"MF_LBM_CUDA_{prec}"
+    if not stock.exists():
+        pytest.skip(f"{stock} not built (oracle/build_ref.sh needs /root/reference)")
+    solid = np.load(REPO / "tests" / "golden" / "tube_sphere_60_60_80.npz")["solid"]
+    nz, ny, nx = solid.shape
+    ours, ref = tmp_path / "ours", tmp_path / "ref"
+    rc.write_case(ours, SHIPPED, solid)
+    shutil.copytree(ours, ref)
+    run_driver(ours, "--prec", prec)
+    r = subprocess.run([str(stock)], cwd=str(ref), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert (ours / "job_status.txt").read_text() == (ref / "job_status.txt").read_text() == "simulation_reached_max_step\n"
+    out_o, out_r = ours / "results" / "out1.output", ref / "results" / "out1.output"
+    for n in ("saturation.dat", "saturation_full_domain.dat"):
+        a, b = rows(out_o / n), rows(out_r / n)
+        assert a.shape == b.shape and a.shape[0] >= 9, (n, a.shape, b.shape)     # one row per monitor step (200, 400, ...)
+        assert np.array_equal(a[:, 0], b[:, 0])
+        # printed with 6 significant digits by both programs: half a unit of the last place on top of the 1e-6 criterion
+        assert (np.abs(a[:, 1:] - b[:, 1:]) <= (1e-6 + 5e-7) * np.maximum(1.0, np.abs(b[:, 1:]))).all(), (n, a, b)
+    rt = np.float32 if prec == "f32" else np.float64
+    co = read_checkpoint(ours / "results" / "out2.checkpoint" / "id0000", nx, ny, nz, rt, False)
+    cr = read_checkpoint(ref / "results" / "out2.checkpoint" / "id0000", nx, ny, nz, rt, False)
+    assert co["ntime"] == cr["ntime"] and co["force_z"] == cr["force_z"] and co["rho_in"] == cr["rho_in"]
+    assert common.relerr(co["pdf"], cr["pdf"]) <= (1e-9 if prec == "f64" else 1e-3), common.relerr(co["pdf"], cr["pdf"])
