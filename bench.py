@@ -494,6 +494,24 @@ def bench_slabs(args, rank: int, world: int, local: int) -> dict | None:
                 stepper.exchange(sm.KIND_PHI)
                 slab.step_phase(nt_, 2)
             t_odd, t_even, nt = time_collide_launches(slab.solver, stream, nt, args.steps, step_fn=one)
+            # where a slab's step goes, phase by phase (serial schedule, CUDA events on the launching stream, mean over 20 steps;
+            # the timed run above overlaps the PDF message with the interior collide tiles): diagnostic, reported as config.phase_ms
+            names = ("collide", "halo_pdf", "boundaries", "halo_phi", "chain")
+            evs = []
+            for _ in range(20):
+                e = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+                e[0].record(stream); slab.step_phase(nt, 0)
+                e[1].record(stream); stepper.exchange(sm.KIND_PDF_ODD if nt % 2 else sm.KIND_PDF_EVEN)
+                e[2].record(stream); slab.step_phase(nt, 1)
+                e[3].record(stream); stepper.exchange(sm.KIND_PHI)
+                e[4].record(stream); slab.step_phase(nt, 2)
+                e[5].record(stream)
+                evs.append(e); nt += 1
+            torch.cuda.synchronize()
+            ph = torch.tensor([float(np.mean([e[i].elapsed_time(e[i + 1]) for e in evs])) for i in range(5)], dtype=torch.float64, device=f"cuda:{local}")
+            ph_max = ph.clone()
+            dist.all_reduce(ph_max, op=dist.ReduceOp.MAX)
+            phase_ms = {n: {"rank0": float(a), "max": float(b)} for n, a, b in zip(names, ph.tolist(), ph_max.tolist())}
             stepper.last_ntime = nt - 1
             tk = torch.tensor([t_odd, t_even], dtype=torch.float64, device=f"cuda:{local}")
             dist.all_reduce(tk, op=dist.ReduceOp.MAX)
@@ -554,7 +572,7 @@ def bench_slabs(args, rank: int, world: int, local: int) -> dict | None:
                        "l2": "state per GPU >> 126 MB L2 (inputs larger than L2, no flush needed)",
                        "fluid_mlups": n_fluid * args.steps / 1e6 / (ms * 1e-3), "geometry_preprocess_s": t_geo,
                        "saturation_full_domain": mon["saturation_full_domain"], "halo_exchanges_per_step": 2,
-                       "partition": args.partition, "slab_width_rank0": rng.nx_local, "parity_checked": parity},
+                       "partition": args.partition, "slab_width_rank0": rng.nx_local, "parity_checked": parity, "phase_ms": phase_ms},
             "roofline": roof,
             "e2e": e2e,
             "gpu_launches": int(launches) * world,

@@ -262,8 +262,9 @@ __global__ void k_init_pdf(const Lattice<T> L, int outlet_convective) {
 // =====================================================================================================
 // monitor: compute_macro_vars (src/Misc.cpp:222-274) + per-slice sums (src/Monitor.cpp:34-80) in one pass, on the
 // device (the reference copies the whole state to the host and loops there).  One block per z slice; the fluid
-// nodes of a slice are the contiguous range [zstart[k-1], zstart[k]) of the permuted order, so every PDF read is
-// a contiguous row.  Warp-shuffle + block reduction, sums in double (the reference sums sequentially in T; see
+// nodes of a slice are two contiguous ranges of the permuted order - [zstart[k-1], zstart[k]) among the nodes of a slab's
+// neighbour-facing columns (empty for a full lattice), [zstart[nz+2+k-1], zstart[nz+2+k]) among the others - so every PDF
+// read is a contiguous row.  Warp-shuffle + block reduction, sums in double (the reference sums sequentially in T; see
 // DESIGN.md).
 // out layout per slice k-1: [0..6] fl1, fl2, pre, mass1, mass2, vol1, vol2, [7] max |u|^2, [8] usq1, [9] usq2, [10] nan flag,
 // [11] sum rho where phi < -0.99, [12] their count, [13] sum rho where phi > 0.99, [14] their count, [15] count phi > 0
@@ -276,7 +277,8 @@ __global__ void __launch_bounds__(256) k_monitor(const Lattice<T> L, const int* 
     double acc[MFLBM_MON_N];
 #pragma unroll
     for (int n = 0; n < MFLBM_MON_N; n++) acc[n] = 0.0;
-    const int t0 = zstart[k - 1], t1 = zstart[k];
+    for (int seg = 0; seg < 2; seg++) {
+    const int t0 = zstart[seg * (L.nz + 2) + k - 1], t1 = zstart[seg * (L.nz + 2) + k];
     for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
         const int u = L.fl_u[t];
         T ft[19];
@@ -301,6 +303,7 @@ __global__ void __launch_bounds__(256) k_monitor(const Lattice<T> L, const int* 
         if (ph < lit<T>(-0.99)) { acc[11] += (double)rho; acc[12] += 1.0; }
         if (ph > lit<T>(0.99)) { acc[13] += (double)rho; acc[14] += 1.0; }
         if (ph > lit<T>(0.)) acc[15] += 1.0;
+    }
     }
     __shared__ double sm[MFLBM_MON_N][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -443,10 +446,17 @@ __device__ __forceinline__ bool halo_await(const HaloSync& hs) {
     return ok_s != 0;
 }
 
+// The wait on its own, one CTA: in the overlapped schedule (Solver::step_p2p) the unpack kernel follows it on the same lane.
+// (An unpack kernel whose every CTA waits fills the SMs' thread slots with spinning CTAs and keeps the interior collide
+// launch from starting until the message is there.)
+__global__ void k_halo_wait(const HaloSync hs) { halo_await(hs); }
+// unpack without a wait of its own: leave the lattice alone once a message has been lost
+__device__ __forceinline__ bool halo_ok(const HaloSync& hs) { return !(hs.error && *reinterpret_cast<volatile unsigned*>(hs.error) != 0u); }
+
 // copy column `col` of the ten slots (PLUS ? ex=+1 : ex=-1) between the lattice and a buffer
 template <typename T, bool PLUS, bool PACK>
 __global__ void k_halo_pdf(const Lattice<T> L, T* __restrict__ buf, const int col, const HaloSync hs) {
-    if (!PACK && !halo_await(hs)) return;
+    if (!PACK && !(hs.flag ? halo_await(hs) : halo_ok(hs))) return;
     const int y = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
     if (y < L.NY1) {
         const int plane = L.NY1 * L.NZ1;
@@ -469,7 +479,7 @@ __global__ void k_halo_pdf(const Lattice<T> L, T* __restrict__ buf, const int co
 // copy 4 phi columns starting at local column `col0` between the lattice and a buffer
 template <typename T, bool PACK>
 __global__ void k_halo_phi(const Lattice<T> L, T* __restrict__ buf, const int col0, const HaloSync hs) {
-    if (!PACK && !halo_await(hs)) return;
+    if (!PACK && !(hs.flag ? halo_await(hs) : halo_ok(hs))) return;
     const int y = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;   // 0-based over the 4-ghost extents
     if (y < L.PY) {
         const int plane = L.PY * L.PZ;

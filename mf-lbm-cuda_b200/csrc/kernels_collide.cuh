@@ -92,7 +92,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 template <typename T, int MRT, int NST, int CTAS>
-__global__ void __launch_bounds__(COLLIDE_EVEN_THREADS, CTAS) k_collide_even_tma(const Lattice<T> L, const int ntiles, const int bulk_skip) {
+__global__ void __launch_bounds__(COLLIDE_EVEN_THREADS, CTAS) k_collide_even_tma(const Lattice<T> L, const int tile0, const int ntiles, const int bulk_skip) {   // tiles [tile0, ntiles)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     typedef Pair<T> Stage[19][COLLIDE_TILE];
     Stage* buf = reinterpret_cast<Stage*>(smem_raw);
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(COLLIDE_EVEN_THREADS, CTAS) k_collide_even_tma
         int s = 0;
         uint32_t phase = 0;   // parity of the empty-phase a refill of stage s has to see completed
         int it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += stride, it++) {
+        for (int tile = tile0 + blockIdx.x; tile < ntiles; tile += stride, it++) {
             if (it >= NST) pipe::mbar_wait(&empty[s], phase);
             if (lane == 0) pipe::mbar_expect_tx(&full[s], (uint32_t)sizeof(Stage));
             if (lane < 19) pipe::bulk_g2s(&buf[s][lane][0], L.pairs(lane) + (long long)tile * COLLIDE_TILE, (uint32_t)(sizeof(Pair<T>) * COLLIDE_TILE), &full[s]);
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(COLLIDE_EVEN_THREADS, CTAS) k_collide_even_tma
         if (u_cn >= 0) pipe::cp_async<sizeof(T)>(&cS[slot * COLLIDE_TILE + tid], L.c_norm + u_cn);
         pipe::cp_async_commit();
     };
-    int tile = blockIdx.x;
+    int tile = tile0 + blockIdx.x;
     int u = site(tile), uN = site(tile + stride);
     prefetch(tile + 2 * stride, u, 0);   // c_norm of the first tile, site of the third
     int s = 0, slot = 0;                 // slot: the pair (cS, uS) half this iteration reads; the other half is being filled
@@ -223,7 +223,7 @@ template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("s
 template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
 template <typename T, int MRT, int NST, int CTAS, int NCONS, int REGS_P, int REGS_C>
-__global__ void __launch_bounds__((NCONS + 1) * COLLIDE_TILE, CTAS) k_collide_odd_ws(const Lattice<T> L, const int ntiles, const int bulk_skip) {
+__global__ void __launch_bounds__((NCONS + 1) * COLLIDE_TILE, CTAS) k_collide_odd_ws(const Lattice<T> L, const int tile0, const int ntiles, const int bulk_skip) {   // tiles [tile0, ntiles)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     typedef OddStage<T> Stage;
     Stage* stg = reinterpret_cast<Stage*>(smem_raw);
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__((NCONS + 1) * COLLIDE_TILE, CTAS) k_collide_od
 #pragma unroll
             for (int q = 1; q < 19; q++) c[q - 1] = u >= 0 ? __ldg(cmap + (u + L.off(q))) : 0;
         };
-        int tile = blockIdx.x;
+        int tile = tile0 + blockIdx.x;
         int uCur = site_of(tile), uNxt = site_of(tile + stride);
         int cN[18], wbN;
         load_raw(tile, uCur, cN, wbN);
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__((NCONS + 1) * COLLIDE_TILE, CTAS) k_collide_od
     if (REGS_C > 0) reg_alloc<REGS_C>();
     const int cg = tid / COLLIDE_TILE, ct = tid - cg * COLLIDE_TILE;   // consumer group, entry within the tile
     for (int i = cg; ; i += NCONS) {
-        const int tile = blockIdx.x + i * stride;
+        const int tile = tile0 + blockIdx.x + i * stride;
         if (tile >= ntiles) break;
         const int st = i % NST;
         Stage& S = stg[st];

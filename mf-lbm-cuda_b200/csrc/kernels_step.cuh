@@ -230,12 +230,12 @@ __device__ __forceinline__ void inlet_phi(const Lattice<T>& L, int i, int j, int
     const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;      \
     if (i > ihi || j > L.ny) return;
 
-template <typename T, bool AFTER>
-__global__ void k_inlet_velocity(const Lattice<T> L, const int ilo, const int ihi) {  // :1009-1077
+template <typename T, bool AFTER, int PART>
+__device__ __forceinline__ void inlet_velocity_plane(const Lattice<T>& L, const int ilo, const int ihi) {  // :1009-1077
     MFLBM_PLANE_IJ();
     const int wi = L.solid(L.u(i, j, 1)) ? 1 : 0;
-    inlet_phi(L, i, j, wi);
-    if (wi) return;
+    if (PART != 2) inlet_phi(L, i, j, wi);
+    if (wi || PART == 1) return;
     T tmp2 = L.W_in[L.iplane(i, j)] * L.relaxation;
     const T tmp1 = tmp2 * L.sa_inject;
     tmp2 = tmp2 - tmp1;
@@ -281,12 +281,12 @@ template <typename T, bool AFTER> __device__ __forceinline__ T zh_tnx(const T (&
                  : lit<T>(0.5) * (v[1] + v[7] + v[9] - (v[2] + v[8] + v[10]));
 }
 
-template <typename T, bool AFTER>
-__global__ void k_inlet_pressure(const Lattice<T> L, const int ilo, const int ihi) {  // :1085-1241
+template <typename T, bool AFTER, int PART>
+__device__ __forceinline__ void inlet_pressure_plane(const Lattice<T>& L, const int ilo, const int ihi) {  // :1085-1241
     MFLBM_PLANE_IJ();
     const int wi = L.solid(L.u(i, j, 1)) ? 1 : 0;
-    inlet_phi(L, i, j, wi);
-    if (wi) return;
+    if (PART != 2) inlet_phi(L, i, j, wi);
+    if (wi || PART == 1) return;
     T rho2 = L.rho_in;
     const T rho1 = L.rho_in * L.sa_inject;
     rho2 = rho2 - rho1;
@@ -319,16 +319,19 @@ __global__ void k_inlet_pressure(const Lattice<T> L, const int ilo, const int ih
     }
 }
 
-template <typename T, bool AFTER>
-__global__ void k_outlet_convective(const Lattice<T> L, const int ilo, const int ihi) {  // :1246-1357
+template <typename T, bool AFTER, int PART>
+__device__ __forceinline__ void outlet_convective_plane(const Lattice<T>& L, const int ilo, const int ihi) {  // :1246-1357
     MFLBM_PLANE_IJ();
     const int nz = L.nz;
     const T u_convec = L.uin_avg;
     const T temp = lit<T>(1.) / (lit<T>(1.) + u_convec);
     const int wi = L.solid(L.u(i, j, nz)) ? 1 : 0;
     const int c = L.u(i, j, nz), sz = L.sz, cb = L.iplane(i, j);
-    const T ph = ((L.phi_convec[cb] + u_convec * L.phi[c]) * temp) * (1 - wi) + L.phi[c + sz] * wi;
-    L.phi[c + sz] = ph; L.phi_convec[cb] = ph; L.phi[c + 2 * sz] = ph; L.phi[c + 3 * sz] = ph; L.phi[c + 4 * sz] = ph;
+    if (PART != 2) {
+        const T ph = ((L.phi_convec[cb] + u_convec * L.phi[c]) * temp) * (1 - wi) + L.phi[c + sz] * wi;
+        L.phi[c + sz] = ph; L.phi_convec[cb] = ph; L.phi[c + 2 * sz] = ph; L.phi[c + 3 * sz] = ph; L.phi[c + 4 * sz] = ph;
+    }
+    if (PART == 1) return;
     const int plane = L.NX1 * L.NY1;
     // addresses, loads, stores in three rounds (see k_inlet_velocity)
     T* dst[10]; const T* inner[10]; T* rec[10]; T a[10], b[10];
@@ -355,15 +358,15 @@ __global__ void k_outlet_convective(const Lattice<T> L, const int ilo, const int
     }
 }
 
-template <typename T, bool AFTER>
-__global__ void k_outlet_pressure(const Lattice<T> L, const int ilo, const int ihi) {  // :1363-1524
+template <typename T, bool AFTER, int PART>
+__device__ __forceinline__ void outlet_pressure_plane(const Lattice<T>& L, const int ilo, const int ihi) {  // :1363-1524
     MFLBM_PLANE_IJ();
     const int nz = L.nz;
     const int wi = L.solid(L.u(i, j, nz)) ? 1 : 0;
     const int c = L.u(i, j, nz), sz = L.sz;
     const T phn = L.phi[c];
-    L.phi[c + sz] = phn; L.phi[c + 2 * sz] = phn; L.phi[c + 3 * sz] = phn; L.phi[c + 4 * sz] = phn;
-    if (wi) return;
+    if (PART != 2) { L.phi[c + sz] = phn; L.phi[c + 2 * sz] = phn; L.phi[c + 3 * sz] = phn; L.phi[c + 4 * sz] = phn; }
+    if (wi || PART == 1) return;
     T v0[11], v1[11], o0[5], o1[5];
     zh_inplane<T, AFTER>(L, i, j, nz, 0, v0);
     zh_inplane<T, AFTER>(L, i, j, nz, 1, v1);
@@ -401,6 +404,22 @@ __global__ void k_outlet_pressure(const Lattice<T> L, const int ilo, const int i
             if (AFTER) L.f(q, g, L.u(i, j, nz)) = val;
             else L.f(o, g, L.u(i - ex(o), j - ey(o), nz + 1)) = val;
         }
+    }
+}
+
+// One launch for both ends of an open z axis: blockIdx.z = 0 runs the inlet plane, 1 the outlet plane (two independent
+// latency-bound plane kernels; they touch k <= 2 and k >= nz - 1).  INLET / OUTLET: 0 none, 1 velocity / convective,
+// 2 pressure (the reference's inlet_BC / outlet_BC).  PART: 0 everything; 1 the phase-field part only (ghost planes of phi,
+// phi_convec); 2 the distribution part only.  The two parts are independent of each other - the distribution part reads phi at
+// real fluid nodes only - so Solver::step runs part 2 on a second lane NEXT TO the gradient chain, which needs part 1 only.
+template <typename T, bool AFTER, int INLET, int OUTLET, int PART>
+__global__ void k_open_z(const Lattice<T> L, const int ilo, const int ihi) {
+    if (blockIdx.z == 0) {
+        if (INLET == 1) inlet_velocity_plane<T, AFTER, PART>(L, ilo, ihi);
+        else if (INLET == 2) inlet_pressure_plane<T, AFTER, PART>(L, ilo, ihi);
+    } else {
+        if (OUTLET == 1) outlet_convective_plane<T, AFTER, PART>(L, ilo, ihi);
+        else if (OUTLET == 2) outlet_pressure_plane<T, AFTER, PART>(L, ilo, ihi);
     }
 }
 

@@ -85,6 +85,7 @@ struct Solver {
     int n_list_phi = 0, n_list_cn = 0, n_list_alter = 0, n_list_alter_all = 0, n_list_n = 0;
     long long counts[4] = {0, 0, 0, 0};
     long long n_fluid = 0;
+    long long n_boundary = 0;   // fluid nodes of the columns that face a neighbour slab: the first entries of the fluid order
     long long launches = 0;
     bool have_geometry = false;
     // staging buffer for layout conversion at the boundary
@@ -109,6 +110,8 @@ struct Solver {
     T* d_recv[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
     // halo messages through peer memory (kernels_aux.cuh): my incoming flags [kind*2+side], block tickets [8 + ...] and
     // message counters [16 + ...]; the neighbours' receive buffers / flags as peer pointers
+    cudaStream_t bc_stream = nullptr;           // second lane of a step: distribution part of the boundary kernels next to the gradient chain
+    cudaEvent_t ev_bc_fork = nullptr, ev_bc_join = nullptr;
     cudaStream_t aux_stream = nullptr;          // second lane for the right-hand neighbour's messages (fork/join with events)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     unsigned char* d_p2p = nullptr;
@@ -119,6 +122,7 @@ struct Solver {
     // CUDA graph of one (odd, even) or (even, odd) step pair
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
     long long pair_launches = 0;
+    bool no_overlap = false;   // MFLBM_NO_OVERLAP=1: halo messages after the whole collide launch (the pre-overlap schedule, for comparison)
     int variant = 0;   // kernel schedule variant (MFLBM_VARIANT, tuning only; results are identical)
     int max_ctas = 0;  // MFLBM_MAX_CTAS: cap on the persistent collide grids (tests only)
     int num_sms = 148;
@@ -197,9 +201,13 @@ struct Solver {
         if (const char* v = getenv("MFLBM_MAX_CTAS")) max_ctas = atoi(v);
         if (const char* v = getenv("MFLBM_CHAIN")) brick_chain = strcmp(v, "list") != 0;
         if (const char* v = getenv("MFLBM_ACT_SCAN")) act_scan = atoi(v) != 0;
+        if (const char* v = getenv("MFLBM_NO_OVERLAP")) no_overlap = atoi(v) != 0;
         MF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
         if (strm) { stream = (cudaStream_t)strm; own_stream = false; }
         else { MF_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true; }
+        MF_CUDA(cudaStreamCreateWithFlags(&bc_stream, cudaStreamNonBlocking));
+        MF_CUDA(cudaEventCreateWithFlags(&ev_bc_fork, cudaEventDisableTiming));
+        MF_CUDA(cudaEventCreateWithFlags(&ev_bc_join, cudaEventDisableTiming));
         if (p->nx < 3 || p->ny < 3 || p->nz < 3) MF_FAIL("lattice too small");
         if (p->iper != 0) MF_FAIL("x-periodic boundaries are not supported (reference: src/IO_multiphase.cpp:210)");
         if (p->mrt < 1 || p->mrt > 4) MF_FAIL("mrt must be 1..4");
@@ -237,11 +245,13 @@ struct Solver {
             zalloc((void**)&d_active, sizeof(int) * nb); zalloc((void**)&d_n_active, sizeof(int));
         }
         if (!brick_chain) zalloc((void**)&d_near, PN);
-        zalloc((void**)&d_zstart, sizeof(int) * (L.nz + 2));
+        zalloc((void**)&d_zstart, sizeof(int) * 2 * (L.nz + 2));
         zalloc((void**)&d_mon, sizeof(double) * MFLBM_MON_N * L.nz);
         MF_CUDA(cudaMallocHost((void**)&h_mon, sizeof(double) * MFLBM_MON_N * L.nz));
         if (is_slab) {
-            MF_CUDA(cudaStreamCreateWithFlags(&aux_stream, cudaStreamNonBlocking));
+            int prio_lo = 0, prio_hi = 0;
+            MF_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            MF_CUDA(cudaStreamCreateWithPriority(&aux_stream, cudaStreamNonBlocking, prio_hi));   // halo kernels go first when CTA slots free up
             MF_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
             MF_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
             // everything a neighbour may write - arrival flags and the six receive buffers - is ONE allocation, so that a
@@ -308,6 +318,9 @@ struct Solver {
         for (int kind = 0; kind < 3; kind++) for (int side = 0; side < 2; side++) { dfree(d_send[kind][side]); d_recv[kind][side] = nullptr; }
         if (h_mon) { cudaFreeHost(h_mon); h_mon = nullptr; }
         if (aux_stream) { cudaStreamDestroy(aux_stream); aux_stream = nullptr; }
+        if (bc_stream) { cudaStreamSynchronize(bc_stream); cudaStreamDestroy(bc_stream); bc_stream = nullptr; }
+        if (ev_bc_fork) { cudaEventDestroy(ev_bc_fork); ev_bc_fork = nullptr; }
+        if (ev_bc_join) { cudaEventDestroy(ev_bc_join); ev_bc_join = nullptr; }
         if (ev_fork) { cudaEventDestroy(ev_fork); ev_fork = nullptr; }
         if (ev_join) { cudaEventDestroy(ev_join); ev_join = nullptr; }
         if (own_stream && stream) cudaStreamDestroy(stream);
@@ -364,7 +377,7 @@ struct Solver {
         auto U = [&](int x, int y, int z) { return (x + 3) + PX * ((y + 3) + PY * (z + 3)); };
         int offq[19];
         for (int q = 0; q < 19; q++) offq[q] = ex(q) + PX * (ey(q) + PY * ez(q));
-        std::vector<int> cmap((size_t)PN, -1), flu, passive, lphi, mphi, lcn, mcn, ln, shell, lbc, mbc, zstart((size_t)nz + 2, 0);
+        std::vector<int> cmap((size_t)PN, -1), flu, passive, lphi, mphi, lcn, mcn, ln, shell, lbc, mbc, flu_b, zstart(2 * ((size_t)nz + 2), 0);
         // planes whose phi the boundary kernels copy into ghost layers (k_chain_pre): inlet_phi reads k = 0, the outlet kernels
         // k = nz and nz + 1 (kernels_step.cuh), k_periodic_phi the four real layers at each end of a periodic axis
         const bool oz = open_z();
@@ -377,7 +390,10 @@ struct Solver {
         flu.reserve((size_t)nx * ny * nz / 2);
         counts[0] = counts[1] = counts[2] = counts[3] = 0;
         for (int z = -3; z <= nz + 4; z++) {
-            if (z >= 1 && z <= nz + 1) zstart[(size_t)z - 1] = (int)flu.size();   // fluid nodes with z' < z
+            // fluid nodes with z' < z, in two segments of the fluid order: the nodes of the columns that face a neighbour slab
+            // come first (their collide tiles run before the halo messages are packed, the rest overlaps the messages), then
+            // all others; each segment in z,y,x order
+            if (z >= 1 && z <= nz + 1) { zstart[(size_t)z - 1] = (int)flu_b.size(); zstart[(size_t)nz + 2 + z - 1] = (int)flu.size(); }
             for (int y = -3; y <= ny + 4; y++) for (int x = -3; x <= nx + 4; x++) {
                 const int u = U(x, y, z);
                 const int t = ty[(size_t)u];
@@ -385,7 +401,10 @@ struct Solver {
                 const bool in2 = x >= -1 && x <= nx + 2 && y >= -1 && y <= ny + 2 && z >= -1 && z <= nz + 2;
                 const bool in1 = x >= 0 && x <= nx + 1 && y >= 0 && y <= ny + 1 && z >= 0 && z <= nz + 1;
                 const bool in0 = x >= 1 && x <= nx && y >= 1 && y <= ny && z >= 1 && z <= nz;
-                if (in1) { if (t <= 0 && in0) flu.push_back(u); else passive.push_back(u); }
+                if (in1) {
+                    if (t <= 0 && in0) { if ((x == 1 && slab.has_left) || (x == nx && slab.has_right)) flu_b.push_back(u); else flu.push_back(u); }
+                    else passive.push_back(u);
+                }
                 if (t <= 0 && !in0 && brick_chain) shell.push_back(u);   // k_act_shell: phi there is written by boundary kernels and halos
                 if (t <= 0 && in2 && !brick_chain) ln.push_back(u);      // k_normals: non-solid sites of [-1..n+2]^3 (:760-764)
                 if (t == 2) {
@@ -403,9 +422,10 @@ struct Solver {
                 }
             }
         }
-        zstart[(size_t)nz + 1] = (int)flu.size();
-        // entries z = nz+1.. of the loop above never fired for z > nz+1; make the tail consistent
-        for (int z = nz; z >= 1; z--) if (zstart[(size_t)z] < zstart[(size_t)z - 1]) zstart[(size_t)z] = zstart[(size_t)z - 1];
+        zstart[(size_t)nz + 1] = (int)flu_b.size(); zstart[2 * (size_t)nz + 3] = (int)flu.size();
+        n_boundary = (long long)flu_b.size();
+        for (size_t k = (size_t)nz + 2; k < zstart.size(); k++) zstart[k] += (int)n_boundary;   // the second segment starts behind the first
+        flu.insert(flu.begin(), flu_b.begin(), flu_b.end());
         n_fluid = (long long)flu.size();
         for (size_t n = 0; n < flu.size(); n++) cmap[(size_t)flu[n]] = (int)n;
         for (size_t n = 0; n < passive.size(); n++) {
@@ -737,32 +757,49 @@ struct Solver {
 
     // persistent grid of the collide kernels: CTAS resident CTAs per SM.  MFLBM_MAX_CTAS caps it (tests: a small lattice
     // then walks many tiles per CTA, so the stage rings wrap as they do at full size)
-    int collide_grid(int ntiles, int ctas) const { return std::max(1, std::min(ntiles, max_ctas > 0 ? std::min(max_ctas, num_sms * ctas) : num_sms * ctas)); }
+    int collide_grid(int ntiles, int ctas) const {
+        const int sms = std::max(1, num_sms - tile_reserve_sms);
+        return std::max(1, std::min(ntiles, max_ctas > 0 ? std::min(max_ctas, sms * ctas) : sms * ctas));
+    }
+    // tile range of the collide launch being issued (set by phase_collide): [tile_first, tile_end) of the fluid order, and the
+    // SMs its persistent grid leaves free for the halo kernels that run next to it (see step_p2p)
+    int tile_first = 0, tile_end = 0, tile_reserve_sms = 0;
 
     // pipelined kernels (kernels_collide.cuh): persistent CTAs, TMA / cp.async staged PDF rows
     template <int MRT, int NST, int CTAS>
     void launch_even() {
-        const int ntiles = ceil_div((int)n_fluid, COLLIDE_TILE);
         auto kern = k_collide_even_tma<T, MRT, NST, CTAS>;
         constexpr size_t smem = collide_even_smem<T, NST>();
         static thread_local int configured = -1;
         if (configured != device) { MF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = device; }
-        kern<<<collide_grid(ntiles, CTAS), COLLIDE_EVEN_THREADS, smem, stream>>>(collide_lattice(0), ntiles, cn_consistent ? 1 : 0);
+        halo_lane_fits(kern, COLLIDE_EVEN_THREADS * CTAS);
+        kern<<<collide_grid(tile_end - tile_first, CTAS), COLLIDE_EVEN_THREADS, smem, stream>>>(collide_lattice(0), tile_first, tile_end, cn_consistent ? 1 : 0);
     }
     template <int MRT, int NST, int CTAS, int NCONS = 1, int REGS_P = 0, int REGS_C = 0>
     void launch_odd_ws() {
-        const int ntiles = ceil_div((int)n_fluid, COLLIDE_TILE);
         auto kern = k_collide_odd_ws<T, MRT, NST, CTAS, NCONS, REGS_P, REGS_C>;
         constexpr size_t smem = collide_odd_ws_smem<T, NST>();
         static thread_local int configured = -1;
         if (configured != device) { MF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = device; }
-        kern<<<collide_grid(ntiles, CTAS), (NCONS + 1) * COLLIDE_TILE, smem, stream>>>(collide_lattice(1), ntiles, cn_consistent ? 1 : 0);
+        halo_lane_fits(kern, (NCONS + 1) * COLLIDE_TILE * CTAS);
+        kern<<<collide_grid(tile_end - tile_first, CTAS), (NCONS + 1) * COLLIDE_TILE, smem, stream>>>(collide_lattice(1), tile_first, tile_end, cn_consistent ? 1 : 0);
     }
+    // An interior collide launch that overlaps halo kernels (tile_reserve_sms < 0 = "decide here"): when the resident CTAs of
+    // the kernel take (almost) the whole register file of an SM - the single-precision odd kernel: 2 x 256 threads x 128
+    // registers - no halo CTA could start next to them before the launch retires, so a few SMs are kept out of its grid.
+    template <typename K>
+    void halo_lane_fits(K kern, int threads_per_sm) {
+        if (tile_reserve_sms >= 0) return;
+        cudaFuncAttributes a{};
+        MF_CUDA(cudaFuncGetAttributes(&a, kern));
+        tile_reserve_sms = ((long long)a.numRegs * threads_per_sm > 65536 - 128 * 32) ? 4 : 0;
+    }
+
     // Stage counts are sized for the 227 KB of shared memory of an SM.  MFLBM_VARIANT = 100*e + o
     // selects other (even, odd) configurations for tuning runs, for the shipped MRT model only.
     template <int MRT>
     void launch_collide_default(bool odd) {
-        if (!n_fluid) return;
+        if (tile_end <= tile_first) return;
         // MFLBM_VARIANT = 100 * even + odd selects the other configurations that were measured (profiles/README.md); they
         // are only instantiated for the shipped MRT model.  0 = the defaults.  Results are identical whatever the variant.
         bool done = false;
@@ -791,7 +828,13 @@ struct Solver {
         check_launch(); count();
     }
 
-    void phase_collide(int ntime) {
+    // part 0: every tile; 1: the tiles that hold the nodes of the neighbour-facing columns (the first n_boundary entries);
+    // 2: the other tiles, launched while the halo messages of part 1 are on their way
+    void phase_collide(int ntime, int part = 0) {
+        const int ntiles = ceil_div((int)n_fluid, COLLIDE_TILE), nb_tiles = std::min(ntiles, ceil_div((int)n_boundary, COLLIDE_TILE));
+        tile_first = part == 2 ? nb_tiles : 0;
+        tile_end = part == 1 ? nb_tiles : ntiles;
+        tile_reserve_sms = part == 2 ? -1 : 0;
         const bool odd = (ntime % 2) != 0;
         switch (P.mrt) {
             case 1: launch_collide_default<1>(odd); break;
@@ -801,60 +844,88 @@ struct Solver {
         }
     }
 
-    // boundary kernels in the reference's order (:1903-1958 even, :1969-2023 odd)
-    void phase_boundaries(int ntime) {
+    // boundary kernels in the reference's order (:1903-1958 even, :1969-2023 odd).
+    // part 0: everything; 1: the phase-field part (ghost layers of phi, phi_convec); 2: the distribution part.  The parts are
+    // independent (kernels_step.cuh, k_open_z): step() runs part 2 on a second lane next to the gradient chain.
+    void phase_boundaries(int ntime, int part = 0) {
         const bool odd = (ntime % 2) != 0;
+        const bool do_phi = part != 2, do_pdf = part != 1;
         const dim3 b = block2();
         const int lo = plo(), hi = phi_();
         const int ni = hi - lo + 1;
         const dim3 gz(ceil_div(ni, b.x), ceil_div(L.ny, b.y), 1), gy(ceil_div(ni, b.x), ceil_div(L.nz, b.y), 1), ge(ceil_div(ni, b.x), 1, 1);
         if (P.kper) {
-            if (odd) k_periodic_pdf<T, 2, true><<<gz, b, 0, stream>>>(L, lo, hi); else k_periodic_pdf<T, 2, false><<<gz, b, 0, stream>>>(L, lo, hi);
-            k_periodic_phi<T, 2><<<gz, b, 0, stream>>>(L, lo, hi);
-            check_launch(); count(2);
+            if (do_pdf) { if (odd) k_periodic_pdf<T, 2, true><<<gz, b, 0, stream>>>(L, lo, hi); else k_periodic_pdf<T, 2, false><<<gz, b, 0, stream>>>(L, lo, hi); count(); }
+            if (do_phi) { k_periodic_phi<T, 2><<<gz, b, 0, stream>>>(L, lo, hi); count(); }
+            check_launch();
         }
         if (P.jper) {
-            if (odd) k_periodic_pdf<T, 1, true><<<gy, b, 0, stream>>>(L, lo, hi); else k_periodic_pdf<T, 1, false><<<gy, b, 0, stream>>>(L, lo, hi);
-            k_periodic_phi<T, 1><<<gy, b, 0, stream>>>(L, lo, hi);
-            check_launch(); count(2);
+            if (do_pdf) { if (odd) k_periodic_pdf<T, 1, true><<<gy, b, 0, stream>>>(L, lo, hi); else k_periodic_pdf<T, 1, false><<<gy, b, 0, stream>>>(L, lo, hi); count(); }
+            if (do_phi) { k_periodic_phi<T, 1><<<gy, b, 0, stream>>>(L, lo, hi); count(); }
+            check_launch();
         }
         if (P.jper && P.kper) {
             const dim3 be(b.x, 1, 1);
-            if (odd) k_periodic_pdf_edges<T, true><<<ge, be, 0, stream>>>(L, lo, hi); else k_periodic_pdf_edges<T, false><<<ge, be, 0, stream>>>(L, lo, hi);
-            k_periodic_phi<T, 3><<<ge, be, 0, stream>>>(L, lo, hi);
-            check_launch(); count(2);
+            if (do_pdf) { if (odd) k_periodic_pdf_edges<T, true><<<ge, be, 0, stream>>>(L, lo, hi); else k_periodic_pdf_edges<T, false><<<ge, be, 0, stream>>>(L, lo, hi); count(); }
+            if (do_phi) { k_periodic_phi<T, 3><<<ge, be, 0, stream>>>(L, lo, hi); count(); }
+            check_launch();
         }
         const dim3 gp(ceil_div(L.nx, b.x), ceil_div(L.ny, b.y), 1);
         if (open_z()) {
-            // (the inlet and outlet kernels are independent, ~15 us each and latency-bound; running them side by side on two
-            // lanes of the graph was measured and bought nothing: 16 430 vs 16 558 MLUPS, profiles/README.md r02i)
-            if (P.inlet_BC == 1) { if (odd) k_inlet_velocity<T, true><<<gp, b, 0, stream>>>(L, 1, L.nx); else k_inlet_velocity<T, false><<<gp, b, 0, stream>>>(L, 1, L.nx); count(); }
-            else if (P.inlet_BC == 2) { if (odd) k_inlet_pressure<T, true><<<gp, b, 0, stream>>>(L, 1, L.nx); else k_inlet_pressure<T, false><<<gp, b, 0, stream>>>(L, 1, L.nx); count(); }
-            if (P.outlet_BC == 1) { if (odd) k_outlet_convective<T, true><<<gp, b, 0, stream>>>(L, 1, L.nx); else k_outlet_convective<T, false><<<gp, b, 0, stream>>>(L, 1, L.nx); count(); }
-            else if (P.outlet_BC == 2) { if (odd) k_outlet_pressure<T, true><<<gp, b, 0, stream>>>(L, 1, L.nx); else k_outlet_pressure<T, false><<<gp, b, 0, stream>>>(L, 1, L.nx); count(); }
+            // inlet and outlet planes in one launch (k_open_z)
+            const dim3 g2(gp.x, gp.y, 2);
+            const int in = (P.inlet_BC == 1 || P.inlet_BC == 2) ? P.inlet_BC : 0, out = (P.outlet_BC == 1 || P.outlet_BC == 2) ? P.outlet_BC : 0;
+            if (in || out) {
+#define MF_OPEN_Z(I, O)                                                                                                                  \
+                if (in == I && out == O) {                                                                                               \
+                    if (part == 1) k_open_z<T, false, I, O, 1><<<g2, b, 0, stream>>>(L, 1, L.nx);                                        \
+                    else if (part == 2) { if (odd) k_open_z<T, true, I, O, 2><<<g2, b, 0, stream>>>(L, 1, L.nx); else k_open_z<T, false, I, O, 2><<<g2, b, 0, stream>>>(L, 1, L.nx); } \
+                    else { if (odd) k_open_z<T, true, I, O, 0><<<g2, b, 0, stream>>>(L, 1, L.nx); else k_open_z<T, false, I, O, 0><<<g2, b, 0, stream>>>(L, 1, L.nx); } \
+                }
+                MF_OPEN_Z(0, 1) MF_OPEN_Z(0, 2) MF_OPEN_Z(1, 0) MF_OPEN_Z(1, 1) MF_OPEN_Z(1, 2) MF_OPEN_Z(2, 0) MF_OPEN_Z(2, 1) MF_OPEN_Z(2, 2)
+#undef MF_OPEN_Z
+                count();
+            }
             check_launch();
         }
-        if (P.porous_plate_cmd != 0) {
+        if (P.porous_plate_cmd != 0 && do_pdf) {
             if (odd) k_porous_plate<T, true><<<gz, b, 0, stream>>>(L, 1, L.nx, lo, hi); else k_porous_plate<T, false><<<gz, b, 0, stream>>>(L, 1, L.nx, lo, hi);
             check_launch(); count();
         }
     }
 
+    // boundaries + gradient chain of one step on two lanes: phase-field part of the boundary kernels, then their distribution
+    // part (second lane) next to the chain (first lane); joined before anything else is enqueued
+    void boundaries_and_chain(int ntime, bool exchange_phi) {
+        phase_boundaries(ntime, 1);
+        MF_CUDA(cudaEventRecord(ev_bc_fork, stream));
+        MF_CUDA(cudaStreamWaitEvent(bc_stream, ev_bc_fork, 0));
+        std::swap(stream, bc_stream);
+        try { phase_boundaries(ntime, 2); } catch (...) { std::swap(stream, bc_stream); throw; }
+        std::swap(stream, bc_stream);
+        MF_CUDA(cudaEventRecord(ev_bc_join, bc_stream));
+        if (exchange_phi) exchange_p2p(2);
+        gradient_chain(ntime & 1);
+        MF_CUDA(cudaStreamWaitEvent(stream, ev_bc_join, 0));
+    }
+
     void step_phase(int ntime, int phase) {
         if (!have_geometry) MF_FAIL("step before geometry");
-        if (phase == 0) phase_collide(ntime);
+        if (phase == 0) phase_collide(ntime, 0);
         else if (phase == 1) phase_boundaries(ntime);
         else if (phase == 2) gradient_chain(ntime & 1);
         else MF_FAIL("bad phase");
     }
 
     void step(int ntime) {
+        if (!have_geometry) MF_FAIL("step before geometry");
         if (is_slab && (slab.has_left || slab.has_right)) {
             if (!p2p_ready()) MF_FAIL("a slab with neighbours steps through step_phase + halo exchange, or through step/run once halo_p2p_connect has been called for every neighbour");
             step_p2p(ntime);
             return;
         }
-        step_phase(ntime, 0); step_phase(ntime, 1); step_phase(ntime, 2);
+        phase_collide(ntime, 0);
+        boundaries_and_chain(ntime, false);
     }
 
     // nsteps consecutive steps; pairs of steps are replayed from a captured CUDA graph (launch-bound small lattices)
@@ -1006,7 +1077,9 @@ struct Solver {
     }
 
     // unpack message `kind` from my receive buffers; wait = true: spin on my flags until the neighbours' pushes have landed
-    void halo_unpack(int kind, bool wait = false, int sides = 3, cudaStream_t on = nullptr) {
+    // wait: 0 none (the caller moved the message, e.g. NCCL), 1 every CTA of the unpack kernel spins on my flag until the
+    // neighbour's push has landed, 2 a one-CTA wait kernel first (overlapped schedule, see k_halo_wait)
+    void halo_unpack(int kind, int wait = 0, int sides = 3, cudaStream_t on = nullptr) {
         cudaStream_t stream = on ? on : this->stream;
         const bool do_left = slab.has_left && (sides & 1), do_right = slab.has_right && (sides & 2);
         if (!is_slab) MF_FAIL("halo_unpack on a non-slab solver");
@@ -1016,7 +1089,10 @@ struct Solver {
         const dim3 g1(ceil_div(L.NY1, bt), L.NZ1, 10), g4(ceil_div(L.PY, bt), L.PZ);
         auto sync = [&](int side) -> HaloSync {
             if (!wait) return HaloSync{nullptr, nullptr, nullptr, nullptr};
-            return HaloSync{d_flags + kind * 2 + side, nullptr, d_flags + 16 + kind * 2 + side, d_flags + 31};
+            const HaloSync hs{d_flags + kind * 2 + side, nullptr, d_flags + 16 + kind * 2 + side, d_flags + 31};
+            if (wait == 1) return hs;
+            k_halo_wait<<<1, 32, 0, stream>>>(hs); count();
+            return HaloSync{nullptr, nullptr, nullptr, d_flags + 31};
         };
         if (kind == 0) {   // neighbour's real boundary column -> my ghost column
             if (do_left) { k_halo_pdf<T, true, false><<<g1, bt, 0, stream>>>(L, d_recv[0][0], 0, sync(0)); count(); }          // left's column nx (ex=+1) -> ghost 0
@@ -1052,20 +1128,37 @@ struct Solver {
         if (slab.has_left && slab.has_right) {
             MF_CUDA(cudaEventRecord(ev_fork, stream));
             MF_CUDA(cudaStreamWaitEvent(aux_stream, ev_fork, 0));
-            halo_pack(kind, true, 2, aux_stream); halo_unpack(kind, true, 2, aux_stream);
-            halo_pack(kind, true, 1); halo_unpack(kind, true, 1);
+            halo_pack(kind, true, 2, aux_stream); halo_unpack(kind, 1, 2, aux_stream);
+            halo_pack(kind, true, 1); halo_unpack(kind, 1, 1);
             MF_CUDA(cudaEventRecord(ev_join, aux_stream));
             MF_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
         } else {
-            halo_pack(kind, true); halo_unpack(kind, true);
+            halo_pack(kind, true); halo_unpack(kind, 1);
         }
     }
+    // One step of a slab with its halo messages through peer memory.  The nodes of the neighbour-facing columns are the
+    // first entries of the fluid order (finish_geometry): their collide tiles run first, then the PDF message - push into the
+    // neighbours' buffers, wait for theirs, unpack - travels on the second lane while the collide launch of all other tiles
+    // runs on the first.  Safe: in the AA pattern every PDF cell is read and written by ONE node per step; the cells a message
+    // packs are written by boundary-column nodes only, the cells it unpacks into belong to ghost-column nodes (odd step) or
+    // are not touched at all during an even step.  The boundary kernels need both and join the lanes.
     void step_p2p(int ntime) {
-        step_phase(ntime, 0);
-        exchange_p2p((ntime % 2) ? 1 : 0);
-        step_phase(ntime, 1);
-        exchange_p2p(2);
-        step_phase(ntime, 2);
+        if (!have_geometry) MF_FAIL("step before geometry");
+        const int kind = (ntime % 2) ? 1 : 0;
+        if (n_boundary > 0 && n_boundary < n_fluid && !no_overlap) {
+            phase_collide(ntime, 1);
+            MF_CUDA(cudaEventRecord(ev_fork, stream));
+            MF_CUDA(cudaStreamWaitEvent(aux_stream, ev_fork, 0));
+            halo_pack(kind, true, 3, aux_stream);
+            halo_unpack(kind, 2, 3, aux_stream);
+            MF_CUDA(cudaEventRecord(ev_join, aux_stream));
+            phase_collide(ntime, 2);
+            MF_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
+        } else {
+            phase_collide(ntime, 0);
+            exchange_p2p(kind);
+        }
+        boundaries_and_chain(ntime, true);
     }
 
     void* device_ptr(const char* name) {
@@ -1196,7 +1289,7 @@ struct DeviceGuard {
         MF_GUARD({ MF_ENTER(P, REAL); MF_SOLVER(P, REAL)->halo_connect(kind, side, peer_recv, peer_flag); })                                     \
     }                                                                                                                                     \
     extern "C" int mflbm_##P##_halo_push(mflbm_##P##_solver* s, int kind) { MF_GUARD({ MF_ENTER(P, REAL); MF_SOLVER(P, REAL)->halo_pack(kind, true); }) } \
-    extern "C" int mflbm_##P##_halo_unpack_wait(mflbm_##P##_solver* s, int kind) { MF_GUARD({ MF_ENTER(P, REAL); MF_SOLVER(P, REAL)->halo_unpack(kind, true); }) } \
+    extern "C" int mflbm_##P##_halo_unpack_wait(mflbm_##P##_solver* s, int kind) { MF_GUARD({ MF_ENTER(P, REAL); MF_SOLVER(P, REAL)->halo_unpack(kind, 1); }) } \
     extern "C" int mflbm_##P##_step_phase(mflbm_##P##_solver* s, int ntime, int phase) {                                                  \
         MF_GUARD({ MF_ENTER(P, REAL); MF_SOLVER(P, REAL)->step_phase(ntime, phase); })                                                           \
     }                                                                                                                                     \

