@@ -17,6 +17,7 @@
 #include "kernels_chain.cuh"
 #include "kernels_aux.cuh"
 #include "scan.cuh"
+#include "kernels_setup.cuh"
 
 namespace mflbm {
 
@@ -365,104 +366,92 @@ struct Solver {
 
     // ------------------------------------------------------------------------------------------------
     // geometry.  d_wtype: walls_type in the reference's s4 layout; d_sn4: the three s4 normal arrays (device).
-    // Builds node types on the U grid, the site permutation of the PDF slots and the compact lists of every
-    // list-driven kernel.  List construction runs on the host (once per geometry).
+    // Builds node types on the U grid, the site permutation of the PDF slots, the wall-link ranks and the compact lists of
+    // every list-driven kernel - all of it on the device (kernels_setup.cuh: flag, exclusive scan, fill).
     void finish_geometry(const int* d_wtype, T* const d_sn4[3]) {
         k_types_to_u<T><<<dim3(ceil_div(L.PX, 128), L.PY, L.PZ), 128, 0, stream>>>(L, d_wtype, d_types); check_launch(); count();
         dfree(d_phi_old);   // indexed by fluid entry: invalid for a new geometry
-        std::vector<signed char> ty((size_t)PN);
-        MF_CUDA(cudaMemcpyAsync(ty.data(), d_types, (size_t)PN, cudaMemcpyDeviceToHost, stream));
-        MF_CUDA(cudaStreamSynchronize(stream));
-        const int PX = L.PX, PY = L.PY, nx = L.nx, ny = L.ny, nz = L.nz;
-        auto U = [&](int x, int y, int z) { return (x + 3) + PX * ((y + 3) + PY * (z + 3)); };
-        int offq[19];
-        for (int q = 0; q < 19; q++) offq[q] = ex(q) + PX * (ey(q) + PY * ez(q));
-        std::vector<int> cmap((size_t)PN, -1), flu, passive, lphi, mphi, lcn, mcn, ln, shell, lbc, mbc, flu_b, zstart(2 * ((size_t)nz + 2), 0);
-        // planes whose phi the boundary kernels copy into ghost layers (k_chain_pre): inlet_phi reads k = 0, the outlet kernels
-        // k = nz and nz + 1 (kernels_step.cuh), k_periodic_phi the four real layers at each end of a periodic axis
-        const bool oz = open_z();
-        auto copied = [&](int y, int z) {
-            if (oz && (z == 0 || z == nz || z == nz + 1)) return true;
-            if (P.kper && ((z >= 1 && z <= 4) || (z >= nz - 3 && z <= nz))) return true;
-            if (P.jper && ((y >= 1 && y <= 4) || (y >= ny - 3 && y <= ny))) return true;
-            return false;
-        };
-        flu.reserve((size_t)nx * ny * nz / 2);
-        counts[0] = counts[1] = counts[2] = counts[3] = 0;
-        for (int z = -3; z <= nz + 4; z++) {
-            // fluid nodes with z' < z, in two segments of the fluid order: the nodes of the columns that face a neighbour slab
-            // come first (their collide tiles run before the halo messages are packed, the rest overlaps the messages), then
-            // all others; each segment in z,y,x order
-            if (z >= 1 && z <= nz + 1) { zstart[(size_t)z - 1] = (int)flu_b.size(); zstart[(size_t)nz + 2 + z - 1] = (int)flu.size(); }
-            for (int y = -3; y <= ny + 4; y++) for (int x = -3; x <= nx + 4; x++) {
-                const int u = U(x, y, z);
-                const int t = ty[(size_t)u];
-                const bool in3 = x >= -2 && x <= nx + 3 && y >= -2 && y <= ny + 3 && z >= -2 && z <= nz + 3;
-                const bool in2 = x >= -1 && x <= nx + 2 && y >= -1 && y <= ny + 2 && z >= -1 && z <= nz + 2;
-                const bool in1 = x >= 0 && x <= nx + 1 && y >= 0 && y <= ny + 1 && z >= 0 && z <= nz + 1;
-                const bool in0 = x >= 1 && x <= nx && y >= 1 && y <= ny && z >= 1 && z <= nz;
-                if (in1) {
-                    if (t <= 0 && in0) { if ((x == 1 && slab.has_left) || (x == nx && slab.has_right)) flu_b.push_back(u); else flu.push_back(u); }
-                    else passive.push_back(u);
-                }
-                if (t <= 0 && !in0 && brick_chain) shell.push_back(u);   // k_act_shell: phi there is written by boundary kernels and halos
-                if (t <= 0 && in2 && !brick_chain) ln.push_back(u);      // k_normals: non-solid sites of [-1..n+2]^3 (:760-764)
-                if (t == 2) {
-                    counts[0]++;
-                    if (in3) {                                           // :737 [-2..n+3]; :885 [0..n+1]
-                        counts[2]++;
-                        int m = 0;
-                        for (int q = 1; q < 19; q++) if (ty[(size_t)(u + offq[q])] <= 0) m |= 1 << (q - 1);
-                        lphi.push_back(u); mphi.push_back(m);
-                        if (brick_chain && copied(y, z)) { lbc.push_back(u); mbc.push_back(m); }
-                        if (in1 && !brick_chain) { lcn.push_back(u); mcn.push_back(m); }
-                    }
-                } else if (t == -1) {
-                    counts[1]++; if (in3) counts[3]++;
-                }
-            }
-        }
-        zstart[(size_t)nz + 1] = (int)flu_b.size(); zstart[2 * (size_t)nz + 3] = (int)flu.size();
-        n_boundary = (long long)flu_b.size();
-        for (size_t k = (size_t)nz + 2; k < zstart.size(); k++) zstart[k] += (int)n_boundary;   // the second segment starts behind the first
-        flu.insert(flu.begin(), flu_b.begin(), flu_b.end());
-        n_fluid = (long long)flu.size();
-        for (size_t n = 0; n < flu.size(); n++) cmap[(size_t)flu[n]] = (int)n;
-        for (size_t n = 0; n < passive.size(); n++) {
-            const int e = (int)(flu.size() + n);
-            // solid-type sites are marked (Lattice::f) - except in a ghost column that mirrors a neighbour slab: links that
-            // end there stay in slot storage, which is what the halo messages carry
-            const int px = passive[n] % PX - 3;
-            const bool halo_col = (px == 0 && slab.has_left) || (px == nx + 1 && slab.has_right);
-            cmap[(size_t)passive[n]] = (ty[(size_t)passive[n]] > 0 && !halo_col) ? -(e + 2) : e;
-        }
-        // wall links: rank of every link inside its direction, per 32-entry group (core.cuh)
-        std::vector<int> wbase(((flu.size() + 31) / 32) * 18 + 18, 0);
-        long long cnt[19] = {0};
-        for (size_t n = 0; n < flu.size(); n++) {
-            if ((n & 31) == 0) for (int q = 1; q < 19; q++) wbase[(n >> 5) * 18 + (q - 1)] = (int)cnt[q];
-            for (int q = 1; q < 19; q++) if (cmap[(size_t)(flu[n] + offq[q])] < -1) cnt[q]++;
-        }
-        n_links = 0;
-        long long max_links = 0;
-        for (int q = 1; q < 19; q++) { n_links += cnt[q]; max_links = std::max(max_links, cnt[q]); }
-        // slot = [fluid nodes | other sites of the 1-ghost box | pad to whole 128-entry tiles (+1: the TMA row copies of the
-        // last fluid tile stay inside the slot) | mailboxes of the one link direction the slot hosts]
-        const long long mb0 = 128 * ((N1 + 127) / 128) + 128;
-        NC = mb0 + 128 * ((max_links + 127) / 128);
-        if (NC >= (1LL << 31) - 2) MF_FAIL("PDF slot exceeds 2^31 entries; decompose into more slabs");
-        L.mb0 = (int)mb0; L.NC = NC;
-        dfree(d_pdf);
-        zalloc((void**)&d_pdf, sizeof(T) * NC * 38);
-        L.pdf = d_pdf;
-        auto up = [&](int*& d, const std::vector<int>& v) {
-            dfree(d);
-            MF_CUDA(cudaMalloc((void**)&d, sizeof(int) * std::max<size_t>(v.size(), 1)));
-            if (!v.empty()) MF_CUDA(cudaMemcpyAsync(d, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice, stream));
-        };
-        up(d_wbase, wbase); L.wbase = d_wbase;
-        up(d_flu, flu); up(d_list_phi, lphi); up(d_mask_phi, mphi); up(d_list_cn, lcn); up(d_mask_cn, mcn); up(d_list_n, ln); up(d_shell, shell); up(d_bc_list, lbc); up(d_bc_mask, mbc);
-        n_list_phi = (int)lphi.size(); n_list_cn = (int)lcn.size(); n_list_n = (int)ln.size(); n_shell = (int)shell.size(); n_bc = (int)lbc.size();
+        const SetupInfo SI{slab.has_left, slab.has_right, open_z() ? 1 : 0, P.kper, P.jper};
+        const dim3 gu(ceil_div(L.PX, 128), L.PY, L.PZ);
+        int *d_pred = nullptr, *d_scan[3] = {nullptr, nullptr, nullptr};
+        unsigned long long* d_counts = nullptr;
+        int* d_links = nullptr;
+        auto cleanup = [&]() { cudaFree(d_pred); for (auto q : d_scan) cudaFree(q); cudaFree(d_counts); cudaFree(d_links); };
+        try {
+            MF_CUDA(cudaMalloc((void**)&d_pred, sizeof(int) * (size_t)(PN + 1)));
+            for (auto& q : d_scan) MF_CUDA(cudaMalloc((void**)&q, sizeof(int) * (size_t)(PN + 1)));
+            MF_CUDA(cudaMemsetAsync(d_pred + PN, 0, sizeof(int), stream));
+            // number of sites that satisfy `kind`, their ranks in d_scan[slot]
+            auto rank = [&](int kind, int slot) -> long long {
+                k_setup_flags<T><<<gu, 128, 0, stream>>>(L, SI, kind, d_pred); check_launch(); count();
+                long long total = 0;
+                MF_CUDA(exclusive_scan(d_pred, d_scan[slot], PN + 1, stream, &total));
+                return total;
+            };
+            // ---- site permutation: [fluid nodes of neighbour-facing columns | other fluid nodes | other sites of the 1-ghost box]
+            n_boundary = rank(P_FLUID_B, 0);
+            const long long n_interior = rank(P_FLUID_I, 1);
+            const long long n_passive = rank(P_PASSIVE, 2);
+            n_fluid = n_boundary + n_interior;
+            if (n_fluid + n_passive != N1) MF_FAIL("internal error: site permutation covers %lld of %lld sites", n_fluid + n_passive, N1);
+            dfree(d_flu);
+            MF_CUDA(cudaMalloc((void**)&d_flu, sizeof(int) * (size_t)std::max<long long>(n_fluid, 1)));
+            k_setup_site_map<T><<<gu, 128, 0, stream>>>(L, SI, d_scan[0], d_scan[1], d_scan[2], (int)n_boundary, (int)n_fluid, d_cmap, d_flu); check_launch(); count();
+            k_setup_zstart<T><<<ceil_div(L.nz + 2, 128), 128, 0, stream>>>(L, d_scan[0], d_scan[1], (int)n_boundary, d_zstart); check_launch(); count();
+            L.n_fluid = (int)n_fluid; L.fl_u = d_flu;
+            // ---- wall links: rank of every link inside its direction, per 32-entry group (core.cuh)
+            const int ngrp = ceil_div((int)n_fluid, 32), nrows = ceil_div((int)n_fluid, COLLIDE_TILE) * (COLLIDE_TILE / 32) + 1;
+            long long link_tot[19] = {0};
+            dfree(d_wbase);
+            MF_CUDA(cudaMalloc((void**)&d_wbase, sizeof(int) * (size_t)nrows * 18));
+            if (ngrp) {
+                MF_CUDA(cudaMalloc((void**)&d_links, sizeof(int) * ((size_t)ngrp * 18 + 1)));
+                MF_CUDA(cudaMemsetAsync(d_links + (size_t)ngrp * 18, 0, sizeof(int), stream));
+                k_setup_link_count<T><<<ceil_div(ngrp, 4), 128, 0, stream>>>(L, ngrp, d_links); check_launch(); count();
+                long long total = 0;
+                MF_CUDA(exclusive_scan(d_links, d_links, (long long)ngrp * 18 + 1, stream, &total));
+                k_setup_wbase<<<ceil_div(nrows * 18, 128), 128, 0, stream>>>(d_links, ngrp, nrows, d_wbase); check_launch(); count();
+                std::vector<int> ends(19);
+                for (int q = 0; q <= 18; q++) MF_CUDA(cudaMemcpyAsync(&ends[(size_t)q], d_links + (size_t)q * ngrp, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                MF_CUDA(cudaStreamSynchronize(stream));
+                for (int q = 1; q <= 18; q++) link_tot[q] = ends[(size_t)q] - ends[(size_t)q - 1];
+            } else MF_CUDA(cudaMemsetAsync(d_wbase, 0, sizeof(int) * (size_t)nrows * 18, stream));
+            L.wbase = d_wbase;
+            n_links = 0;
+            long long max_links = 0;
+            for (int q = 1; q < 19; q++) { n_links += link_tot[q]; max_links = std::max(max_links, link_tot[q]); }
+            // slot = [fluid nodes | other sites of the 1-ghost box | pad to whole 128-entry tiles (+1: the TMA row copies of the
+            // last fluid tile stay inside the slot) | mailboxes of the one link direction the slot hosts]
+            const long long mb0 = 128 * ((N1 + 127) / 128) + 128;
+            NC = mb0 + 128 * ((max_links + 127) / 128);
+            if (NC >= (1LL << 31) - 2) MF_FAIL("PDF slot exceeds 2^31 entries; decompose into more slabs");
+            L.mb0 = (int)mb0; L.NC = NC;
+            dfree(d_pdf);
+            zalloc((void**)&d_pdf, sizeof(T) * NC * 38);
+            L.pdf = d_pdf;
+            // ---- compact site lists
+            auto make_list = [&](int kind, int*& d_list, int** d_mask) -> int {
+                const long long n = rank(kind, 0);
+                dfree(d_list);
+                MF_CUDA(cudaMalloc((void**)&d_list, sizeof(int) * (size_t)std::max<long long>(n, 1)));
+                if (d_mask) { dfree(*d_mask); MF_CUDA(cudaMalloc((void**)d_mask, sizeof(int) * (size_t)std::max<long long>(n, 1))); }
+                if (n) { k_setup_fill<T><<<gu, 128, 0, stream>>>(L, SI, kind, d_scan[0], d_list, d_mask ? *d_mask : nullptr); check_launch(); count(); }
+                return (int)n;
+            };
+            n_list_phi = make_list(P_PHI, d_list_phi, &d_mask_phi);
+            n_list_cn = n_list_n = n_shell = n_bc = 0;
+            if (brick_chain) { n_shell = make_list(P_SHELL, d_shell, nullptr); n_bc = make_list(P_COPIED, d_bc_list, &d_bc_mask); }
+            else { n_list_cn = make_list(P_CN, d_list_cn, &d_mask_cn); n_list_n = make_list(P_NORMALS, d_list_n, nullptr); }
+            // ---- counters of the reference's geometry report
+            MF_CUDA(cudaMalloc((void**)&d_counts, 4 * sizeof(unsigned long long)));
+            MF_CUDA(cudaMemsetAsync(d_counts, 0, 4 * sizeof(unsigned long long), stream));
+            k_setup_counts<T><<<gu, 128, 0, stream>>>(L, d_counts); check_launch(); count();
+            unsigned long long hc[4];
+            MF_CUDA(cudaMemcpyAsync(hc, d_counts, sizeof hc, cudaMemcpyDeviceToHost, stream));
+            MF_CUDA(cudaStreamSynchronize(stream));
+            for (int n = 0; n < 4; n++) counts[n] = (long long)hc[n];
+        } catch (...) { cleanup(); throw; }
+        cleanup();
         dfree(d_live_n); dfree(d_live_cn);
         MF_CUDA(cudaMalloc((void**)&d_live_n, std::max(n_list_n, 1))); MF_CUDA(cudaMalloc((void**)&d_live_cn, std::max(n_list_cn, 1)));
         // fluid-boundary sites of the whole U grid (wetting; the kernels check their own range [-1..n+2]^3, :814) and, for the
@@ -492,9 +481,6 @@ struct Solver {
             cudaFree(d_cnt);
         }
         mark_all_live();
-        MF_CUDA(cudaMemcpyAsync(d_cmap, cmap.data(), sizeof(int) * (size_t)PN, cudaMemcpyHostToDevice, stream));
-        MF_CUDA(cudaMemcpyAsync(d_zstart, zstart.data(), sizeof(int) * zstart.size(), cudaMemcpyHostToDevice, stream));
-        L.n_fluid = (int)n_fluid; L.fl_u = d_flu;
         if (brick_chain) {   // bricks touched by every group of 32 fluid entries (kernels_chain.cuh, raise_activity / k_chain_pre)
             n_groups = ceil_div((int)n_fluid, 32);
             dfree(d_grp); dfree(d_grp_start); dfree(d_grp_bricks);
