@@ -179,6 +179,11 @@ MFLBM_DECLARE_API(f64, double)
 int mflbm_ipc_export(void* device_ptr, void* handle64);
 int mflbm_ipc_import(const void* handle64, void** device_ptr);
 int mflbm_ipc_release(void* device_ptr);
+/* x-slabs of one lattice on several devices driven from ONE process (mflbm_run --gpus N, host/domain.hpp): enables peer
+ * access between two devices in both directions, after which the pointers of halo_p2p_local can be passed to the
+ * neighbour's halo_p2p_connect as they are.  New (the reference is single-GPU, README.md:119). */
+int mflbm_peer_enable(int device_a, int device_b);
+
 const char* mflbm_last_error(void);
 int mflbm_version(void);
 

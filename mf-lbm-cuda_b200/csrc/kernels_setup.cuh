@@ -135,13 +135,15 @@ __global__ void k_setup_wbase(const int* __restrict__ scan, const int n_groups, 
 }
 
 // counters of the reference's geometry report (src/Geometry_preprocessing.cpp:389-401): solid- and fluid-boundary nodes over
-// the whole 4-ghost grid ("global") and over [-2 .. n+3]^3
+// the whole 4-ghost grid ("global") and over [-2 .. n+3]^3.  An x-slab counts the columns it owns (its real columns, plus
+// the lattice's own ghost columns on a side without a neighbour), so that the slabs' counters add up to the lattice's.
 template <typename T>
-__global__ void __launch_bounds__(128) k_setup_counts(const Lattice<T> L, unsigned long long* __restrict__ counts) {
+__global__ void __launch_bounds__(128) k_setup_counts(const Lattice<T> L, const SetupInfo A, unsigned long long* __restrict__ counts) {
     const int X = (int)(blockIdx.x * blockDim.x + threadIdx.x), Y = (int)blockIdx.y, Z = (int)blockIdx.z;
     int t = 0;
     bool in3 = false;
-    if (X < L.nx + 8) {   // the padding cells of a U row are not lattice sites
+    const int xlo = A.has_left ? 1 : -3, xhi = A.has_right ? L.nx : L.nx + 4;
+    if (X - 3 >= xlo && X - 3 <= xhi) {   // (the padding cells of a U row are not lattice sites)
         t = L.types[X + L.PX * (Y + L.PY * Z)];
         const int x = X - 3, y = Y - 3, z = Z - 3;
         in3 = x >= -2 && x <= L.nx + 3 && y >= -2 && y <= L.ny + 3 && z >= -2 && z <= L.nz + 3;

@@ -445,7 +445,7 @@ struct Solver {
             // ---- counters of the reference's geometry report
             MF_CUDA(cudaMalloc((void**)&d_counts, 4 * sizeof(unsigned long long)));
             MF_CUDA(cudaMemsetAsync(d_counts, 0, 4 * sizeof(unsigned long long), stream));
-            k_setup_counts<T><<<gu, 128, 0, stream>>>(L, d_counts); check_launch(); count();
+            k_setup_counts<T><<<gu, 128, 0, stream>>>(L, SI, d_counts); check_launch(); count();
             unsigned long long hc[4];
             MF_CUDA(cudaMemcpyAsync(hc, d_counts, sizeof hc, cudaMemcpyDeviceToHost, stream));
             MF_CUDA(cudaStreamSynchronize(stream));
@@ -1308,6 +1308,26 @@ extern "C" int mflbm_ipc_import(const void* handle64, void** device_ptr) {
     })
 }
 extern "C" int mflbm_ipc_release(void* device_ptr) { MF_GUARD({ if (device_ptr) MF_CUDA(cudaIpcCloseMemHandle(device_ptr)); }) }
+
+// x-slabs of one lattice on several devices driven from ONE process (mflbm_run --gpus N): peer access both ways, so that the
+// pointers returned by halo_p2p_local can be handed to halo_p2p_connect of the neighbour as they are
+static void peer_enable(int device_a, int device_b) {
+    if (device_a == device_b) return;
+    int prev = 0, ok_ab = 0, ok_ba = 0;
+    MF_CUDA(cudaGetDevice(&prev));
+    MF_CUDA(cudaDeviceCanAccessPeer(&ok_ab, device_a, device_b));
+    MF_CUDA(cudaDeviceCanAccessPeer(&ok_ba, device_b, device_a));
+    if (!ok_ab || !ok_ba) MF_FAIL("devices %d and %d cannot access each other's memory", device_a, device_b);
+    for (int k = 0; k < 2; k++) {
+        const int from = k ? device_b : device_a, to = k ? device_a : device_b;
+        MF_CUDA(cudaSetDevice(from));
+        const cudaError_t e = cudaDeviceEnablePeerAccess(to, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (e != cudaSuccess) { cudaSetDevice(prev); MF_CUDA(e); }
+    }
+    MF_CUDA(cudaSetDevice(prev));
+}
+extern "C" int mflbm_peer_enable(int device_a, int device_b) { MF_GUARD(peer_enable(device_a, device_b)) }
 
 extern "C" const char* mflbm_last_error(void) { return g_last_error.c_str(); }
 extern "C" int mflbm_version(void) { return MFLBM_VERSION; }

@@ -19,6 +19,17 @@ template <typename T> struct Api;
         using Handle = mflbm_##P##_solver;                                                                                          \
         static constexpr const char* name = #P;                                                                                     \
         static void create(const Params& p, int device, Handle** h) { api_check(mflbm_##P##_create(&p, nullptr, device, nullptr, h), "create"); } \
+        static void create_slab(const Params& p, const mflbm_slab& s, int device, Handle** h) {                                     \
+            api_check(mflbm_##P##_create(&p, &s, device, nullptr, h), "create (slab)");                                             \
+        }                                                                                                                           \
+        /* my message of `kind` through `side` lands in the neighbour's buffer of side `nside` */                                  \
+        static void connect(Handle* me, int kind, int side, Handle* neighbour, int nside) {                                         \
+            REAL* recv = nullptr; uint32_t* flag = nullptr;                                                                         \
+            api_check(mflbm_##P##_halo_p2p_local(neighbour, kind, nside, &recv, &flag), "halo_p2p_local");                          \
+            api_check(mflbm_##P##_halo_p2p_connect(me, kind, side, recv, flag), "halo_p2p_connect");                                \
+        }                                                                                                                           \
+        static void halo_push(Handle* h, int kind) { api_check(mflbm_##P##_halo_push(h, kind), "halo_push"); }                      \
+        static void halo_unpack_wait(Handle* h, int kind) { api_check(mflbm_##P##_halo_unpack_wait(h, kind), "halo_unpack_wait"); } \
         static void destroy(Handle* h) { mflbm_##P##_destroy(h); }                                                                  \
         static void set_params(Handle* h, const Params& p) { api_check(mflbm_##P##_set_params(h, &p), "set_params"); }              \
         static void preprocess_geometry(Handle* h, const int8_t* w) { api_check(mflbm_##P##_preprocess_geometry(h, w), "preprocess_geometry"); } \

@@ -10,6 +10,8 @@
 //   * the time loop hands the GPU whole batches of steps up to the next output event (monitor / VTK / timer /
 //     checkpoint step) instead of synchronising eight times per step (src/main_iteration_GPU.cu:1903-2055), and the state
 //     only crosses PCIe when a checkpoint or a VTK file is written: the monitor reductions run on the device;
+//   * --gpus N (or --devices a,b,..) cuts the lattice into N x-slabs, one per GPU of the box (host/domain.hpp); every file
+//     is written in the reference's single-domain format whatever the decomposition;
 //   * geometry_preprocess_cmd 1 (unimplemented in the reference too, src/Geometry_preprocessing.cpp:426) is rejected.
 #include <chrono>
 #include <cmath>
@@ -20,6 +22,7 @@
 #include <memory>
 
 #include "api.hpp"
+#include "domain.hpp"
 #include "case.hpp"
 #include "control.hpp"
 #include "output.hpp"
@@ -32,6 +35,7 @@ struct Options {
     std::string dir = ".";
     std::string prec = "f64";
     int device = 0;
+    std::vector<int> devices;   // --gpus N / --devices a,b,...: x-slabs over several GPUs of the box (host/domain.hpp)
     int mrt = 2;             // includes/preprocessor.h:4
     bool quirk = true;       // swapped-stride geometry read, src/Misc.cpp:171
     bool check_input = false;
@@ -41,7 +45,6 @@ template <typename T>
 class Run {
   public:
     explicit Run(const Options& o) : opt(o) {}
-    ~Run() { if (h) Api<T>::destroy(h); }
 
     int main() {
         std::cout << "Solver precision: " << (sizeof(T) == 4 ? "Single" : "Double") << " precision" << std::endl;
@@ -64,12 +67,13 @@ class Run {
 
         typename Api<T>::Params P;
         cs.fill_params(P, opt.mrt);
-        Api<T>::create(P, opt.device, &h);
+        h.create(P, opt.devices.empty() ? std::vector<int>{opt.device} : opt.devices);
+        if (h.slabs() > 1) std::cout << "Lattice cut into " << h.slabs() << " x-slabs, one per GPU" << std::endl;
         std::cout << "------ Start processing boundary nodes info ------" << std::endl;
         auto t0 = Clock::now();
-        Api<T>::preprocess_geometry(h, cs.walls.data());
+        h.preprocess_geometry(cs.walls.data());
         int64_t counts[4];
-        Api<T>::geometry_counts(h, counts);
+        h.geometry_counts(counts);
         std::cout << "Total number of solid boundary nodes = " << counts[0] << std::endl << "Total number of fluid boundary nodes = " << counts[1] << std::endl;
         std::cout << "------ End processing boundary nodes info -------- (" << seconds_since(t0) << " s on the device)" << std::endl;
         write_info(counts);
@@ -79,9 +83,9 @@ class Run {
                 throw Fatal("Input parameter initial_fluid_distribution_option error! Stop program!!!");
             cs.ntime0 = 1;
             const T* W = cs.W_in.empty() ? nullptr : cs.W_in.data();
-            if (c.initial_fluid_distribution_option == 6) { const std::vector<T> phi = random_phi(); Api<T>::init_state_from_phi(h, phi.data(), W); }
-            else Api<T>::init_state(h, c.initial_fluid_distribution_option, c.interface_z0, W);
-            if (c.steady_state_option == 2) Api<T>::phi_change(h, 1, nullptr);   // phi_old = phi, src/Init_multiphase.cpp:381-391
+            if (c.initial_fluid_distribution_option == 6) { const std::vector<T> phi = random_phi(); h.init_state_from_phi(phi.data(), W); }
+            else h.init_state(c.initial_fluid_distribution_option, c.interface_z0, W);
+            if (c.steady_state_option == 2) h.phi_change(1, nullptr);   // phi_old = phi, src/Init_multiphase.cpp:381-391
         } else {
             load_checkpoint(P);
         }
@@ -100,7 +104,7 @@ class Run {
         } else if (c.open_z() && c.inlet_BC == 2 && c.rho_in_new) {   // new pressure BC value overrides the loaded one, src/main.cpp:123-135
             cs.pressure_inlet();
             cs.fill_params(P, opt.mrt);
-            Api<T>::set_params(h, P);
+            h.set_params(P);
         }
         std::cout << "Initial saturation: " << T(m.saturation_full_domain) << std::endl;
         loop();
@@ -112,7 +116,7 @@ class Run {
   private:
     Options opt;
     Case<T> cs;
-    typename Api<T>::Handle* h = nullptr;
+    Domain<T> h;
     int ntime = 0, end_indicator = 0;
     T monitor_previous = 0, monitor_current = 0;
     std::vector<double> prof[7];   // fl1, fl2, pre, mass1, mass2, vol1, vol2 per z slice
@@ -167,7 +171,7 @@ class Run {
     void change_inlet_fluid_phase() {
         const long long NX1 = cs.nx() + 2, NY1 = cs.ny() + 2, n1 = N(1);
         std::vector<T> pdf((size_t)(38 * n1));
-        Api<T>::download(h, pdf.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        h.download(pdf.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
         const int to = cs.ctl.change_inlet_fluid_phase_cmd == 1 ? 0 : 1, from = 1 - to;
         if (cs.ctl.change_inlet_fluid_phase_cmd == 1 || cs.ctl.change_inlet_fluid_phase_cmd == 2)
             for (long long k = 0; k <= cs.nz() + 1; k++) {
@@ -180,7 +184,7 @@ class Run {
                             pdf[(size_t)(q + 19 * from) * n1 + cell] = T(0.);
                         }
             }
-        Api<T>::upload_pdf(h, pdf.data());
+        h.upload_pdf(pdf.data());
     }
 
     // results/out1.output/info.txt, src/Init_multiphase.cpp:128-165
@@ -210,11 +214,11 @@ class Run {
         cs.ntime0 = ck.ntime_next - 1;   // the last step index is executed again, like the reference does
         cs.force_z = ck.force_z; cs.rho_in = ck.rho_in;
         cs.fill_params(P, opt.mrt);
-        Api<T>::set_params(h, P);
-        Api<T>::upload_restart(h, ck.pdf.data(), ck.phi.data(), cs.W_in.empty() ? nullptr : cs.W_in.data(),
+        h.set_params(P);
+        h.upload_restart(ck.pdf.data(), ck.phi.data(), cs.W_in.empty() ? nullptr : cs.W_in.data(),
                                convective() ? ck.f_convec.data() : nullptr, convective() ? ck.g_convec.data() : nullptr,
                                convective() ? ck.phi_convec.data() : nullptr);
-        Api<T>::color_gradient(h);
+        h.color_gradient();
         std::cout << "Complete" << std::endl;
     }
 
@@ -225,7 +229,7 @@ class Run {
         ck.ntime_next = ntime + 1; ck.force_z = cs.force_z; ck.rho_in = cs.rho_in;
         ck.pdf.resize((size_t)(38 * N(1))); ck.phi.resize((size_t)N(4));
         if (convective()) { ck.f_convec.resize((size_t)(19 * NP())); ck.g_convec.resize((size_t)(19 * NP())); ck.phi_convec.resize((size_t)NP()); }
-        Api<T>::download(h, ck.pdf.data(), ck.phi.data(), nullptr, nullptr, nullptr, nullptr, convective() ? ck.f_convec.data() : nullptr,
+        h.download(ck.pdf.data(), ck.phi.data(), nullptr, nullptr, nullptr, nullptr, convective() ? ck.f_convec.data() : nullptr,
                          convective() ? ck.g_convec.data() : nullptr, convective() ? ck.phi_convec.data() : nullptr);
         write_checkpoint(checkpoint_path(opt.dir, secondary), ck, convective());
         if (!secondary) { std::cout << "Saving checkpoint data completed!" << std::endl; write_status("continue_simulation"); }
@@ -244,7 +248,7 @@ class Run {
         const long long nx = cs.nx(), ny = cs.ny(), nz = cs.nz();
         std::vector<T> phi((size_t)N(4));
         if (type == 2) {
-            Api<T>::download(h, nullptr, phi.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+            h.download(nullptr, phi.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
             std::vector<float> f4;
             crop(phi, 4, nx, ny, nz, f4);
             for (size_t n = 0; n < f4.size(); n++) if (cs.walls[n]) f4[n] = 0.f;   // phi zeroed in solids, :558-566
@@ -254,8 +258,8 @@ class Run {
         }
         const char* fmt = cs.ctl.output_fieldData_precision_cmd == 0 ? "float" : "double";   // declared type; the data is always T
         std::vector<T> a((size_t)N(type == 1 ? 1 : 2)), b(a.size()), c(a.size()), d(a.size());
-        if (type == 1) { Api<T>::download_macro(h, d.data(), a.data(), b.data(), c.data()); Api<T>::download(h, nullptr, phi.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr); }
-        else Api<T>::download(h, nullptr, phi.data(), a.data(), b.data(), c.data(), d.data(), nullptr, nullptr, nullptr);
+        if (type == 1) { h.download_macro(d.data(), a.data(), b.data(), c.data()); h.download(nullptr, phi.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr); }
+        else h.download(nullptr, phi.data(), a.data(), b.data(), c.data(), d.data(), nullptr, nullptr, nullptr);
         const int g = type == 1 ? 1 : 2;
         std::vector<T> out;
         VtkFile v(vtk_name(opt.dir, type == 1 ? "full_flow_field/full_flow_field_" : "full_flow_field/force_vector_", nt), nx, ny, nz);
@@ -279,7 +283,7 @@ class Run {
         for (auto& p : prof) p.assign((size_t)cs.nz(), 0.0);
         m.fl1 = prof[0].data(); m.fl2 = prof[1].data(); m.pre = prof[2].data(); m.mass1 = prof[3].data(); m.mass2 = prof[4].data();
         m.vol1 = prof[5].data(); m.vol2 = prof[6].data();
-        Api<T>::monitor(h, &m);
+        h.monitor(&m);
     }
 
     bool fresh_file() const { return cs.ntime0 == 1 && ntime == cs.ntime_monitor; }
@@ -360,7 +364,7 @@ class Run {
         mflbm_monitor_out m;
         monitor_raw(m);
         double d = 0.0;
-        Api<T>::phi_change(h, 0, &d);
+        h.phi_change(0, &d);
         if (ntime <= 0) return;
         if (std::isnan(m.umax) || std::isnan(d) || m.nan_detected) { std::cout << "Simulation failed due to NAN!" << std::endl; end_indicator = 3; return; }
         RowFile(opt.dir, "steady_monitor_max_phi_change.dat", fresh_file()) << ntime << " " << T(d) << " " << T(m.umax) << "\n";
@@ -394,11 +398,11 @@ class Run {
         ntime = cs.ntime0;
         while (ntime <= last) {
             const int e = next_event(ntime, last);
-            Api<T>::run(h, ntime, e - ntime + 1);
+            h.run(ntime, e - ntime + 1);
             since_display += e - ntime + 1;
             ntime = e;
             const bool any = due(e, c.ntime_clock_sum) || due(e, cs.ntime_monitor) || due(e, c.ntime_display_steps) || due(e, cs.ntime_animation) || due(e, cs.ntime_visual);
-            if (any) Api<T>::sync(h);
+            if (any) h.sync();
             if (due(e, c.ntime_clock_sum)) {
                 std::ofstream f((opt.dir + "/results/out1.output/time.dat").c_str(), (cs.ntime0 == 1 && e == c.ntime_clock_sum) ? std::ios_base::out : std::ios_base::app);
                 if (!f.good()) throw Fatal("Could not open results/out1.output/time.dat");
@@ -427,7 +431,7 @@ class Run {
             if (end_indicator > 0) break;
             ntime = e + 1;
         }
-        Api<T>::sync(h);
+        h.sync();
         std::cout << "************************** Exiting main iteration *********************************" << std::endl;
         const double total = seconds_since(t_loop);
         const double speed = double(cs.nx() * cs.ny() * cs.nz()) * double((ntime - cs.ntime0) - 1) / (1e6 * total);
@@ -467,11 +471,13 @@ int main(int argc, char** argv) {
         if (s == "--dir") o.dir = next();
         else if (s == "--prec") o.prec = next();
         else if (s == "--device") o.device = std::stoi(next());
+        else if (s == "--gpus") { const int n = std::stoi(next()); o.devices.clear(); for (int d = 0; d < n; d++) o.devices.push_back(d); }
+        else if (s == "--devices") { std::stringstream ss(next()); std::string tok; o.devices.clear(); while (std::getline(ss, tok, ',')) if (!tok.empty()) o.devices.push_back(std::stoi(tok)); }
         else if (s == "--mrt") o.mrt = std::stoi(next());
         else if (s == "--no-geometry-quirk") o.quirk = false;
         else if (s == "--check-input") o.check_input = true;
         else {
-            std::cerr << "usage: mflbm_run [--dir CASE_DIR] [--prec f32|f64] [--device N] [--mrt 1..4] [--no-geometry-quirk] [--check-input]" << std::endl;
+            std::cerr << "usage: mflbm_run [--dir CASE_DIR] [--prec f32|f64] [--device N | --gpus N | --devices a,b,..] [--mrt 1..4] [--no-geometry-quirk] [--check-input]" << std::endl;
             return s == "--help" || s == "-h" ? 0 : 2;
         }
     }
