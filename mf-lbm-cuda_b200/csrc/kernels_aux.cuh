@@ -190,14 +190,37 @@ __global__ void k_list_s4(const Lattice<T> L, const int* __restrict__ list, cons
     if (GATHER) compact[t] = s4[c4]; else s4[c4] = compact[t];
 }
 
-// one PDF slot: dense 1-ghost array (reference order) <-> internal storage (permuted slot / wall-link mailboxes)
+// one PDF slot: dense 1-ghost array (reference order) <-> internal storage, in two kernels.
+// k_pdf_slot moves every cell between the dense array and SLOT storage (the entry of its site).  The cells of wall links live
+// in mailboxes instead (core.cuh): k_pdf_mail, one thread per fluid entry, moves those - the mailbox entry of a link is the
+// rank the odd collide kernel computes (wbase + ballot / popc), the dense cell is the solid neighbour's.  On the way in the
+// second kernel runs after the first (a mailbox cell also got a harmless copy in the solid site's unused slot storage), on the
+// way out it overwrites what the first kernel read from there.  (A first version resolved mailboxes per SITE through
+// Lattice::f: every solid site next to a fluid node walked its 32-entry group, 3 ms per slot - the state upload was bound by
+// this kernel, not by PCIe.)
 template <typename T, bool TO_SLOT>
-__global__ void k_pdf_slot(const Lattice<T> L, T* __restrict__ dense_s1, const int slot) {
+__global__ void __launch_bounds__(128) k_pdf_slot(const Lattice<T> L, T* __restrict__ dense_s1, const int slot) {
     const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     const int y = (int)blockIdx.y, z = (int)blockIdx.z;
     if (x > L.nx + 1) return;
     const long long c1 = x + (long long)L.NX1 * (y + (long long)L.NY1 * z);
-    T& cell = L.f(slot % 19, slot / 19, L.u(x, y, z));
+    T& cell = L.f_raw(slot % 19, slot / 19, L.u(x, y, z));
+    if (TO_SLOT) cell = dense_s1[c1]; else dense_s1[c1] = cell;
+}
+template <typename T, bool TO_SLOT>
+__global__ void __launch_bounds__(128) k_pdf_mail(const Lattice<T> L, T* __restrict__ dense_s1, const int slot) {
+    const int t = (int)(blockIdx.x * blockDim.x + threadIdx.x), lane = threadIdx.x & 31;
+    const int q = slot % 19, g = slot / 19, o = opc(q);   // the cell (x + e_o, slot q) is the mailbox of link (x, o)
+    const bool live = t < L.n_fluid;
+    const int u = live ? L.fl_u[t] : 0;
+    const int cc = live ? L.cmap[u + L.off(o)] : 0;
+    const unsigned walls = __ballot_sync(0xffffffffu, cc < 0);
+    if (cc >= 0) return;
+    const int entry = L.mb0 + L.wbase[(t >> 5) * 18 + (o - 1)] + __popc(walls & ((1u << lane) - 1u));
+    const unsigned Z = fastdiv((unsigned)u, L.dv_sz), r = (unsigned)u - Z * (unsigned)L.sz, Y = fastdiv(r, L.dv_px), X = r - Y * (unsigned)L.PX;
+    const int x = (int)X - 3 + ex(o), y = (int)Y - 3 + ey(o), z = (int)Z - 3 + ez(o);   // the solid neighbour, reference coordinates
+    const long long c1 = x + (long long)L.NX1 * (y + (long long)L.NY1 * z);
+    T& cell = L.at(q, g, entry);
     if (TO_SLOT) cell = dense_s1[c1]; else dense_s1[c1] = cell;
 }
 

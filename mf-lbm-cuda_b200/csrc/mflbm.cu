@@ -605,7 +605,10 @@ struct Solver {
         if (pdf) {
             const dim3 g = grid_box(1, 128);
             for (int s = 0; s < 38; s++)
-                ring_upload(pdf + (size_t)s * N1, sizeof(T) * N1, [&](void* st) { k_pdf_slot<T, true><<<g, 128, 0, stream>>>(L, (T*)st, s); check_launch(); count(); });
+                ring_upload(pdf + (size_t)s * N1, sizeof(T) * N1, [&](void* st) {
+                    k_pdf_slot<T, true><<<g, 128, 0, stream>>>(L, (T*)st, s); check_launch(); count();
+                    if (s % 19 != 0 && n_fluid) { k_pdf_mail<T, true><<<ceil_div((int)n_fluid, 128), 128, 0, stream>>>(L, (T*)st, s); check_launch(); count(); }
+                });
         }
         if (phi) to_u<T>(phi, d_phi, 4, N4);
         if (cnx) to_u<T>(cnx, d_cnx, 2, N2);
@@ -630,7 +633,10 @@ struct Solver {
         if (pdf) {
             const dim3 g = grid_box(1, 128);
             for (int s = 0; s < 38; s++)
-                ring_download(pdf + (size_t)s * N1, sizeof(T) * N1, [&](void* st) { k_pdf_slot<T, false><<<g, 128, 0, stream>>>(L, (T*)st, s); check_launch(); count(); });
+                ring_download(pdf + (size_t)s * N1, sizeof(T) * N1, [&](void* st) {
+                    k_pdf_slot<T, false><<<g, 128, 0, stream>>>(L, (T*)st, s); check_launch(); count();
+                    if (s % 19 != 0 && n_fluid) { k_pdf_mail<T, false><<<ceil_div((int)n_fluid, 128), 128, 0, stream>>>(L, (T*)st, s); check_launch(); count(); }
+                });
         }
         if (phi) {
             // the brick chain leaves phi at the solid-boundary sites of long-quiet bricks at its last evaluation (kernels_chain.cuh):
