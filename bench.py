@@ -133,8 +133,10 @@ class ClockSampler:
         self.index, self.proc, self.lines = index, None, []
 
     def __enter__(self):
+        if self.index < 0:   # N > 1: rank 0 samples its GPU; 8 nvidia-smi pollers at once stall the driver for everybody
+            return self
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.t.start()
@@ -468,7 +470,7 @@ def bench_slabs(args, rank: int, world: int, local: int) -> dict | None:
         if args.halo == "p2p":
             slab.connect_p2p(dist)
         stepper = sm.SlabStepper(slab, rng)
-        with ClockSampler(local) as clk:
+        with ClockSampler(local if rank == 0 else -1) as clk:
             stepper.run(1, args.warmup)
             nt = 1 + args.warmup
             torch.cuda.synchronize()

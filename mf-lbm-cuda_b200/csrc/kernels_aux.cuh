@@ -476,25 +476,32 @@ __global__ void k_halo_wait(const HaloSync hs) { halo_await(hs); }
 // unpack without a wait of its own: leave the lattice alone once a message has been lost
 __device__ __forceinline__ bool halo_ok(const HaloSync& hs) { return !(hs.error && *reinterpret_cast<volatile unsigned*>(hs.error) != 0u); }
 
-// copy column `col` of the ten slots (PLUS ? ex=+1 : ex=-1) between the lattice and a buffer
-template <typename T, bool PLUS, bool PACK>
-__global__ void k_halo_pdf(const Lattice<T> L, T* __restrict__ buf, const int col, const HaloSync hs) {
-    if (!PACK && !(hs.flag ? halo_await(hs) : halo_ok(hs))) return;
+// slot entries of one x column over the (ny+2) x (nz+2) plane, built once per geometry: a halo kernel then needs no site-map
+// look-up (a scattered 4-byte gather per value before)
+template <typename T>
+__global__ void __launch_bounds__(128) k_setup_face(const Lattice<T> L, const int col, int* __restrict__ face) {
     const int y = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
-    if (y < L.NY1) {
-        const int plane = L.NY1 * L.NZ1;
-        // slot storage proper (f_raw).  Wall links that end in a neighbour-facing ghost column are not mailboxes (Solver::
-        // finish_geometry), so everything a neighbour slab reads or writes lives in slot storage and is exchanged as is; a
-        // solid site of the real boundary column can additionally be the far end of a link of THIS slab's nodes, which keep
-        // that cell in a mailbox the exchange must not touch.
-        const int uu = L.u(col, y, z);
-        // one thread per (slot, y, z): blockIdx.z = 5 * component + n.  (With one thread per site walking its ten slots
-        // the kernel was a chain of dependent look-up -> access pairs, 17-23 us for a 258 x 258 face.)
-        const int g = blockIdx.z / 5, n = blockIdx.z % 5;
+    if (y < L.NY1) face[y + L.NY1 * z] = Lattice<T>::entry_of(L.cmap[L.u(col, y, z)]);
+}
+
+// copy one x column of the ten slots (PLUS ? ex=+1 : ex=-1) between the lattice and a buffer; face = the column's slot entries.
+// Slot storage proper: wall links that end in a neighbour-facing ghost column are not mailboxes (Solver::finish_geometry), so
+// everything a neighbour slab reads or writes lives in slot storage and is exchanged as is; a solid site of the real boundary
+// column can additionally be the far end of a link of THIS slab's nodes, which keep that cell in a mailbox the exchange does
+// not touch.  One thread per (population, y, z): the two components of a population sit side by side (core.cuh), one 8/16-byte
+// access moves both.  blockIdx.y = n, the population's index among the five.
+template <typename T, bool PLUS, bool PACK>
+__global__ void __launch_bounds__(128) k_halo_pdf(const Lattice<T> L, T* __restrict__ buf, const int* __restrict__ face, const HaloSync hs) {
+    if (!PACK && !(hs.flag ? halo_await(hs) : halo_ok(hs))) return;
+    const int plane = L.NY1 * L.NZ1;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x, n = blockIdx.y;
+    if (p < plane) {
         const int q = PLUS ? slot_exp(n) : slot_exm(n);
-        T* cell = &L.f_raw(q, g, uu);
-        T* b = buf + (long long)(g * 5 + n) * plane + (y + L.NY1 * z);
-        if (PACK) *b = *cell; else *cell = __ldcg(b);
+        Pair<T>* cell = L.pairs(q) + face[p];
+        T* b0 = buf + (long long)n * plane + p;
+        T* b1 = buf + (long long)(5 + n) * plane + p;
+        if (PACK) { const Pair<T> v = *cell; *b0 = v.a; *b1 = v.b; }
+        else *cell = Pair<T>{__ldcg(b0), __ldcg(b1)};
     }
     if (PACK) halo_publish(hs);
 }

@@ -115,6 +115,7 @@ struct Solver {
     cudaEvent_t ev_bc_fork = nullptr, ev_bc_join = nullptr;
     cudaStream_t aux_stream = nullptr;          // second lane for the right-hand neighbour's messages (fork/join with events)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int* d_face[4] = {nullptr, nullptr, nullptr, nullptr};   // slot entries of columns 0, 1, nx, nx+1 over the y-z plane (k_halo_pdf)
     unsigned char* d_p2p = nullptr;
     size_t p2p_bytes = 0;
     unsigned* d_flags = nullptr;
@@ -309,6 +310,7 @@ struct Solver {
         dfree(d_live_n); dfree(d_live_cn); dfree(d_near);
         dfree(d_act); dfree(d_quiet); dfree(d_active); dfree(d_n_active); dfree(d_shell); dfree(d_bc_list); dfree(d_bc_mask); dfree(d_alt_start); dfree(d_sb_start); dfree(d_sb_list); dfree(d_sb_mask); dfree(d_grp); dfree(d_grp_start); dfree(d_grp_bricks);
         dfree(d_mon); dfree(d_phi_old); dfree(d_p2p); d_flags = nullptr;
+        for (auto& q : d_face) dfree(q);
         if (d_stage) { cudaFree(d_stage); d_stage = nullptr; }
         ring_drain(true);
         for (int b = 0; b < RING_NB; b++) {
@@ -503,7 +505,15 @@ struct Solver {
             MF_CUDA(cudaMalloc((void**)&d_sn[a], sizeof(T) * std::max(n_list_alter_all, 1)));
             if (n_list_alter_all) { k_list_s4<T, true><<<ceil_div(n_list_alter_all, 128), 128, 0, stream>>>(L, d_list_alter, n_list_alter_all, d_sn4[a], d_sn[a]); check_launch(); count(); }
         }
-        MF_CUDA(cudaStreamSynchronize(stream));   // host vectors go out of scope
+        if (is_slab) {
+            const int cols[4] = {0, 1, L.nx, L.nx + 1};
+            for (int k = 0; k < 4; k++) {
+                dfree(d_face[k]);
+                MF_CUDA(cudaMalloc((void**)&d_face[k], sizeof(int) * (size_t)L.NY1 * L.NZ1));
+                k_setup_face<T><<<dim3(ceil_div(L.NY1, 128), L.NZ1), 128, 0, stream>>>(L, cols[k], d_face[k]); check_launch(); count();
+            }
+        }
+        MF_CUDA(cudaStreamSynchronize(stream));
         have_geometry = true;
         drop_graphs();
     }
@@ -931,14 +941,18 @@ struct Solver {
         if (!cn_consistent && left > 0) { step(nt); nt++; left--; }
         if (left >= 4) {
             const int par = nt & 1;
-            if (!graph_exec[par]) {
+            // both step-pair graphs are built at the first call that needs one (capture does not execute): a later batch that
+            // starts on the other parity - e.g. timed steps after an odd number of warm-up steps - finds its graph ready
+            for (int k = 0; k < 2; k++) {
+                const int pp = par ^ k;
+                if (graph_exec[pp]) continue;
                 const long long l0 = launches;
                 cudaGraph_t g = nullptr;
                 MF_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-                try { step(nt); step(nt + 1); }
+                try { step(nt + k); step(nt + k + 1); }
                 catch (...) { cudaStreamEndCapture(stream, &g); if (g) cudaGraphDestroy(g); throw; }
                 MF_CUDA(cudaStreamEndCapture(stream, &g));
-                MF_CUDA(cudaGraphInstantiate(&graph_exec[par], g, 0));
+                MF_CUDA(cudaGraphInstantiate(&graph_exec[pp], g, 0));
                 MF_CUDA(cudaGraphDestroy(g));
                 pair_launches = launches - l0;
                 launches = l0;   // capture does not execute
@@ -1045,7 +1059,7 @@ struct Solver {
         if (!have_geometry) MF_FAIL("halo_pack before geometry");
         if (kind < 0 || kind > 2) MF_FAIL("bad halo kind");
         const int bt = 128;
-        const dim3 g1(ceil_div(L.NY1, bt), L.NZ1, 10), g4(ceil_div(L.PY, bt), L.PZ);
+        const dim3 g1(ceil_div(L.NY1 * L.NZ1, bt), 5), g4(ceil_div(L.PY, bt), L.PZ);
         auto dst = [&](int side) -> T* {
             if (!push) return d_send[kind][side];
             if (!peer_recv[kind][side] || !peer_flag[kind][side]) MF_FAIL("halo_push: neighbour %d of message kind %d is not connected", side, kind);
@@ -1056,11 +1070,11 @@ struct Solver {
             return HaloSync{peer_flag[kind][side], d_flags + 8 + kind * 2 + side, d_flags + 16 + kind * 2 + side, nullptr};
         };
         if (kind == 0) {   // after an even step: real boundary columns -> neighbour ghost columns
-            if (do_left) { k_halo_pdf<T, false, true><<<g1, bt, 0, stream>>>(L, dst(0), 1, sync(0)); count(); }          // ex=-1 slots of column 1
-            if (do_right) { k_halo_pdf<T, true, true><<<g1, bt, 0, stream>>>(L, dst(1), L.nx, sync(1)); count(); }       // ex=+1 slots of column nx
+            if (do_left) { k_halo_pdf<T, false, true><<<g1, bt, 0, stream>>>(L, dst(0), d_face[1], sync(0)); count(); }      // ex=-1 slots of column 1
+            if (do_right) { k_halo_pdf<T, true, true><<<g1, bt, 0, stream>>>(L, dst(1), d_face[2], sync(1)); count(); }      // ex=+1 slots of column nx
         } else if (kind == 1) {   // after an odd step: what was pushed into my ghost columns -> neighbour real columns
-            if (do_left) { k_halo_pdf<T, true, true><<<g1, bt, 0, stream>>>(L, dst(0), 0, sync(0)); count(); }           // ex=+1 slots of ghost column 0
-            if (do_right) { k_halo_pdf<T, false, true><<<g1, bt, 0, stream>>>(L, dst(1), L.nx + 1, sync(1)); count(); }  // ex=-1 slots of ghost column nx+1
+            if (do_left) { k_halo_pdf<T, true, true><<<g1, bt, 0, stream>>>(L, dst(0), d_face[0], sync(0)); count(); }       // ex=+1 slots of ghost column 0
+            if (do_right) { k_halo_pdf<T, false, true><<<g1, bt, 0, stream>>>(L, dst(1), d_face[3], sync(1)); count(); }     // ex=-1 slots of ghost column nx+1
         } else {
             if (do_left) { k_halo_phi<T, true><<<g4, bt, 0, stream>>>(L, dst(0), 1, sync(0)); count(); }
             if (do_right) { k_halo_phi<T, true><<<g4, bt, 0, stream>>>(L, dst(1), L.nx - 3, sync(1)); count(); }
@@ -1078,7 +1092,7 @@ struct Solver {
         if (!have_geometry) MF_FAIL("halo_unpack before geometry");
         if (kind < 0 || kind > 2) MF_FAIL("bad halo kind");
         const int bt = 128;
-        const dim3 g1(ceil_div(L.NY1, bt), L.NZ1, 10), g4(ceil_div(L.PY, bt), L.PZ);
+        const dim3 g1(ceil_div(L.NY1 * L.NZ1, bt), 5), g4(ceil_div(L.PY, bt), L.PZ);
         auto sync = [&](int side) -> HaloSync {
             if (!wait) return HaloSync{nullptr, nullptr, nullptr, nullptr};
             const HaloSync hs{d_flags + kind * 2 + side, nullptr, d_flags + 16 + kind * 2 + side, d_flags + 31};
@@ -1087,11 +1101,11 @@ struct Solver {
             return HaloSync{nullptr, nullptr, nullptr, d_flags + 31};
         };
         if (kind == 0) {   // neighbour's real boundary column -> my ghost column
-            if (do_left) { k_halo_pdf<T, true, false><<<g1, bt, 0, stream>>>(L, d_recv[0][0], 0, sync(0)); count(); }          // left's column nx (ex=+1) -> ghost 0
-            if (do_right) { k_halo_pdf<T, false, false><<<g1, bt, 0, stream>>>(L, d_recv[0][1], L.nx + 1, sync(1)); count(); } // right's column 1 (ex=-1) -> ghost nx+1
+            if (do_left) { k_halo_pdf<T, true, false><<<g1, bt, 0, stream>>>(L, d_recv[0][0], d_face[0], sync(0)); count(); }     // left's column nx (ex=+1) -> ghost 0
+            if (do_right) { k_halo_pdf<T, false, false><<<g1, bt, 0, stream>>>(L, d_recv[0][1], d_face[3], sync(1)); count(); }   // right's column 1 (ex=-1) -> ghost nx+1
         } else if (kind == 1) {   // neighbour's ghost column -> my real boundary column
-            if (do_left) { k_halo_pdf<T, false, false><<<g1, bt, 0, stream>>>(L, d_recv[1][0], 1, sync(0)); count(); }         // left's ghost nx+1 (ex=-1) -> column 1
-            if (do_right) { k_halo_pdf<T, true, false><<<g1, bt, 0, stream>>>(L, d_recv[1][1], L.nx, sync(1)); count(); }      // right's ghost 0 (ex=+1) -> column nx
+            if (do_left) { k_halo_pdf<T, false, false><<<g1, bt, 0, stream>>>(L, d_recv[1][0], d_face[1], sync(0)); count(); }    // left's ghost nx+1 (ex=-1) -> column 1
+            if (do_right) { k_halo_pdf<T, true, false><<<g1, bt, 0, stream>>>(L, d_recv[1][1], d_face[2], sync(1)); count(); }    // right's ghost 0 (ex=+1) -> column nx
         } else {
             if (do_left) { k_halo_phi<T, false><<<g4, bt, 0, stream>>>(L, d_recv[2][0], -3, sync(0)); count(); }
             if (do_right) { k_halo_phi<T, false><<<g4, bt, 0, stream>>>(L, d_recv[2][1], L.nx + 1, sync(1)); count(); }
