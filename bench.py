@@ -634,7 +634,24 @@ def run_reference(args) -> dict:
     return base
 
 
-def main():
+def resolve_workload(args, world: int = 1) -> None:
+    """fill in the workload defaults: N = 1 -> BASELINE configs[1] (256^3 drainage; the metric is quoted on it), N > 1 -> configs[4]
+    (512^3 per GPU, imbibition, weak scaling); --config strong -> configs[3] (1024 x 512 x 512 drainage with the next seed)"""
+    args.warmup = max(args.warmup, 3)
+    if world > 1 and world != args.gpus:
+        args.gpus = world
+    multi = args.gpus > 1
+    if args.config == "strong":
+        args.global_nx, args.size, args.case, args.seed = 1024, args.size or 512, args.case or "drainage", args.seed + 1
+    elif args.config == "weak":
+        args.size, args.case = args.size or 512, args.case or "imbibition"
+    if not args.size:
+        args.size = 512 if multi else 256
+    if not args.case:
+        args.case = "imbibition" if multi else "drainage"
+
+
+def build_parser() -> argparse.ArgumentParser:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000, help="timed steps (BASELINE configs 2/3: 2 k timed steps after 100 warm-up)")
@@ -660,20 +677,12 @@ def main():
                     help="gradient chain: brick by brick where an interface can be (kernels_chain.cuh, default) or the four list kernels (kernels_step.cuh)")
     ap.add_argument("--geometry", default="pack", choices=["pack", "open"], help="open = empty duct, diagnostic only (not the benchmark workload)")
     ap.add_argument("--ref-block", default="", help="--impl reference: block_Threads_X,Y,Z override (the shipped control file has 128,1,1)")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    if world > 1 and world != args.gpus:
-        args.gpus = world
-    multi = args.gpus > 1
-    if args.config == "strong":
-        args.global_nx, args.size, args.case, args.seed = 1024, args.size or 512, args.case or "drainage", args.seed + 1
-    elif args.config == "weak":
-        args.size, args.case = args.size or 512, args.case or "imbibition"
-    if not args.size:
-        args.size = 512 if multi else 256
-    if not args.case:
-        args.case = "imbibition" if multi else "drainage"
+    return ap
+
+
+def main():
+    args = build_parser().parse_args()
+    resolve_workload(args, int(os.environ.get("WORLD_SIZE", 1)))
     if args.chain is not None:
         os.environ["MFLBM_CHAIN"] = args.chain   # read by the library when a solver is created
     if args.impl == "reference":

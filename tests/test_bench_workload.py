@@ -38,3 +38,26 @@ def test_numpy_inlet_profile_matches_oracle(prec):
         assert np.abs(W - Wo).max() <= 1e-13 * np.abs(Wo).max()   # numpy sums the series pairwise, the reference sequentially
     else:
         assert np.abs(W - Wo).max() <= 2e-5 * np.abs(Wo).max()
+
+
+def test_workload_defaults_follow_the_baseline_configs():
+    """N = 1: BASELINE configs[1] (256^3 drainage); N > 1: configs[4] (512^3 per GPU, imbibition); --config strong: configs[3]"""
+    import bench
+    def resolved(argv, world=1):
+        a = bench.build_parser().parse_args(argv)
+        bench.resolve_workload(a, world)
+        return a
+    a = resolved([])
+    assert (a.gpus, a.size, a.case, a.global_nx, a.prec) == (1, 256, "drainage", 0, "f64")
+    a = resolved(["--steps", "2", "--warmup", "1"])
+    assert a.warmup == 3 and a.steps == 2          # at least three warm-up steps
+    a = resolved(["--gpus", "8"], world=8)
+    assert (a.size, a.case, a.global_nx) == (512, "imbibition", 0)
+    a = resolved(["--gpus", "2", "--impl", "reference"])      # the reference arm of an N-GPU run: one GPU's share of that lattice
+    assert (a.size, a.case) == (512, "imbibition")
+    a = resolved(["--gpus", "4", "--config", "strong"], world=4)
+    assert (a.size, a.case, a.global_nx, a.seed) == (512, "drainage", 1024, 20240230)
+    a = resolved(["--gpus", "4", "--size", "256", "--case", "drainage"], world=4)
+    assert (a.size, a.case) == (256, "drainage")
+    a = resolved([], world=2)                      # launched under torchrun without --gpus
+    assert a.gpus == 2 and a.size == 512
