@@ -619,7 +619,9 @@ def run_reference(args) -> dict:
     base.update({"value": mlups, "ms_per_step": float(tim["ms_per_step"]),
                  "config": {"workload": f"{dims} random sphere pack (radius 12, porosity ~0.4), {args.case}, velocity inlet + convective outlet, theta 45, {prec}",
                             "what": f"reference CUDA kernels (unmodified sources, nvcc sm_100 -O3, block {args.ref_block or '128,1,1 (shipped)'}) via main_iteration_kernel_GPU()",
-                            "host_setup_s": float(host["initialization_basic_multi_s"]), "wall_s": wall},
+                            "host_setup_s": float(host["initialization_basic_multi_s"]), "wall_s": wall,
+                            "note": None if args.gpus <= 1 else f"the reference is single-GPU (README.md:119): at --gpus {args.gpus} this is one GPU's share of our arm's lattice"
+                                    + (" (weak scaling)" if not args.global_nx else " - here the whole strong-scaling lattice on one GPU")},
                  "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": 1, "kind": "reference",
                                   "sample": "the reference has no CPU solver: this is its own CUDA build on 1 B200; 1 host core drives it"},
                  "e2e": {"value": mlups, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
