@@ -399,3 +399,33 @@ def test_driver_on_two_gpus_writes_what_one_gpu_writes(gpu_lib, tmp_path, name, 
             ra, rb = rows(one / rel), rows(two / rel)
             assert ra.shape == rb.shape, rel
             assert np.allclose(ra, rb, rtol=1e-5 if prec == "f64" else 1e-3, atol=1e-9 if prec == "f64" else 1e-5), rel
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_driver_restart_on_two_gpus(gpu_lib, tmp_path, prec):
+    """continue_simulation on two x-slabs from a checkpoint written by a single-GPU run (and the other way round): the windows
+    cut out of the global checkpoint arrays (own + ghost columns, host/domain.hpp) must reproduce the single-GPU continuation
+    byte for byte."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ctl, solid = common.CASES["pack_velocity"]()
+    base = dict(ctl, max_time_step=19, monitor_timer=10, computation_time_timer=20, display_steps_timer=1000, benchmark_cmd=1)
+    nz, ny, nx = solid.shape
+    second = dict(base, max_time_step=40, nxGlobal=nx, nyGlobal=ny, nzGlobal=nz, external_geometry_read_cmd=1)
+    finals = {}
+    for first_gpus in ("1", "2"):
+        first = tmp_path / f"first{first_gpus}"
+        rc.write_case(first, base, solid)
+        run_driver(first, "--prec", prec, "--gpus", first_gpus)
+        for gpus in ("1", "2"):
+            d = tmp_path / f"cont{first_gpus}{gpus}"
+            shutil.copytree(first, d)
+            (d / "input" / "simulation_control.txt").write_text(rc.control_text(second))
+            (d / "input" / "job_status.txt").write_text("continue_simulation")
+            run_driver(d, "--prec", prec, "--gpus", gpus)
+            finals[(first_gpus, gpus)] = (d / "results" / "out2.checkpoint" / "id0000").read_bytes()
+    ref = finals[("1", "1")]
+    for k, v in finals.items():
+        assert v == ref, k
