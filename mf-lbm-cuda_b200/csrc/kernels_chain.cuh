@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 8) k_chain_normals(const Lattic
 // One warp per brick over the brick's entries of a compact list (sites + 18-bit fluid-neighbour masks, built once per
 // geometry): most bricks of an open region hold none, a brick inside the pack a few dozen.
 template <typename T>
-__global__ void __launch_bounds__(CHAIN_THREADS, 16) k_chain_extrap_cn(const Lattice<T> L, const int* __restrict__ active, const int* __restrict__ n_active_ptr,
+__global__ void __launch_bounds__(CHAIN_THREADS, 12) k_chain_extrap_cn(const Lattice<T> L, const int* __restrict__ active, const int* __restrict__ n_active_ptr,
                                                                       const int* __restrict__ sb_start, const int* __restrict__ sb_list, const int* __restrict__ sb_mask) {
     const int lane = threadIdx.x & 31;
     const int n_active = *n_active_ptr;

@@ -743,7 +743,7 @@ struct Solver {
         // the verdict kernel clears the set the next step's collide raises into
         unsigned char* clr = parity < 0 ? nullptr : act_set((parity & 1) ^ 1, 0);
         k_act_verdict<<<ceil_div(nb, bl), bl, 0, stream>>>(bricks, La.act_p, La.act_m, d_quiet, d_active, d_n_active, clr, clr ? clr + nb : nullptr); check_launch(); count();
-        const int grid = std::max(1, std::min(nb, num_sms * 8)), grid_cn = std::max(1, std::min(nb, num_sms * 16));
+        const int grid = std::max(1, std::min(nb, num_sms * 8)), grid_cn = std::max(1, std::min(nb, num_sms * 12));
         BrickNormals<T> SN{d_alt_start, d_sn[0], d_sn[1], d_sn[2]};
         k_chain_normals<T><<<grid, CHAIN_THREADS, 0, stream>>>(L, tm_phi, d_active, d_n_active, SN); check_launch(); count();
         k_chain_extrap_cn<T><<<grid_cn, CHAIN_THREADS, 0, stream>>>(L, d_active, d_n_active, d_sb_start, d_sb_list, d_sb_mask); check_launch(); count();
