@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "api.hpp"
+#include "slabs.hpp"
 
 namespace mfhost {
 
@@ -41,12 +42,8 @@ class Domain {
         for (int a = 0; a + 1 < n; a++)
             if (devices[a] != devices[a + 1]) api_check(mflbm_peer_enable(devices[a], devices[a + 1]), "peer access between neighbouring devices");
         hs.assign((size_t)n, nullptr);
-        const long long base = nxg / n, rem = nxg % n;
-        for (int r = 0; r < n; r++) {   // contiguous, balanced x ranges: the first nx % n slabs get one extra column
-            mflbm_slab s{(int64_t)(1 + r * base + std::min<long long>(r, rem)), (int64_t)(base + (r < rem ? 1 : 0)), r > 0, r < n - 1};
-            cut.push_back(s);
-            Api<T>::create_slab(p, s, devices[r], &hs[(size_t)r]);
-        }
+        cut = cut_slabs(nxg, n);
+        for (int r = 0; r < n; r++) Api<T>::create_slab(p, cut[(size_t)r], devices[r], &hs[(size_t)r]);
     }
     // neighbours' receive buffers and arrival flags: a message sent through my right face lands in my right neighbour's
     // left-side buffer.  After the geometry (the buffers exist from create on, the call order only mirrors mflbm/slab.py).
@@ -178,21 +175,14 @@ class Domain {
         for (auto h : hs) Api<T>::halo_unpack_wait(h, 1);
     }
 
-    // arrays are [outer][rows][x] with x fastest: rows = (ny + 2g) * (z extent), global width nxg + 2g, local width nx_local + 2g;
-    // local column lx holds global column x0 - 1 + lx
+    // arrays are [outer][z][y][x] with x fastest (slabs.hpp)
     void window(const T* global, int g, long long outer, long long zext, int r, std::vector<T>& local) const {
         if (!global) { local.clear(); return; }
-        const long long rows = outer * zext * (ny + 2 * g), wg = nxg + 2 * g, wl = cut[r].nx_local + 2 * g, off = cut[r].x0 - 1;
-        local.resize((size_t)(rows * wl));
-        if (slabs() == 1) { std::memcpy(local.data(), global, sizeof(T) * (size_t)(rows * wl)); return; }
-        for (long long n = 0; n < rows; n++) std::memcpy(&local[(size_t)(n * wl)], global + n * wg + off, sizeof(T) * (size_t)wl);
+        slab_window(global, outer * zext * (ny + 2 * g), g, nxg, cut[(size_t)r], local);
     }
-    // the columns slab r owns: its real columns, plus the lattice's own ghost columns on a side without a neighbour
     void gather(T* global, const std::vector<T>& local, int g, long long outer, long long zext, int r) const {
         if (!global) return;
-        const long long rows = outer * zext * (ny + 2 * g), wg = nxg + 2 * g, wl = cut[r].nx_local + 2 * g, off = cut[r].x0 - 1;
-        const long long lo = cut[r].has_left ? g : 0, hi = cut[r].has_right ? g + cut[r].nx_local : wl;   // local columns [lo, hi)
-        for (long long n = 0; n < rows; n++) std::memcpy(global + n * wg + off + lo, &local[(size_t)(n * wl + lo)], sizeof(T) * (size_t)(hi - lo));
+        slab_gather(global, local.data(), outer * zext * (ny + 2 * g), g, nxg, cut[(size_t)r]);
     }
 };
 

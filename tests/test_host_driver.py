@@ -95,6 +95,14 @@ def test_fatal_inputs_are_fatal(tmp_path):
     assert run_driver(d, "--check-input", check=False).returncode == 1
 
 
+def test_slab_windows_and_owned_columns(tmp_path):
+    """host/slabs.hpp (what mflbm_run --gpus N uploads to / gathers from every slab), compiled and run on the CPU"""
+    exe = tmp_path / "slabs_check"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", str(REPO / "tests" / "host_slabs_check.cpp"), "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and "SLABS_OK" in r.stdout, r.stdout
+
+
 # ----------------------------------------------------------------------------------------------------------
 # GPU: against the reference's stock program
 # ----------------------------------------------------------------------------------------------------------
