@@ -349,7 +349,10 @@ def run_ours(args) -> dict:
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        return bench_slabs(args, rank, world, local)
+        try:
+            return bench_slabs(args, rank, world, local)
+        finally:
+            dist.destroy_process_group()
     S, prec = args.size, args.prec
     NX = args.global_nx or S
     dims = f"{S}^3" if NX == S else f"{NX}x{S}x{S}"
