@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # tuning helper: time the collide kernel configurations (MFLBM_VARIANT = 100*even + odd, mflbm.cu launch_collide_default;
-# +10000 = TMA-tiled normals kernel, +20000 = list kernel) on the benchmark workload.
+# on the benchmark workload (last swept in round 2: profiles/README.md, the defaults are the fastest).
 #   VARIANTS="0 1 2 3 4 100" PRECS="f64" bash profiles/sweep_variants.sh
 for prec in ${PRECS:-f64 f32}; do
   for v in ${VARIANTS:-0 1 2 3 4 100}; do
