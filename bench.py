@@ -295,7 +295,7 @@ def measure_single(args, prec: str, local: int, want_e2e: bool) -> dict:
             solver.sync()
     mon = solver.monitor()
     assert mon["nan_detected"] == 0, "simulation produced non-finite values"
-    chain_bricks = solver.chain_bricks() if solver.chain == "brick" else None
+    chain_bricks = solver.chain_bricks() if solver.chain != "list" else None
     ms_step = ms / args.steps
     traffic = None
     tf = REPO / "profiles" / "traffic.json"
@@ -678,8 +678,8 @@ def build_parser() -> argparse.ArgumentParser:
                     help="N > 1: equal-width x-slabs, or cuts that balance fluid nodes + halo cost per rank (slab.balanced_cuts)")
     ap.add_argument("--halo-cost", type=float, default=10.0,
                     help="--partition balanced: cost of one neighbour per face site, in fluid-node updates (f64 256^2 faces: ~104 us = 10.5)")
-    ap.add_argument("--chain", default=None, choices=["brick", "list"],
-                    help="gradient chain: brick by brick where an interface can be (kernels_chain.cuh, default) or the four list kernels (kernels_step.cuh)")
+    ap.add_argument("--chain", default=None, choices=["brick", "csr", "list"],
+                    help="gradient chain: brick by brick where an interface can be (kernels_chain.cuh; csr = per-brick site lists built once per geometry) or the four list kernels (kernels_step.cuh)")
     ap.add_argument("--geometry", default="pack", choices=["pack", "open"], help="open = empty duct, diagnostic only (not the benchmark workload)")
     ap.add_argument("--ref-block", default="", help="--impl reference: block_Threads_X,Y,Z override (the shipped control file has 128,1,1)")
     return ap

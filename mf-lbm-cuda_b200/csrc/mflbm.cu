@@ -70,10 +70,15 @@ struct Solver {
     // four list kernels of kernels_step.cuh instead, MFLBM_ACT_SCAN=1 takes the brick flags from a scan of phi instead of the
     // collide kernels - both for cross-checks, results are identical)
     bool brick_chain = true, act_scan = false;
+    bool chain_csr = true;               // k_chain_normals_csr (per-brick CSR of the box's solid-boundary sites); MFLBM_CHAIN=brick: k_chain_normals (sites collected per step)
+    int *d_bx_start = nullptr, *d_bx_ent = nullptr;   // solid-boundary sites of the 10 x 6 x 6 box of every brick (k_brick_box_sites)
     BrickGrid bricks{};
     unsigned char* d_act = nullptr;      // [3 sets][P | M][bricks]: sets 0 / 1 are raised by the collide kernel of even / odd steps, set 2 by k_act_scan
     unsigned char* d_quiet = nullptr;    // [bricks] verdict of the previous chain
-    int *d_active = nullptr, *d_n_active = nullptr;   // bricks to process in this chain, their number
+    int *d_active = nullptr, *d_n_active = nullptr;   // bricks to process in this chain; {their number, their cn-extrapolation entries} (one 64-bit counter)
+    unsigned* d_chain_live = nullptr;                 // [bricks][4 warps] bit per site: outputs of k_chain_normals_csr may be non-zero in memory
+    int* d_ent_off = nullptr;                         // [slot] first entry of the listed brick in the flat numbering of k_chain_extrap_cn_flat
+    int n_sb = 0;                                     // entries of d_sb_list
     int *d_shell = nullptr, n_shell = 0;              // non-solid sites outside the real box
     int *d_bc_list = nullptr, *d_bc_mask = nullptr, n_bc = 0;   // solid-boundary sites whose phi a boundary kernel copies (k_chain_pre)
     int* d_alt_start = nullptr;                       // [bricks + 1] first fluid-boundary entry of every brick (d_list_alter, d_sn)
@@ -201,7 +206,7 @@ struct Solver {
         MF_CUDA(cudaSetDevice(device));   // before any stream / event is created: they belong to the current device
         if (const char* v = getenv("MFLBM_VARIANT")) variant = atoi(v);
         if (const char* v = getenv("MFLBM_MAX_CTAS")) max_ctas = atoi(v);
-        if (const char* v = getenv("MFLBM_CHAIN")) brick_chain = strcmp(v, "list") != 0;
+        if (const char* v = getenv("MFLBM_CHAIN")) { brick_chain = strcmp(v, "list") != 0; chain_csr = brick_chain && strcmp(v, "brick") != 0; }
         if (const char* v = getenv("MFLBM_ACT_SCAN")) act_scan = atoi(v) != 0;
         if (const char* v = getenv("MFLBM_NO_OVERLAP")) no_overlap = atoi(v) != 0;
         MF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
@@ -244,7 +249,7 @@ struct Solver {
             make_tile_map(&tm_phi, d_phi, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, sizeof(T));
             const size_t nb = (size_t)bricks.count();
             zalloc((void**)&d_act, 6 * nb); zalloc((void**)&d_quiet, nb);
-            zalloc((void**)&d_active, sizeof(int) * nb); zalloc((void**)&d_n_active, sizeof(int));
+            zalloc((void**)&d_active, sizeof(int) * nb); zalloc((void**)&d_n_active, 2 * sizeof(int)); zalloc((void**)&d_ent_off, sizeof(int) * nb); zalloc((void**)&d_chain_live, sizeof(unsigned) * 4 * nb);
         }
         if (!brick_chain) zalloc((void**)&d_near, PN);
         zalloc((void**)&d_zstart, sizeof(int) * 2 * (L.nz + 2));
@@ -308,7 +313,7 @@ struct Solver {
         dfree(d_list_phi); dfree(d_mask_phi); dfree(d_list_cn); dfree(d_mask_cn); dfree(d_list_alter); dfree(d_list_n);
         for (auto& q : d_sn) dfree(q);
         dfree(d_live_n); dfree(d_live_cn); dfree(d_near);
-        dfree(d_act); dfree(d_quiet); dfree(d_active); dfree(d_n_active); dfree(d_shell); dfree(d_bc_list); dfree(d_bc_mask); dfree(d_alt_start); dfree(d_sb_start); dfree(d_sb_list); dfree(d_sb_mask); dfree(d_grp); dfree(d_grp_start); dfree(d_grp_bricks);
+        dfree(d_act); dfree(d_quiet); dfree(d_active); dfree(d_n_active); dfree(d_ent_off); dfree(d_chain_live); dfree(d_shell); dfree(d_bc_list); dfree(d_bc_mask); dfree(d_alt_start); dfree(d_sb_start); dfree(d_sb_list); dfree(d_sb_mask); dfree(d_grp); dfree(d_grp_start); dfree(d_grp_bricks); dfree(d_bx_start); dfree(d_bx_ent);
         dfree(d_mon); dfree(d_phi_old); dfree(d_p2p); d_flags = nullptr;
         for (auto& q : d_face) dfree(q);
         if (d_stage) { cudaFree(d_stage); d_stage = nullptr; }
@@ -478,7 +483,8 @@ struct Solver {
             try {
                 n_list_alter_all = compact(k_brick_sites<T, 0, 0>, k_brick_sites<T, 0, 1>, d_alt_start, d_list_alter, nullptr);
                 n_list_alter = n_list_alter_all;
-                if (brick_chain) compact(k_brick_sites<T, 1, 0>, k_brick_sites<T, 1, 1>, d_sb_start, d_sb_list, &d_sb_mask);
+                if (brick_chain) n_sb = compact(k_brick_sites<T, 1, 0>, k_brick_sites<T, 1, 1>, d_sb_start, d_sb_list, &d_sb_mask);
+                if (brick_chain && chain_csr) compact(k_brick_box_sites<T, 0>, k_brick_box_sites<T, 1>, d_bx_start, d_bx_ent, nullptr);
             } catch (...) { cudaFree(d_cnt); throw; }
             cudaFree(d_cnt);
         }
@@ -674,6 +680,7 @@ struct Solver {
         if (d_live_n) MF_CUDA(cudaMemsetAsync(d_live_n, 1, std::max(n_list_n, 1), stream));
         if (d_live_cn) MF_CUDA(cudaMemsetAsync(d_live_cn, 1, std::max(n_list_cn, 1), stream));
         if (d_quiet) MF_CUDA(cudaMemsetAsync(d_quiet, 0, (size_t)bricks.count(), stream));   // every brick is processed by the next chain
+        if (d_chain_live) MF_CUDA(cudaMemsetAsync(d_chain_live, 0xff, sizeof(unsigned) * 4 * (size_t)bricks.count(), stream));   // ... and stores every site
     }
 
     bool open_z() const { return P.kper == 0 && P.wall_z_min == 0 && P.wall_z_max == 0; }
@@ -742,11 +749,22 @@ struct Solver {
         }
         // the verdict kernel clears the set the next step's collide raises into
         unsigned char* clr = parity < 0 ? nullptr : act_set((parity & 1) ^ 1, 0);
-        k_act_verdict<<<ceil_div(nb, bl), bl, 0, stream>>>(bricks, La.act_p, La.act_m, d_quiet, d_active, d_n_active, clr, clr ? clr + nb : nullptr); check_launch(); count();
-        const int grid = std::max(1, std::min(nb, num_sms * 8)), grid_cn = std::max(1, std::min(nb, num_sms * 12));
+        // csr chain: the verdict kernel also hands every listed brick its offset in a flat numbering of the cn-extrapolation entries
+        k_act_verdict<<<ceil_div(nb, bl), bl, 0, stream>>>(bricks, La.act_p, La.act_m, d_quiet, d_active, d_n_active, clr, clr ? clr + nb : nullptr, d_sb_start, chain_csr ? d_ent_off : nullptr);
+        check_launch(); count();
         BrickNormals<T> SN{d_alt_start, d_sn[0], d_sn[1], d_sn[2]};
-        k_chain_normals<T><<<grid, CHAIN_THREADS, 0, stream>>>(L, tm_phi, d_active, d_n_active, SN); check_launch(); count();
-        k_chain_extrap_cn<T><<<grid_cn, CHAIN_THREADS, 0, stream>>>(L, d_active, d_n_active, d_sb_start, d_sb_list, d_sb_mask); check_launch(); count();
+        if (chain_csr) {
+            // resident CTAs per SM: the single-precision kernel's 40 registers allow 12, the double-precision one needs 64 (8; with
+            // 10 and 48 registers it spills a dozen words and was measured slower, profiles/r03a_chain_variants.json)
+            constexpr int C = sizeof(T) == 8 ? 8 : 12;
+            k_chain_normals_csr<T, C><<<std::max(1, std::min(nb, num_sms * C)), CHAIN_THREADS, 0, stream>>>(L, tm_phi, d_active, d_n_active, SN, d_bx_start, d_bx_ent, d_chain_live);
+            check_launch(); count();
+            k_chain_extrap_cn_flat<T><<<std::max(1, std::min(ceil_div(n_sb, CHAIN_THREADS), num_sms * 12)), CHAIN_THREADS, 0, stream>>>(L, d_active, d_n_active, d_ent_off, d_sb_start, d_sb_list, d_sb_mask);
+            check_launch(); count();
+        } else {
+            k_chain_normals<T><<<std::max(1, std::min(nb, num_sms * 8)), CHAIN_THREADS, 0, stream>>>(L, tm_phi, d_active, d_n_active, SN); check_launch(); count();
+            k_chain_extrap_cn<T><<<std::max(1, std::min(nb, num_sms * 12)), CHAIN_THREADS, 0, stream>>>(L, d_active, d_n_active, d_sb_start, d_sb_list, d_sb_mask); check_launch(); count();
+        }
         cn_consistent = true;
     }
 

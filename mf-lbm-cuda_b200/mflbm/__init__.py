@@ -190,6 +190,9 @@ def derive_params(control: dict, prec: str, mrt: int = 2):
     return P
 
 
+DEFAULT_CHAIN = "csr"   # what csrc/mflbm.cu does when MFLBM_CHAIN is unset
+
+
 class Solver:
     """One solver handle = one lattice (or x-slab) resident on one GPU."""
 
@@ -203,8 +206,11 @@ class Solver:
         self.nx = int(slab.nx_local) if slab is not None else int(params.nx)
         self.ny, self.nz = int(params.ny), int(params.nz)
         # the library reads MFLBM_CHAIN when a solver is created ("list": the four list kernels of kernels_step.cuh instead of
-        # the brick chain of kernels_chain.cuh; results are identical); recorded here so that callers can report it
-        self.chain = "list" if os.environ.get("MFLBM_CHAIN", "") == "list" else "brick"
+        # the brick chain of kernels_chain.cuh; "csr": the brick chain with per-brick site lists; results are identical);
+        # recorded here so that callers can report it
+        self.chain = os.environ.get("MFLBM_CHAIN", "")
+        if self.chain not in ("list", "brick", "csr"):
+            self.chain = DEFAULT_CHAIN
         rc = self._fn("create")(C.byref(params), C.byref(slab) if slab is not None else None, device, stream, C.byref(self.h))
         self._check(rc)
 

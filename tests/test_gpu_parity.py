@@ -199,13 +199,14 @@ def test_full_size_run_is_deterministic(gpu_lib, prec):
         s.close()
 
 
-def _pair_with_and_without_activity(monkeypatch, make, scan=False):
+def _pair_with_and_without_activity(monkeypatch, make, scan=False, chain="brick"):
     """two solvers over the same input: list gradient chain (every site every step, kernels_step.cuh) / brick chain
     (kernels_chain.cuh: only where an interface can be).  MFLBM_CHAIN is read when a solver is created.  scan: the brick
-    flags come from a scan of phi instead of the collide kernels (MFLBM_ACT_SCAN)"""
+    flags come from a scan of phi instead of the collide kernels (MFLBM_ACT_SCAN).  chain: "brick" = k_chain_normals (node-type
+    tile, sites collected per step), "csr" = k_chain_normals_csr (per-brick site lists built once per geometry, the default)"""
     monkeypatch.setenv("MFLBM_CHAIN", "list")
     plain = make()
-    monkeypatch.setenv("MFLBM_CHAIN", "brick")
+    monkeypatch.setenv("MFLBM_CHAIN", chain)
     if scan:
         monkeypatch.setenv("MFLBM_ACT_SCAN", "1")
     act = make()
@@ -221,14 +222,15 @@ def _assert_states_identical(plain, act, where):
         assert np.array_equal(a[k], b[k], equal_nan=True), (where, k, int((a[k] != b[k]).sum()))
 
 
+@pytest.mark.parametrize("chain", ["brick", "csr"])
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 @pytest.mark.parametrize("name", ["pack_velocity", "tube_pressure", "periodic_drop", "imbibition_plate2", "rect_quirk", "duct_no_geometry"])
-def test_brick_chain_is_bit_identical(gpu_lib, monkeypatch, name, prec):
+def test_brick_chain_is_bit_identical(gpu_lib, monkeypatch, name, prec, chain):
     """kernels_chain.cuh: where every non-solid phi of a 27-brick neighbourhood is +1 (or -1) to within eps the chain
     skips its stencils; elsewhere it evaluates them from a TMA-staged tile.  Every array - phi at the solid-boundary sites and
     the zeroed normals included - must equal the list chain's bit for bit, step loop and graph replay alike."""
     o, ctl, solid = common.make_oracle(name, prec)
-    plain, act = _pair_with_and_without_activity(monkeypatch, lambda: common.solver_from_oracle(o, ctl, prec))
+    plain, act = _pair_with_and_without_activity(monkeypatch, lambda: common.solver_from_oracle(o, ctl, prec), chain=chain)
     _assert_states_identical(plain, act, "initial state")
     for s in (plain, act):
         for n in range(1, 4):
@@ -244,9 +246,10 @@ def test_brick_chain_is_bit_identical(gpu_lib, monkeypatch, name, prec):
     plain.close(); act.close()
 
 
+@pytest.mark.parametrize("chain", ["brick", "csr"])
 @pytest.mark.parametrize("scan", [False, True])
 @pytest.mark.parametrize("prec", ["f64", "f32"])
-def test_brick_chain_follows_a_moving_interface(gpu_lib, monkeypatch, prec, scan):
+def test_brick_chain_follows_a_moving_interface(gpu_lib, monkeypatch, prec, scan, chain):
     """A lattice large enough for most bricks to be quiet (64 x 48 x 128 pack, interface at z = 40), driven hard enough
     (Ca 0.05) for the front to sweep bricks from quiet to active and back: sites whose normals were non-zero must be zeroed
     when their brick falls quiet again, held extrapolated values must be dropped when it wakes up."""
@@ -265,7 +268,7 @@ def test_brick_chain_follows_a_moving_interface(gpu_lib, monkeypatch, prec, scan
         s.init_state(1, ctl["initial_interface_position"], W_in=W)
         return s
 
-    plain, act = _pair_with_and_without_activity(monkeypatch, make, scan=scan)
+    plain, act = _pair_with_and_without_activity(monkeypatch, make, scan=scan, chain=chain)
     _assert_states_identical(plain, act, "initial state")
     nt = 1
     for chunk in (1, 1, 98, 300):
