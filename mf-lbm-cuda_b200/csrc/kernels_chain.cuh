@@ -19,13 +19,17 @@
 //   verdict    k_act_verdict: a brick is quiet when its 27-brick neighbourhood does not hold both kinds.  Bricks that are
 //              not quiet now, or were not quiet in the previous chain (their non-zero normals have to be zeroed once), are
 //              appended to the list of bricks to process.
-//   process    k_chain_normals, one CTA per listed brick: the 16 x 8 x 8 tile of phi around the brick is staged into shared
-//              memory by TMA (cp.async.bulk, one copy per row, mbarrier transaction count), node types next to it; then
+//   process    k_chain_normals_csr (first version: k_chain_normals, MFLBM_CHAIN=brick), persistent CTAs, one listed brick per
+//              iteration: the 16 x 8 x 8 tile of phi around the brick is staged into shared memory by ONE tensor-map TMA request
+//              (mbarrier transaction count); then
 //                 phase 0  phi at the solid-boundary sites of the 10 x 6 x 6 box (:732-755) from the tile, stored to the tile
-//                          and to global memory (neighbouring bricks recompute the same values: identical stores)
+//                          and to global memory (neighbouring bricks recompute the same values: identical stores); the sites
+//                          and the masks of their non-solid neighbours come from a per-brick list built once per geometry
+//                          (first version: collected every step from a staged tile of node types)
 //                 phase 1  interface normal of the thread's own site from the tile (18 LDS, :757-807) and, on fluid-boundary
 //                          sites, the wetting rotation (:809-878) on the values still in registers
-//              k_chain_extrap_cn, same bricks: cn at the solid-boundary sites from the fluid neighbours' cn (:880-906).
+//              k_chain_extrap_cn_flat (first version: k_chain_extrap_cn, one warp per brick), same bricks: cn at the
+//              solid-boundary sites from the fluid neighbours' cn (:880-906), one thread per site.
 //
 // Results are bit-identical to the list chain (tests/test_gpu_parity.py compares every array after every kind of step),
 // with one documented exception that no kernel of the stepping path can observe: phi at the solid-boundary sites of a brick
