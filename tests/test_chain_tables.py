@@ -77,3 +77,15 @@ def test_flat_entry_numbering_is_monotone_and_bisection_finds_the_brick(seed):
         assert 0 <= local < entries[b]
         seen[b] += 1
     assert np.array_equal(seen, np.where(proc, entries, 0))   # every entry of every listed brick exactly once
+
+
+def test_python_emulation_mirrors_the_kernel_header():
+    """the checks above must be about what the CUDA code does: same table shape, same index, same packed counter"""
+    import re
+    from pathlib import Path
+    src = (Path(__file__).resolve().parent.parent / "mf-lbm-cuda_b200" / "csrc" / "kernels_chain.cuh").read_text()
+    assert re.search(r"constexpr int WSUM_N = 7 \* 13;", src)
+    assert re.search(r"return 13 \* __popc\(m & 0x3f\) \+ __popc\(m >> 6\);", src)
+    assert re.search(r"for \(int n = 0; n < n6; n\+\+\) w \+= w_equ<T>\(1\);\s*for \(int n = 0; n < n12; n\+\+\) w \+= w_equ<T>\(7\);", src)
+    assert re.search(r"\(\(unsigned long long\)\(unsigned\)tot << 32\) \| \(unsigned\)__popc\(vote\)", src)
+    assert re.search(r"if \(\(unsigned\)__ldg\(ent_off \+ mid\) <= g\) lo = mid; else hi = mid - 1;", src)
